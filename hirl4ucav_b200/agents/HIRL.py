@@ -1,0 +1,376 @@
+"""Drop-in for ``hirl.agents.HIRL.Agent`` (reference hirl/agents/HIRL.py:148-350) whose update
+runs as ONE persistent fused sm_100a kernel (csrc/update.cuh) behind the C ABI.
+
+What stays on the host, exactly as in the reference: the three RNG streams
+(``random.sample`` for replay indices, buffer.py:45; ``np.random.choice`` for the BC batch,
+HIRL.py:249; ``torch.normal`` for the target-policy noise, HIRL.py:265), the
+actorTrainable / update_count schedule (HIRL.py:291, 327-332) and Adam's bias corrections
+(computed in Python floats like torch.optim.Adam).  Everything numerical is on the GPU; there
+is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from .. import _lib, nets
+from ..utils.buffer import UniformMemory
+
+SOFT_SENTINEL = 100
+_BETA1, _BETA2 = 0.9, 0.999
+
+
+def _adam_scalars(lr: float, step: int):
+    """-step_size and sqrt(bias_correction2) as torch's single-tensor Adam computes them."""
+    bc1 = 1 - _BETA1 ** step
+    bc2 = 1 - _BETA2 ** step
+    return -(lr / bc1), bc2 ** 0.5
+
+
+class Agent(object):
+    _MODE = 0            # 0 HIRL, 1 TD3 (see agents/TD3.py)
+    _GAIN = "relu"
+    _ACT = _lib.ACT_RELU
+
+    def __init__(self, actorLR, criticLR, stateDim, actionDim, full1Dim, full2Dim, tau, gamma, bufferSize, batchSize,
+                 layerNorm, name, expert_states, expert_actions, bc_weight, expert_warm_up, device=None,
+                 max_fused_steps=64):
+        if (stateDim, actionDim, full1Dim, full2Dim) != (13, 4, 256, 512):
+            raise NotImplementedError("the fused kernel is specialised for the reference driver's geometry "
+                                      "13/4/256/512 (hirl/train_all.py:200-203)")
+        if not layerNorm:
+            raise NotImplementedError("layerNorm=False is outside the fused path (train_all.py:204 hard-codes True)")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.tau, self.gamma = tau, gamma
+        self.bufferSize, self.batchSize = int(bufferSize), int(batchSize)
+        self.actorLR, self.criticLR = actorLR, criticLR
+        self.actorTrainable = True
+        self.actionDim = actionDim
+        self.actionNoise = 0.1
+        self.TD3LearningNoise = 0.2
+        self.TD3LearningNoiseClamp = 0.5
+        self.expert_states = expert_states
+        self.expert_actions = expert_actions
+        self.bc_weight = bc_weight
+        self.expert_warm_up = expert_warm_up
+        self.update_count = 0
+        self.loss_lambda = 10000
+        self.target_update_freq = 3
+        self.buffer_upsample = False
+        self.expert_upsample = False
+        self._critic_t = 0      # Adam step counters (torch keeps them in optimizer.state)
+        self._actor_t = 0
+        self._max_steps = int(max_fused_steps)
+        has_expert = expert_states is not None and len(expert_states) > 0
+        if has_expert:
+            self.target_indices = np.where(np.asarray(expert_actions)[:, 3] == 1)[0]
+            print(f"upsample expert data num is {np.size(self.target_indices)}")
+
+        # host parameter containers, created in the reference's order (RNG stream!)
+        mk_a = lambda tag: nets.make_actor(stateDim, actionDim, full1Dim, full2Dim, tag + name, self._GAIN)
+        mk_c = lambda tag: nets.make_critic(stateDim, actionDim, full1Dim, full2Dim, tag + name, self._GAIN)
+        self.actor = mk_a("Actor_")
+        self.targetActor = mk_a("TargetActor_")
+        self.targetActor.load_state_dict(self.actor.state_dict())
+        self.critic = mk_c("Critic_")
+        self.targetCritic = mk_c("TargetCritic_")
+        self.targetCritic.load_state_dict(self.critic.state_dict())
+        self.bc_actor = mk_a("") if self._MODE == 0 else None
+        if self._MODE == 0:
+            print(f"buffer upsample is {self.buffer_upsample}, expert upsample is {self.expert_upsample}, "
+                  f"loss lambda is {self.loss_lambda}")
+
+        n_exp = len(expert_states) if has_expert else 0
+        cfg = _lib.Config(device=self.device.index, batch=self.batchSize, online_capacity=self.bufferSize,
+                          expert_capacity=n_exp + 10, bc_rows=n_exp, max_steps=self._max_steps, activation=self._ACT,
+                          replicas=1, gamma=gamma, tau=tau, noise_clamp=self.TD3LearningNoiseClamp,
+                          loss_lambda=float(self.loss_lambda))
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        _lib.check(self._lib.hirl_agent_create(C.byref(cfg), C.byref(self._h)))
+        self._nets = {_lib.NET_ACTOR: self.actor, _lib.NET_TARGET_ACTOR: self.targetActor, _lib.NET_CRITIC: self.critic,
+                      _lib.NET_TARGET_CRITIC: self.targetCritic}
+        if self.bc_actor is not None:
+            self._nets[_lib.NET_BC_ACTOR] = self.bc_actor
+        self._host_stale = False
+        self.push_parameters()
+        if has_expert:
+            es, ea = _lib.f32c(expert_states), _lib.f32c(expert_actions)
+            _lib.check(self._lib.hirl_bc_table_set(self._h, _lib.ptr(es), _lib.ptr(ea), n_exp))
+
+        self.buffer = UniformMemory(self.bufferSize, self.buffer_upsample)
+        self.buffer._attach(self._h, _lib.BUF_ONLINE)
+        self.expert_buffer = UniformMemory(n_exp + 10, False)
+        self.expert_buffer._attach(self._h, _lib.BUF_EXPERT)
+
+        # pinned staging for the step streams
+        K, B = self._max_steps, self.batchSize
+        pin = torch.cuda.is_available()
+        mk = lambda shape, dt: torch.zeros(shape, dtype=dt, pin_memory=pin)
+        self._st_steps_t = mk((K * _lib.STEP_DTYPE.itemsize,), torch.uint8)
+        self._st_steps = self._st_steps_t.numpy().view(_lib.STEP_DTYPE)
+        self._st_on_t, self._st_ex_t, self._st_bc_t = mk((K, B), torch.int32), mk((K, B), torch.int32), mk((K, B), torch.int32)
+        self._st_on, self._st_ex, self._st_bc = self._st_on_t.numpy(), self._st_ex_t.numpy(), self._st_bc_t.numpy()
+        self._st_out_t = mk((K, _lib.OUT_SCALARS), torch.float32)
+        self._st_out = self._st_out_t.numpy()
+        self._ret = (np.float32(0), np.float32(0), np.float32(0), np.float32(0), 0.0, bc_weight)
+        self.last_draws = {}
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._lib.hirl_agent_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def __str__(self):
+        return f"{type(self).__name__}(fused sm_100a update, batch={self.batchSize}, device={self.device})"
+
+    # ---- parameter traffic ---------------------------------------------------------------
+    def push_parameters(self):
+        """host containers -> device arena (after construction / checkpoint load)."""
+        for net_id, mod in self._nets.items():
+            v = mod.flat()
+            _lib.check(self._lib.hirl_params_import(self._h, 0, net_id, _lib.ptr(v), v.size))
+        self._host_stale = False
+
+    def pull_parameters(self):
+        """device arena -> host containers (before a checkpoint save / state_dict read)."""
+        for net_id, mod in self._nets.items():
+            mod.load_flat(self.export_flat(net_id))
+        self._host_stale = False
+
+    def export_flat(self, net_id) -> np.ndarray:
+        n = _lib.CRITIC_PARAMS if net_id in (_lib.NET_CRITIC, _lib.NET_TARGET_CRITIC) else _lib.ACTOR_PARAMS
+        out = np.empty(n, np.float32)
+        _lib.check(self._lib.hirl_params_export(self._h, 0, net_id, _lib.ptr(out), n))
+        return out
+
+    def export_grads(self, net_id) -> np.ndarray:
+        n = _lib.CRITIC_PARAMS if net_id == _lib.NET_CRITIC else _lib.ACTOR_PARAMS
+        out = np.empty(n, np.float32)
+        _lib.check(self._lib.hirl_grads_export(self._h, 0, net_id, _lib.ptr(out), n))
+        return out
+
+    def export_adam(self, net_id):
+        n = _lib.CRITIC_PARAMS if net_id == _lib.NET_CRITIC else _lib.ACTOR_PARAMS
+        m, v = np.empty(n, np.float32), np.empty(n, np.float32)
+        _lib.check(self._lib.hirl_adam_export(self._h, 0, net_id, _lib.ptr(m), _lib.ptr(v), n))
+        return m, v
+
+    def import_adam(self, net_id, m, v, step):
+        m, v = _lib.f32c(m), _lib.f32c(v)
+        _lib.check(self._lib.hirl_adam_import(self._h, 0, net_id, _lib.ptr(m), _lib.ptr(v), m.size))
+        if net_id == _lib.NET_CRITIC:
+            self._critic_t = int(step)
+        else:
+            self._actor_t = int(step)
+
+    # ---- acting (HIRL.py:192-212) --------------------------------------------------------
+    def _actor_forward(self, state, net_id=_lib.NET_ACTOR) -> np.ndarray:
+        s = _lib.f32c(state).reshape(-1, 13)
+        out = np.empty((s.shape[0], 4), np.float32)
+        _lib.check(self._lib.hirl_act(self._h, 0, net_id, _lib.ptr(s), s.shape[0], _lib.ptr(out)))
+        return out
+
+    def _noisy(self, state, sigma):
+        a = torch.from_numpy(self._actor_forward(state)[0])
+        noise = torch.normal(mean=torch.zeros(self.actionDim), std=torch.ones(self.actionDim) * sigma)
+        return (a + noise).clamp(-1, +1).numpy()
+
+    def chooseAction(self, state):
+        return self._noisy(state, self.actionNoise)
+
+    def chooseActionSmallNoise(self, state):
+        return self._noisy(state, self.actionNoise / 10)
+
+    def chooseActionNoNoise(self, state):
+        return self._actor_forward(state)[0]
+
+    def act_batch(self, states, net="actor") -> np.ndarray:
+        """Noise-free actions for n states in one call (batched acting)."""
+        ids = {"actor": _lib.NET_ACTOR, "targetActor": _lib.NET_TARGET_ACTOR, "bc_actor": _lib.NET_BC_ACTOR}
+        return self._actor_forward(states, ids[net])
+
+    def store(self, *args):
+        self.buffer.store(*args)
+
+    def upsample_expert_data(self, BCActions):
+        return np.where(BCActions[:, 3] == 1)[0]
+
+    # ---- the update ------------------------------------------------------------------------
+    def _draw(self, k, bc_weight_now, expert_num_now, bc_warm_up_weight, forced):
+        """Fills staging slot k with one call's index/noise draws, in the reference's RNG order."""
+        B = self.batchSize
+        st = self._st_steps[k]
+        forced = forced or {}
+        if self.expert_warm_up and expert_num_now:
+            n_ex = int(expert_num_now)
+            idx_on = forced.get("online") if "online" in forced else self.buffer.sample_indices(B - n_ex)
+            idx_ex = forced.get("expert") if "expert" in forced else self.expert_buffer.sample_indices(n_ex)
+        else:
+            n_ex = 0
+            idx_on = forced.get("online") if "online" in forced else self.buffer.sample_indices(B)
+            idx_ex = []
+        n_on = B - n_ex
+        if len(idx_on) != n_on or len(idx_ex) != n_ex:
+            raise ValueError("index streams do not match the batch split")
+        if n_on == 0:
+            # the reference fails on random.sample(memory, 0) + zip(*[]) (HIRL.py:226, buffer.py:47)
+            raise TypeError("expert_num_now == batchSize leaves no online rows (Transition(*zip(*[])) in the reference)")
+        self._st_on[k, :n_on] = idx_on
+        if n_ex:
+            self._st_ex[k, :n_ex] = idx_ex
+        if self._MODE == 0:
+            n_bc = len(self.expert_states)
+            idx_bc = forced["bc"] if "bc" in forced else np.random.choice(n_bc, B, replace=False)
+            self._st_bc[k, :] = idx_bc
+        else:
+            idx_bc = None
+        if "noise" in forced:
+            noise = np.asarray(forced["noise"], np.float32)
+        else:
+            noise = torch.normal(mean=torch.zeros(self.actionDim),
+                                 std=torch.ones(self.actionDim) * self.TD3LearningNoise).numpy()
+        # schedule + Adam scalars
+        do_actor = bool(self.actorTrainable)
+        self._critic_t += 1
+        c_neg, c_bs = _adam_scalars(self.criticLR, self._critic_t)
+        a_neg = a_bs = 0.0
+        do_polyak = False
+        if do_actor:
+            self._actor_t += 1
+            a_neg, a_bs = _adam_scalars(self.actorLR, self._actor_t)
+            self.update_count += 1
+            do_polyak = self.update_count % self.target_update_freq == 0
+        self.actorTrainable = not self.actorTrainable
+        st["n_online"], st["n_expert"], st["do_actor"], st["do_polyak"] = n_on, n_ex, int(do_actor), int(do_polyak)
+        st["bc_weight_now"], st["bc_warm_up"] = bc_weight_now, bc_warm_up_weight
+        st["force_soft_weight"] = forced.get("soft_weight", -1.0)
+        st["noise"] = noise
+        st["critic_neg_step"], st["critic_bc2_sqrt"], st["actor_neg_step"], st["actor_bc2_sqrt"] = c_neg, c_bs, a_neg, a_bs
+        st["mode"] = self._MODE
+        self.last_draws = {"online": list(idx_on), "expert": list(idx_ex), "bc": idx_bc, "noise": noise.copy()}
+        return do_actor
+
+    def _finish(self, k, do_actor, bc_weight_now, bc_warm_up_weight):
+        """Builds the reference's return tuple (HIRL.py:334) from the kernel's scalars."""
+        o = self._st_out[k]
+        critic_loss = np.float32(o[0])
+        if do_actor:
+            if self._MODE == 0:
+                w = bc_weight_now
+                if bc_weight_now == SOFT_SENTINEL:
+                    forced = float(self._st_steps[k]["force_soft_weight"])
+                    mean = np.float32(forced) if forced >= 0 else np.float32(o[6]) / np.float32(self.batchSize)
+                    w = float(mean) + bc_warm_up_weight
+                if w > 1:
+                    w = 1
+                self.bc_weight = w
+                fire = float(o[4]) * self.loss_lambda
+            else:
+                fire = 0.0
+            self._ret = (critic_loss, np.float32(o[1]), np.float32(o[2]), np.float32(o[3]), fire, self.bc_weight)
+        else:
+            self._ret = (critic_loss,) + self._ret[1:]
+        return self._ret
+
+    def _launch(self, k_steps):
+        self.buffer.flush()
+        self.expert_buffer.flush()
+        _lib.check(self._lib.hirl_learn(self._h, k_steps, self._st_steps.ctypes.data_as(C.c_void_p), _lib.ptr(self._st_on),
+                                        _lib.ptr(self._st_ex), _lib.ptr(self._st_bc), _lib.ptr(self._st_out)))
+        self._host_stale = True
+
+    def learn(self, bc_weight_now, expert_num_now, bc_warm_up_weight=0, forced=None):
+        do_actor = self._draw(0, bc_weight_now, expert_num_now, bc_warm_up_weight, forced)
+        self._launch(1)
+        return self._finish(0, do_actor, bc_weight_now, bc_warm_up_weight)
+
+    def learn_many(self, calls, forced=None):
+        """Runs len(calls) consecutive learn() calls in ONE kernel launch.
+
+        ``calls`` is a sequence of (bc_weight_now, expert_num_now, bc_warm_up_weight).  The index and
+        noise streams are pre-drawn in call order, which is legal because they depend only on the
+        buffer lengths, and those do not change between fused calls.  Returns the list of
+        per-call return tuples.
+        """
+        calls = list(calls)
+        out = []
+        for base in range(0, len(calls), self._max_steps):
+            chunk = calls[base:base + self._max_steps]
+            flags = [self._draw(k, c[0], c[1], c[2] if len(c) > 2 else 0, forced[base + k] if forced else None)
+                     for k, c in enumerate(chunk)]
+            self._launch(len(chunk))
+            out += [self._finish(k, flags[k], c[0], c[2] if len(c) > 2 else 0) for k, c in enumerate(chunk)]
+        return out
+
+    # aliases named by the north star
+    select_action = chooseAction
+    train = learn
+
+    # ---- test hooks --------------------------------------------------------------------------
+    def gather(self, idx_online, idx_expert=()):
+        self.buffer.flush()
+        self.expert_buffer.flush()
+        io, ie = _lib.i32c(idx_online), _lib.i32c(idx_expert)
+        out = np.empty((io.size + ie.size, 32), np.float32)
+        _lib.check(self._lib.hirl_gather(self._h, 0, _lib.ptr(io), io.size, _lib.ptr(ie), ie.size, _lib.ptr(out)))
+        return out
+
+    def gather_bc(self, idx_bc):
+        ib = _lib.i32c(idx_bc)
+        s, a = np.empty((ib.size, 13), np.float32), np.empty((ib.size, 4), np.float32)
+        _lib.check(self._lib.hirl_gather_bc(self._h, _lib.ptr(ib), ib.size, _lib.ptr(s), _lib.ptr(a)))
+        return s, a
+
+    def debug_stop_after(self, stage):
+        _lib.check(self._lib.hirl_debug_stop_after(self._h, int(stage)))
+
+    def debug_buffer(self, buffer_id, index=0):
+        n = C.c_size_t()
+        _lib.check(self._lib.hirl_debug_export(self._h, buffer_id, index, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.float32)
+        _lib.check(self._lib.hirl_debug_export(self._h, buffer_id, index, _lib.ptr(out), out.size, None))
+        return out
+
+    # ---- checkpoints (HIRL.py:99-103, 142-146, 336-350) -----------------------------------
+    @staticmethod
+    def _ckpt_path(ajan, model_name, net_name):
+        return model_name + "\\{}".format(ajan) + net_name   # the reference's literal backslash
+
+    def saveCheckpoints(self, ajan, model_name):
+        self.pull_parameters()
+        for mod in (self.critic, self.actor, self.targetCritic, self.targetActor):
+            torch.save(mod.state_dict(), self._ckpt_path(ajan, model_name, mod.name))
+
+    def loadCheckpoints(self, ajan, model_name):
+        if self._host_stale:
+            self.pull_parameters()
+        for mod in (self.critic, self.actor, self.targetCritic, self.targetActor):
+            mod.load_state_dict(torch.load(self._ckpt_path(ajan, model_name, mod.name), map_location="cpu"))
+        self.push_parameters()
+
+    def load_bc_actor(self, ajan, model_name):
+        if self._host_stale:
+            self.pull_parameters()
+        self.bc_actor.load_state_dict(torch.load(self._ckpt_path(ajan, model_name, self.bc_actor.name), map_location="cpu"))
+        self.push_parameters()
+
+    def save_training_state(self, path):
+        """Checkpoint extras the reference does not keep: Adam moments, counters."""
+        am, av = self.export_adam(_lib.NET_ACTOR)
+        cm, cv = self.export_adam(_lib.NET_CRITIC)
+        np.savez(path, actor_m=am, actor_v=av, critic_m=cm, critic_v=cv, actor_t=self._actor_t, critic_t=self._critic_t,
+                 update_count=self.update_count, actorTrainable=self.actorTrainable)
+
+    def load_training_state(self, path):
+        z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+        self.import_adam(_lib.NET_ACTOR, z["actor_m"], z["actor_v"], int(z["actor_t"]))
+        self.import_adam(_lib.NET_CRITIC, z["critic_m"], z["critic_v"], int(z["critic_t"]))
+        self.update_count, self.actorTrainable = int(z["update_count"]), bool(z["actorTrainable"])

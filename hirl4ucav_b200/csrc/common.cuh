@@ -1,0 +1,137 @@
+// common.cuh -- layouts and the kernel context shared by the update kernels and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hirl_b200.h"
+
+namespace hirl {
+
+constexpr int S = HIRL_STATE_DIM;    // 13
+constexpr int A = HIRL_ACTION_DIM;   // 4
+constexpr int SA = S + A;            // 17
+constexpr int H1 = HIRL_H1;          // 256
+constexpr int H2 = HIRL_H2;          // 512
+constexpr int ROW = HIRL_ROW_WORDS;  // 32
+constexpr int BCW = HIRL_BC_WORDS;   // 20
+constexpr float LN_EPS = 1e-5f;      // nn.LayerNorm default (reference HIRL.py:28)
+
+// Internal tower layout (floats).  Every segment starts on a 32-float (128 B) boundary so all
+// vector loads are aligned; W1 is kept TRANSPOSED ([k][n]) because the first layer is evaluated
+// one row per warp with lanes striding over n.  import/export convert from/to state_dict order.
+template <int K0, int NOUT>
+struct TowerLayout {
+    static constexpr int k0 = K0, nout = NOUT;
+    static constexpr int W1T = 0;                  // [K0][H1]
+    static constexpr int B1 = W1T + K0 * H1;       // [H1]
+    static constexpr int G1 = B1 + H1;             // layernorm1.weight
+    static constexpr int BE1 = G1 + H1;            // layernorm1.bias
+    static constexpr int W2 = BE1 + H1;            // [H2][H1] row-major (out,in)
+    static constexpr int B2 = W2 + H2 * H1;
+    static constexpr int G2 = B2 + H2;
+    static constexpr int BE2 = G2 + H2;
+    static constexpr int W3 = BE2 + H2;            // [NOUT][H2]
+    static constexpr int B3 = W3 + NOUT * H2;      // [NOUT] padded to 32
+    static constexpr int SIZE = B3 + 32;
+    static constexpr int SMALL = SIZE - H2 * H1;   // everything but W2 (per-CTA partial grads)
+    // index into the "small" partial-gradient layout for an arena offset outside W2
+    __host__ __device__ static constexpr int small_index(int off) { return off < W2 ? off : off - H2 * H1; }
+};
+using ActorL = TowerLayout<S, A>;    // 138784 floats
+using CriticL = TowerLayout<SA, 1>;  // 138272 floats per tower, two towers per critic
+static_assert(ActorL::SIZE % 32 == 0 && CriticL::SIZE % 32 == 0, "tower arenas must stay 128B aligned");
+
+constexpr int ACTOR_SIZE = ActorL::SIZE;
+constexpr int CRITIC_SIZE = 2 * CriticL::SIZE;
+
+// forward passes of one learn() call (scratch buffers are indexed by these)
+enum Pass { P_TA = 0, P_C1, P_C2, P_TC1, P_TC2, P_A, P_AB, P_BC, P_QP, P_QS, N_PASS };
+// passes that are back-propagated keep xhat1/rstd1 and receive dH1: index into those arrays
+__host__ __device__ constexpr int bwd_slot(int pass) {
+    return pass == P_C1 ? 0 : pass == P_C2 ? 1 : pass == P_A ? 2 : pass == P_AB ? 3 : pass == P_QP ? 4 : -1;
+}
+constexpr int N_BWD = 5;
+constexpr int MAX_SPLIT = 4;   // split-K partial buffers per GEMM output
+// split-K factors are chosen per GEMM group on the host (makespan heuristic); producers and
+// consumers of a buffer read the same entry.
+enum SplitIdx { NS_G1 = 0, NS_G1_ACTOR, NS_G2, NS_G3DX, NS_G5, NS_G6, NS_G7DX, NS_COUNT };
+constexpr int MAX_CTAS = 160;  // >= SM count (148 on B200)
+constexpr int LP_WORDS = 16;   // per-CTA loss/count partial words
+
+// stages of one learn() call, in execution order (hirl_debug_stop_after uses these numbers)
+enum Stage {
+    ST_R0 = 1,  // gather + first layers (TA, C1, C2 [+ A, AB, BC])
+    ST_G1,      // second-layer GEMMs of those passes
+    ST_R1,      // TA head -> a' ; first layers of TC1, TC2 ; [actor heads -> pi, pi_bc, a_bc]
+    ST_G2,      // second-layer GEMMs of TC1, TC2
+    ST_R2,      // TD target, critic heads, loss, backward through head + LayerNorm2
+    ST_G3,      // dW2 and dH1 of both critic towers
+    ST_R3,      // backward through LayerNorm1 / first layer of the critic
+    ST_G4,      // critic Adam
+    ST_R4,      // first layers of Q1(s,pi), Q1(s,a_bc) with the UPDATED critic
+    ST_G5,      // their second-layer GEMMs
+    ST_R5,      // Q heads, soft count, backward of Q1(s,pi) to dz2
+    ST_G6,      // dH1 of Q1(s,pi)
+    ST_R6,      // d pi ; actor heads backward (both branches) to dz2
+    ST_G7,      // actor dW2, dH1 (both branches)
+    ST_R7,      // backward through LayerNorm1 / first layer of the actor
+    ST_G8,      // actor Adam, Polyak, scalars
+    ST_END
+};
+
+// debug buffer ids (hirl_debug_export)
+enum DebugBuf { DB_X = 0, DB_XB, DB_H1, DB_XH1, DB_RS1, DB_Z2, DB_DH1, DB_APRIME, DB_PI, DB_PIB, DB_ABC,
+                DB_Y, DB_Q, DB_TQ, DB_RLQ, DB_SOFTQ, DB_GPI, DB_LP };
+
+struct Scratch {
+    float *X;        // [B][32] gathered replay rows
+    float *XB;       // [B][20] gathered expert (s,a) rows
+    float *H1;       // [N_PASS][B][H1]
+    float *XH1;      // [N_BWD][B][H1]
+    float *RS1;      // [N_BWD][B]
+    float *Z2;       // [N_PASS][nsplit][B][H2]   second-layer pre-activations, later dz2 (split 0)
+    float *DH1;      // [N_BWD][nsplit][B][H1]
+    float *APRIME;   // [B][4]
+    float *PI, *PIB, *ABC, *GPI;  // [B][4]
+    float *Y;        // [B]
+    float *Q;        // [2][B]
+    float *TQ;       // [2][B]
+    float *RLQ, *SOFTQ;           // [B]
+    float *PART_C;   // [MAX_CTAS][2][CriticL::SMALL]
+    float *PART_A;   // [MAX_CTAS][ActorL::SMALL]
+    float *LP;       // [MAX_CTAS][LP_WORDS]
+};
+
+// Everything one replica's update needs.  Passed to the kernel by value (per-replica array in
+// global memory for ensembles).
+struct AgentCtx {
+    // parameters (internal layout), gradients and Adam moments
+    float *actor, *tactor, *critic, *tcritic, *bc;
+    float *g_actor, *g_critic;
+    float *m_actor, *v_actor, *m_critic, *v_critic;
+    // replay tables
+    const float *online;   // [online_capacity][32]
+    const float *expert;   // [expert_capacity][32]
+    const float *bctab;    // [bc_rows][20]
+    Scratch sc;
+    // per-launch step streams
+    const hirl_step_t *steps;
+    const int32_t *idx_online, *idx_expert, *idx_bc;  // [k][B]
+    float *out_scalars;    // [k][8]
+    float *carry;          // [8] scalars carried between calls (stale-value semantics, HIRL.py:334)
+    int B;
+    int zsplit;            // allocated split-K slots per Z2 / DH1 buffer (max of ns[])
+    int ns[NS_COUNT];      // split-K factor per GEMM group
+    int activation;
+    float gamma, tau, noise_clamp, loss_lambda;
+};
+
+struct LaunchCtx {
+    AgentCtx agent;        // single-agent launch: the context travels as a kernel parameter
+    unsigned *bar_count;   // grid barrier arrival counter
+    unsigned *bar_gen;     // grid barrier generation
+    int k_steps;
+    int stop_after;        // debug: leave after this stage of step 0 (0 = never)
+};
+
+}  // namespace hirl

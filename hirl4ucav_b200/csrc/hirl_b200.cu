@@ -1,0 +1,645 @@
+// hirl_b200.cu -- kernels' entry points and the C ABI of libhirl_b200.so (include/hirl_b200.h).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "env.cuh"
+#include "update.cuh"
+
+using namespace hirl;
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+// The persistent fused update: k_steps learn() calls, one launch, team = whole grid.
+__global__ void __launch_bounds__(THREADS, 1) hirl_update_kernel(const __grid_constant__ LaunchCtx L) {
+    extern __shared__ float4 smem4[];
+    float *smem = reinterpret_cast<float *>(smem4);
+    const AgentCtx &ctx = L.agent;
+    Team tm;
+    tm.rank = blockIdx.x; tm.size = gridDim.x; tm.count = L.bar_count; tm.gen_ptr = L.bar_gen;
+    tm.gen = ld_acquire_u32(L.bar_gen);
+    __syncthreads();
+    for (int step = 0; step < L.k_steps; ++step)
+        if (learn_step(ctx, step, tm, smem, step == 0 ? L.stop_after : 0)) return;
+}
+
+// buffer.py:38-48 + HIRL.py:229-233 as a standalone op (the fused kernel gathers in stage R0)
+__global__ void gather_kernel(const float *__restrict__ online, const float *__restrict__ expert, const int32_t *__restrict__ idx_on,
+                              int n_on, const int32_t *__restrict__ idx_ex, int n_ex, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < n_on + n_ex; b += gridDim.x * wpb) {
+        const float *src = b < n_on ? online + (size_t)idx_on[b] * ROW : expert + (size_t)idx_ex[b - n_on] * ROW;
+        out[(size_t)b * ROW + lane] = __ldg(src + lane);
+    }
+}
+__global__ void gather_bc_kernel(const float *__restrict__ tab, const int32_t *__restrict__ idx, int n, float *__restrict__ out_s,
+                                 float *__restrict__ out_a) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < n; b += gridDim.x * wpb) {
+        const float *src = tab + (size_t)idx[b] * BCW;
+        if (lane < S) out_s[(size_t)b * S + lane] = __ldg(src + lane);
+        else if (lane < SA) out_a[(size_t)b * A + lane - S] = __ldg(src + lane);
+    }
+}
+
+// HIRL.py:192-212: actor forward for n rows, one CTA per row (latency path; no noise here)
+__global__ void __launch_bounds__(THREADS) act_kernel(const float *net, const float *__restrict__ states, int n, float *__restrict__ actions,
+                                                       float slope) {
+    __shared__ __align__(16) float h1[H1];
+    __shared__ __align__(16) float z2[H2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        if (warp == 0) {
+            const float w = lane < S ? states[(size_t)b * S + lane] : 0.f;
+            float x[S];
+#pragma unroll
+            for (int k = 0; k < S; ++k) x[k] = __shfl_sync(0xffffffffu, w, k);
+            l1_row<ActorL>(net, x, slope, lane, h1, nullptr, nullptr);
+        }
+        __syncthreads();
+        float hreg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hreg[j] = h1[lane * 8 + j];
+        for (int i = 0; i < H2 / WARPS; ++i) {
+            const int col = warp * (H2 / WARPS) + i;
+            const float *wr = net + ActorL::W2 + (size_t)col * H1 + lane * 8;
+            const float4 w0 = ld4(wr), w1 = ld4(wr + 4);
+            float p = hreg[0] * w0.x;
+            p = fmaf(hreg[1], w0.y, p); p = fmaf(hreg[2], w0.z, p); p = fmaf(hreg[3], w0.w, p);
+            p = fmaf(hreg[4], w1.x, p); p = fmaf(hreg[5], w1.y, p); p = fmaf(hreg[6], w1.z, p); p = fmaf(hreg[7], w1.w, p);
+            p = warp_sum(p);
+            if (lane == 0) z2[col] = p + net[ActorL::B2 + col];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            float z[16], xh[16], h[16], rstd, out[A];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 t = ld4(z2 + 4 * lane + 128 * j);
+                z[4 * j] = t.x; z[4 * j + 1] = t.y; z[4 * j + 2] = t.z; z[4 * j + 3] = t.w;
+            }
+            head_forward<ActorL>(net, z, slope, lane, xh, h, rstd, out);
+            if (lane < A) actions[(size_t)b * A + lane] = tanhf(out[lane]);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return fail(HIRL_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct hirl_agent {
+    hirl_config_t cfg;
+    int sm_count = 0, grid = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void *> allocs;
+    AgentCtx h_ctx;            // replica 0 (ensembles: array, later)
+    unsigned *d_bar = nullptr;
+    float *online = nullptr, *expert = nullptr, *bctab = nullptr;
+    hirl_step_t *d_steps = nullptr;
+    int32_t *d_ion = nullptr, *d_iex = nullptr, *d_ibc = nullptr;
+    float *d_out = nullptr;
+    int stop_after = 0, last_launches = 0;
+    size_t scratch_elems[32];
+};
+
+template <class T>
+static int dev_alloc(hirl_agent *h, T **p, size_t n, bool zero = true) {
+    void *q = nullptr;
+    CU(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    if (zero) CU(cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    h->allocs.push_back(q);
+    *p = static_cast<T *>(q);
+    return 0;
+}
+
+// ---- state_dict <-> internal layout --------------------------------------------------------
+// state_dict order of one tower: W1 (H1,K0) row-major, b1, g1, be1, W2 (H2,H1), b2, g2, be2, W3 (NOUT,H2), b3
+template <class L>
+static void tower_to_internal(const float *src, float *dst) {
+    std::fill(dst, dst + L::SIZE, 0.f);
+    const float *p = src;
+    for (int n = 0; n < H1; ++n)
+        for (int k = 0; k < L::k0; ++k) dst[L::W1T + k * H1 + n] = p[n * L::k0 + k];
+    p += H1 * L::k0;
+    std::memcpy(dst + L::B1, p, H1 * 4); p += H1;
+    std::memcpy(dst + L::G1, p, H1 * 4); p += H1;
+    std::memcpy(dst + L::BE1, p, H1 * 4); p += H1;
+    std::memcpy(dst + L::W2, p, (size_t)H2 * H1 * 4); p += H2 * H1;
+    std::memcpy(dst + L::B2, p, H2 * 4); p += H2;
+    std::memcpy(dst + L::G2, p, H2 * 4); p += H2;
+    std::memcpy(dst + L::BE2, p, H2 * 4); p += H2;
+    std::memcpy(dst + L::W3, p, (size_t)L::nout * H2 * 4); p += L::nout * H2;
+    std::memcpy(dst + L::B3, p, L::nout * 4);
+}
+template <class L>
+static void tower_from_internal(const float *src, float *dst) {
+    float *p = dst;
+    for (int n = 0; n < H1; ++n)
+        for (int k = 0; k < L::k0; ++k) p[n * L::k0 + k] = src[L::W1T + k * H1 + n];
+    p += H1 * L::k0;
+    std::memcpy(p, src + L::B1, H1 * 4); p += H1;
+    std::memcpy(p, src + L::G1, H1 * 4); p += H1;
+    std::memcpy(p, src + L::BE1, H1 * 4); p += H1;
+    std::memcpy(p, src + L::W2, (size_t)H2 * H1 * 4); p += H2 * H1;
+    std::memcpy(p, src + L::B2, H2 * 4); p += H2;
+    std::memcpy(p, src + L::G2, H2 * 4); p += H2;
+    std::memcpy(p, src + L::BE2, H2 * 4); p += H2;
+    std::memcpy(p, src + L::W3, (size_t)L::nout * H2 * 4); p += L::nout * H2;
+    std::memcpy(p, src + L::B3, L::nout * 4);
+}
+template <class L>
+constexpr size_t tower_flat() { return (size_t)H1 * L::k0 + 3 * H1 + (size_t)H2 * H1 + 3 * H2 + (size_t)L::nout * H2 + L::nout; }
+static_assert(tower_flat<ActorL>() == HIRL_ACTOR_PARAMS, "actor flat size");
+static_assert(2 * tower_flat<CriticL>() == HIRL_CRITIC_PARAMS, "critic flat size");
+
+static bool is_critic(int net) { return net == HIRL_NET_CRITIC || net == HIRL_NET_TARGET_CRITIC; }
+static int net_ptr(hirl_agent *h, int net, int kind /*0 w,1 g,2 m,3 v*/, float **out) {
+    AgentCtx &c = h->h_ctx;
+    float *p = nullptr;
+    if (kind == 0) p = net == HIRL_NET_ACTOR ? c.actor : net == HIRL_NET_TARGET_ACTOR ? c.tactor : net == HIRL_NET_CRITIC ? c.critic
+                   : net == HIRL_NET_TARGET_CRITIC ? c.tcritic : net == HIRL_NET_BC_ACTOR ? c.bc : nullptr;
+    else if (net == HIRL_NET_ACTOR) p = kind == 1 ? c.g_actor : kind == 2 ? c.m_actor : c.v_actor;
+    else if (net == HIRL_NET_CRITIC) p = kind == 1 ? c.g_critic : kind == 2 ? c.m_critic : c.v_critic;
+    if (!p) return fail(HIRL_E_INVALID, "bad network selector");
+    *out = p;
+    return 0;
+}
+static int flat_import(hirl_agent *h, int net, int kind, const float *src, size_t n) {
+    float *d;
+    if (int rc = net_ptr(h, net, kind, &d)) return rc;
+    const bool cr = is_critic(net);
+    if (n != (cr ? (size_t)HIRL_CRITIC_PARAMS : (size_t)HIRL_ACTOR_PARAMS)) return fail(HIRL_E_INVALID, "flat parameter vector has the wrong length");
+    std::vector<float> tmp(cr ? CRITIC_SIZE : ACTOR_SIZE);
+    if (cr) {
+        tower_to_internal<CriticL>(src, tmp.data());
+        tower_to_internal<CriticL>(src + tower_flat<CriticL>(), tmp.data() + CriticL::SIZE);
+    } else tower_to_internal<ActorL>(src, tmp.data());
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(d, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+static int flat_export(hirl_agent *h, int net, int kind, float *dst, size_t n) {
+    float *d;
+    if (int rc = net_ptr(h, net, kind, &d)) return rc;
+    const bool cr = is_critic(net);
+    if (n != (cr ? (size_t)HIRL_CRITIC_PARAMS : (size_t)HIRL_ACTOR_PARAMS)) return fail(HIRL_E_INVALID, "flat parameter vector has the wrong length");
+    std::vector<float> tmp(cr ? CRITIC_SIZE : ACTOR_SIZE);
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(tmp.data(), d, tmp.size() * 4, cudaMemcpyDeviceToHost));
+    if (cr) {
+        tower_from_internal<CriticL>(tmp.data(), dst);
+        tower_from_internal<CriticL>(tmp.data() + CriticL::SIZE, dst + tower_flat<CriticL>());
+    } else tower_from_internal<ActorL>(tmp.data(), dst);
+    return 0;
+}
+
+// split-K choice.  A stage is a list of (tiles, cost) jobs handed out round-robin exactly as
+// run_gemm_jobs does; pick the split of the splittable jobs that minimises the busiest CTA.
+struct JobShape { int tiles; double cost; bool splittable; };
+static double stage_makespan(const std::vector<JobShape> &jobs, int ns, int ctas) {
+    std::vector<double> load(ctas, 0.0);
+    int t = 0;
+    for (const JobShape &j : jobs) {
+        const int n = j.splittable ? j.tiles * ns : j.tiles;
+        const double c = j.splittable ? j.cost / ns + 1.0 : j.cost + 1.0;  // +1: per-tile prologue/epilogue
+        for (int i = 0; i < n; ++i, ++t) load[t % ctas] += c;
+    }
+    return *std::max_element(load.begin(), load.end());
+}
+static int pick_split(const std::vector<JobShape> &jobs, int ctas, int forced) {
+    if (forced > 0) return std::min(forced, MAX_SPLIT);
+    int best = 1;
+    double best_t = 1e300;
+    for (int ns = 1; ns <= MAX_SPLIT; ns *= 2) {
+        const double t = stage_makespan(jobs, ns, ctas) * (1.0 + 0.05 * (ns - 1));  // partial-sum traffic penalty
+        if (t < best_t - 1e-9) { best_t = t; best = ns; }
+    }
+    return best;
+}
+
+extern "C" {
+
+int hirl_abi_version(void) { return HIRL_ABI_VERSION; }
+const char *hirl_last_error(void) { return g_err.c_str(); }
+
+int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
+    if (!cfg || !out) return fail(HIRL_E_INVALID, "null argument");
+    if (cfg->batch < 1 || cfg->online_capacity < 1 || cfg->expert_capacity < 1 || cfg->bc_rows < 0 || cfg->max_steps < 1)
+        return fail(HIRL_E_INVALID, "batch/capacities/max_steps must be positive");
+    if (cfg->replicas != 1) return fail(HIRL_E_UNSUPPORTED, "replicas != 1: use the ensemble entry points");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(HIRL_E_INVALID, "no such CUDA device");
+    CU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(HIRL_E_UNSUPPORTED, "libhirl_b200 is built for sm_100a (B200) only");
+    hirl_agent *h = new hirl_agent();
+    h->cfg = *cfg;
+    h->sm_count = prop.multiProcessorCount;
+    CU(cudaFuncSetAttribute(hirl_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hirl_update_kernel, THREADS, SMEM_BYTES));
+    if (occ < 1) return fail(HIRL_E_CUDA, "update kernel does not fit on an SM");
+    h->grid = std::min(h->sm_count, MAX_CTAS) & ~1;  // even: the row stages split CTAs in two groups
+    if (const char *g = getenv("HIRL_GRID")) h->grid = std::max(2, std::min(h->grid, atoi(g)) & ~1);
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+    AgentCtx &c = h->h_ctx;
+    std::memset(&c, 0, sizeof(c));
+    const size_t B = cfg->batch;
+    c.B = cfg->batch;
+    c.activation = cfg->activation;
+    c.gamma = cfg->gamma; c.tau = cfg->tau; c.noise_clamp = cfg->noise_clamp; c.loss_lambda = cfg->loss_lambda;
+    // split-K factors (unit = one 64x64 output tile over the layer's full K)
+    const int forced = getenv("HIRL_NSPLIT") ? atoi(getenv("HIRL_NSPLIT")) : 0;
+    const int tm = (cfg->batch + 63) / 64;
+    const double kb = std::ceil(cfg->batch / 16.0);                  // k-tiles of a batch-long reduction
+    const JobShape fwd{tm * 8, 16.0, true}, dx{tm * 4, 32.0, true};  // K=256 / K=512 in 16-wide k-tiles
+    c.ns[NS_G1] = pick_split({fwd, fwd, fwd}, h->grid, forced);
+    c.ns[NS_G1_ACTOR] = pick_split({fwd, fwd, fwd, fwd, fwd, fwd}, h->grid, forced);
+    c.ns[NS_G2] = pick_split({fwd, fwd}, h->grid, forced);
+    c.ns[NS_G3DX] = pick_split({{32, kb, false}, {32, kb, false}, dx, dx}, h->grid, forced);
+    c.ns[NS_G5] = pick_split({fwd, fwd}, h->grid, forced);
+    c.ns[NS_G6] = pick_split({dx}, h->grid, forced);
+    c.ns[NS_G7DX] = pick_split({{32, 2 * kb, false}, dx, dx}, h->grid, forced);
+    c.zsplit = 1;
+    for (int i = 0; i < NS_COUNT; ++i) c.zsplit = std::max(c.zsplit, c.ns[i]);
+
+    int rc = 0;
+    float *arena = nullptr;
+    const size_t arena_n = 6 * (size_t)ACTOR_SIZE + 5 * (size_t)CRITIC_SIZE;
+    if ((rc = dev_alloc(h, &arena, arena_n))) return rc;
+    float *p = arena;
+    c.actor = p; p += ACTOR_SIZE; c.tactor = p; p += ACTOR_SIZE; c.bc = p; p += ACTOR_SIZE;
+    c.g_actor = p; p += ACTOR_SIZE; c.m_actor = p; p += ACTOR_SIZE; c.v_actor = p; p += ACTOR_SIZE;
+    c.critic = p; p += CRITIC_SIZE; c.tcritic = p; p += CRITIC_SIZE;
+    c.g_critic = p; p += CRITIC_SIZE; c.m_critic = p; p += CRITIC_SIZE; c.v_critic = p; p += CRITIC_SIZE;
+    if ((rc = dev_alloc(h, &h->online, (size_t)cfg->online_capacity * ROW))) return rc;
+    if ((rc = dev_alloc(h, &h->expert, (size_t)cfg->expert_capacity * ROW))) return rc;
+    if ((rc = dev_alloc(h, &h->bctab, (size_t)std::max(cfg->bc_rows, 1) * BCW))) return rc;
+    c.online = h->online; c.expert = h->expert; c.bctab = h->bctab;
+    Scratch &s = c.sc;
+    size_t *se = h->scratch_elems;
+#define SCR(field, id, n)                                        \
+    if ((rc = dev_alloc(h, &s.field, (n)))) return rc;            \
+    se[id] = (n);
+    SCR(X, DB_X, B * ROW) SCR(XB, DB_XB, B * BCW)
+    SCR(H1, DB_H1, (size_t)N_PASS * B * H1) SCR(XH1, DB_XH1, (size_t)N_BWD * B * H1) SCR(RS1, DB_RS1, (size_t)N_BWD * B)
+    SCR(Z2, DB_Z2, (size_t)N_PASS * c.zsplit * B * H2) SCR(DH1, DB_DH1, (size_t)N_BWD * c.zsplit * B * H1)
+    SCR(APRIME, DB_APRIME, B * A) SCR(PI, DB_PI, B * A) SCR(PIB, DB_PIB, B * A) SCR(ABC, DB_ABC, B * A) SCR(GPI, DB_GPI, B * A)
+    SCR(Y, DB_Y, B) SCR(Q, DB_Q, 2 * B) SCR(TQ, DB_TQ, 2 * B) SCR(RLQ, DB_RLQ, B) SCR(SOFTQ, DB_SOFTQ, B)
+    SCR(LP, DB_LP, (size_t)MAX_CTAS * LP_WORDS)
+#undef SCR
+    if ((rc = dev_alloc(h, &s.PART_C, (size_t)MAX_CTAS * 2 * CriticL::SMALL))) return rc;
+    if ((rc = dev_alloc(h, &s.PART_A, (size_t)MAX_CTAS * ActorL::SMALL))) return rc;
+    const size_t K = cfg->max_steps;
+    if ((rc = dev_alloc(h, &h->d_steps, K))) return rc;
+    if ((rc = dev_alloc(h, &h->d_ion, K * B))) return rc;
+    if ((rc = dev_alloc(h, &h->d_iex, K * B))) return rc;
+    if ((rc = dev_alloc(h, &h->d_ibc, K * B))) return rc;
+    if ((rc = dev_alloc(h, &h->d_out, K * HIRL_OUT_SCALARS))) return rc;
+    if ((rc = dev_alloc(h, &c.carry, 8))) return rc;
+    if ((rc = dev_alloc(h, &h->d_bar, 64))) return rc;
+    *out = h;
+    return 0;
+}
+
+int hirl_agent_destroy(hirl_agent_t *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    for (void *p : h->allocs) cudaFree(p);
+    delete h;
+    return 0;
+}
+int hirl_agent_sm_count(hirl_agent_t *h) { return h ? h->grid : 0; }
+
+int hirl_params_import(hirl_agent_t *h, int replica, int net, const float *src, size_t n) {
+    if (!h || !src || replica != 0) return fail(HIRL_E_INVALID, "bad handle/replica");
+    return flat_import(h, net, 0, src, n);
+}
+int hirl_params_export(hirl_agent_t *h, int replica, int net, float *dst, size_t n) {
+    if (!h || !dst || replica != 0) return fail(HIRL_E_INVALID, "bad handle/replica");
+    return flat_export(h, net, 0, dst, n);
+}
+int hirl_adam_import(hirl_agent_t *h, int replica, int net, const float *m, const float *v, size_t n) {
+    if (!h || !m || !v || replica != 0) return fail(HIRL_E_INVALID, "bad handle/replica");
+    if (int rc = flat_import(h, net, 2, m, n)) return rc;
+    return flat_import(h, net, 3, v, n);
+}
+int hirl_adam_export(hirl_agent_t *h, int replica, int net, float *m, float *v, size_t n) {
+    if (!h || !m || !v || replica != 0) return fail(HIRL_E_INVALID, "bad handle/replica");
+    if (int rc = flat_export(h, net, 2, m, n)) return rc;
+    return flat_export(h, net, 3, v, n);
+}
+int hirl_grads_export(hirl_agent_t *h, int replica, int net, float *dst, size_t n) {
+    if (!h || !dst || replica != 0) return fail(HIRL_E_INVALID, "bad handle/replica");
+    return flat_export(h, net, 1, dst, n);
+}
+
+int hirl_store_rows(hirl_agent_t *h, int replica, int buffer, int first_slot, int n_rows, const float *rows32) {
+    if (!h || !rows32 || replica != 0) return fail(HIRL_E_INVALID, "bad handle/replica");
+    const int cap = buffer == HIRL_BUF_ONLINE ? h->cfg.online_capacity : buffer == HIRL_BUF_EXPERT ? h->cfg.expert_capacity : -1;
+    if (cap < 0) return fail(HIRL_E_INVALID, "bad buffer selector");
+    if (n_rows < 0 || n_rows > cap || first_slot < 0 || first_slot >= cap) return fail(HIRL_E_INVALID, "row range outside the ring");
+    float *base = buffer == HIRL_BUF_ONLINE ? h->online : h->expert;
+    CU(cudaSetDevice(h->cfg.device));
+    const int first = std::min(n_rows, cap - first_slot);
+    CU(cudaMemcpyAsync(base + (size_t)first_slot * ROW, rows32, (size_t)first * ROW * 4, cudaMemcpyHostToDevice, h->stream));
+    if (n_rows > first) CU(cudaMemcpyAsync(base, rows32 + (size_t)first * ROW, (size_t)(n_rows - first) * ROW * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int hirl_bc_table_set(hirl_agent_t *h, const float *states13, const float *actions4, int n_rows) {
+    if (!h || !states13 || !actions4) return fail(HIRL_E_INVALID, "null argument");
+    if (n_rows != h->cfg.bc_rows) return fail(HIRL_E_INVALID, "expert table size differs from cfg.bc_rows");
+    std::vector<float> tmp((size_t)n_rows * BCW, 0.f);
+    for (int i = 0; i < n_rows; ++i) {
+        std::memcpy(&tmp[(size_t)i * BCW], states13 + (size_t)i * S, S * 4);
+        std::memcpy(&tmp[(size_t)i * BCW + S], actions4 + (size_t)i * A, A * 4);
+    }
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpy(h->bctab, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int hirl_gather(hirl_agent_t *h, int replica, const int32_t *idx_online, int n_online, const int32_t *idx_expert, int n_expert,
+                float *out_rows32) {
+    if (!h || !out_rows32 || replica != 0 || n_online < 0 || n_expert < 0) return fail(HIRL_E_INVALID, "bad argument");
+    const int n = n_online + n_expert;
+    if (n == 0) return 0;
+    for (int i = 0; i < n_online; ++i)
+        if (idx_online[i] < 0 || idx_online[i] >= h->cfg.online_capacity) return fail(HIRL_E_INVALID, "online index out of range");
+    for (int i = 0; i < n_expert; ++i)
+        if (idx_expert[i] < 0 || idx_expert[i] >= h->cfg.expert_capacity) return fail(HIRL_E_INVALID, "expert index out of range");
+    CU(cudaSetDevice(h->cfg.device));
+    int32_t *d_idx = nullptr;
+    float *d_out = nullptr;
+    CU(cudaMalloc(&d_idx, (size_t)n * 4));
+    CU(cudaMalloc(&d_out, (size_t)n * ROW * 4));
+    if (n_online) CU(cudaMemcpyAsync(d_idx, idx_online, (size_t)n_online * 4, cudaMemcpyHostToDevice, h->stream));
+    if (n_expert) CU(cudaMemcpyAsync(d_idx + n_online, idx_expert, (size_t)n_expert * 4, cudaMemcpyHostToDevice, h->stream));
+    gather_kernel<<<std::min((n + 7) / 8, 4 * h->sm_count), 256, 0, h->stream>>>(h->online, h->expert, d_idx, n_online, d_idx + n_online, n_expert, d_out);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_rows32, d_out, (size_t)n * ROW * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d_idx);
+    cudaFree(d_out);
+    return 0;
+}
+
+int hirl_gather_bc(hirl_agent_t *h, const int32_t *idx_bc, int n, float *out_states13, float *out_actions4) {
+    if (!h || !idx_bc || !out_states13 || !out_actions4 || n < 0) return fail(HIRL_E_INVALID, "bad argument");
+    if (n == 0) return 0;
+    for (int i = 0; i < n; ++i)
+        if (idx_bc[i] < 0 || idx_bc[i] >= h->cfg.bc_rows) return fail(HIRL_E_INVALID, "expert-table index out of range");
+    CU(cudaSetDevice(h->cfg.device));
+    int32_t *d_idx = nullptr;
+    float *d_s = nullptr, *d_a = nullptr;
+    CU(cudaMalloc(&d_idx, (size_t)n * 4));
+    CU(cudaMalloc(&d_s, (size_t)n * S * 4));
+    CU(cudaMalloc(&d_a, (size_t)n * A * 4));
+    CU(cudaMemcpyAsync(d_idx, idx_bc, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    gather_bc_kernel<<<std::min((n + 7) / 8, 4 * h->sm_count), 256, 0, h->stream>>>(h->bctab, d_idx, n, d_s, d_a);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_states13, d_s, (size_t)n * S * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out_actions4, d_a, (size_t)n * A * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d_idx); cudaFree(d_s); cudaFree(d_a);
+    return 0;
+}
+
+static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_dev, const int32_t *ion, const int32_t *iex, const int32_t *ibc,
+                         float *out_dev, cudaStream_t stream) {
+    LaunchCtx L;
+    L.agent = h->h_ctx;
+    AgentCtx &c = L.agent;
+    c.steps = steps_dev; c.idx_online = ion; c.idx_expert = iex; c.idx_bc = ibc; c.out_scalars = out_dev;
+    L.bar_count = h->d_bar; L.bar_gen = h->d_bar + 32; L.k_steps = k_steps; L.stop_after = h->stop_after;
+    void *args[] = {&L};
+    CU(cudaLaunchCooperativeKernel((void *)hirl_update_kernel, dim3(h->grid), dim3(THREADS), args, SMEM_BYTES, stream));
+    h->last_launches = 1;
+    return 0;
+}
+
+static int check_steps(hirl_agent *h, int k_steps, const hirl_step_t *steps) {
+    if (k_steps < 1 || k_steps > h->cfg.max_steps) return fail(HIRL_E_INVALID, "k_steps outside [1, cfg.max_steps]");
+    for (int k = 0; k < k_steps; ++k) {
+        const hirl_step_t &s = steps[k];
+        if (s.n_online < 0 || s.n_expert < 0 || s.n_online + s.n_expert != h->cfg.batch)
+            return fail(HIRL_E_INVALID, "n_online + n_expert must equal the batch size");
+        if (s.mode < 0 || s.mode > 1) return fail(HIRL_E_INVALID, "bad step mode");
+        if (s.mode == 0 && s.do_actor && h->cfg.bc_rows < h->cfg.batch) return fail(HIRL_E_INVALID, "expert table smaller than the batch (np.random.choice without replacement)");
+    }
+    return 0;
+}
+
+int hirl_learn(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, const int32_t *idx_online, const int32_t *idx_expert,
+               const int32_t *idx_bc, float *out_scalars) {
+    if (!h || !steps || !idx_online || !out_scalars) return fail(HIRL_E_INVALID, "null argument");
+    if (int rc = check_steps(h, k_steps, steps)) return rc;
+    const size_t B = h->cfg.batch, K = k_steps;
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(h->d_steps, steps, K * sizeof(hirl_step_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_ion, idx_online, K * B * 4, cudaMemcpyHostToDevice, h->stream));
+    if (idx_expert) CU(cudaMemcpyAsync(h->d_iex, idx_expert, K * B * 4, cudaMemcpyHostToDevice, h->stream));
+    if (idx_bc) CU(cudaMemcpyAsync(h->d_ibc, idx_bc, K * B * 4, cudaMemcpyHostToDevice, h->stream));
+    if (int rc = launch_update(h, k_steps, h->d_steps, h->d_ion, h->d_iex, h->d_ibc, h->d_out, h->stream)) return rc;
+    CU(cudaMemcpyAsync(out_scalars, h->d_out, K * HIRL_OUT_SCALARS * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int hirl_learn_dev(hirl_agent_t *h, int k_steps, const hirl_step_t *steps_dev, const int32_t *idx_online_dev, const int32_t *idx_expert_dev,
+                   const int32_t *idx_bc_dev, float *out_scalars_dev, void *stream) {
+    if (!h || !steps_dev || !idx_online_dev || !out_scalars_dev) return fail(HIRL_E_INVALID, "null argument");
+    if (k_steps < 1) return fail(HIRL_E_INVALID, "k_steps must be >= 1");
+    CU(cudaSetDevice(h->cfg.device));
+    return launch_update(h, k_steps, steps_dev, idx_online_dev, idx_expert_dev ? idx_expert_dev : h->d_iex, idx_bc_dev ? idx_bc_dev : h->d_ibc,
+                         out_scalars_dev, (cudaStream_t)stream);
+}
+int hirl_last_launch_count(hirl_agent_t *h) { return h ? h->last_launches : 0; }
+
+int hirl_act(hirl_agent_t *h, int replica, int net, const float *states13, int n, float *actions4) {
+    if (!h || !states13 || !actions4 || replica != 0 || n < 0) return fail(HIRL_E_INVALID, "bad argument");
+    if (is_critic(net)) return fail(HIRL_E_INVALID, "hirl_act needs an actor network");
+    if (n == 0) return 0;
+    float *w;
+    if (int rc = net_ptr(h, net, 0, &w)) return rc;
+    CU(cudaSetDevice(h->cfg.device));
+    float *d_s = nullptr, *d_a = nullptr;
+    CU(cudaMalloc(&d_s, (size_t)n * S * 4));
+    CU(cudaMalloc(&d_a, (size_t)n * A * 4));
+    CU(cudaMemcpyAsync(d_s, states13, (size_t)n * S * 4, cudaMemcpyHostToDevice, h->stream));
+    act_kernel<<<std::min(n, 8 * h->sm_count), THREADS, 0, h->stream>>>(w, d_s, n, d_a, h->cfg.activation == HIRL_ACT_LEAKY_RELU ? 0.01f : 0.f);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(actions4, d_a, (size_t)n * A * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d_s); cudaFree(d_a);
+    return 0;
+}
+
+int hirl_debug_stop_after(hirl_agent_t *h, int stage) {
+    if (!h || stage < 0 || stage >= ST_END) return fail(HIRL_E_INVALID, "bad stage");
+    h->stop_after = stage;
+    return 0;
+}
+int hirl_debug_export(hirl_agent_t *h, int buffer_id, int pass, float *dst, size_t n, size_t *n_out) {
+    if (!h) return fail(HIRL_E_INVALID, "null handle");
+    const Scratch &s = h->h_ctx.sc;
+    const size_t B = h->cfg.batch, zs = h->h_ctx.zsplit;
+    const float *src = nullptr;
+    size_t cnt = 0;
+    switch (buffer_id) {
+        case DB_X: src = s.X; cnt = B * ROW; break;
+        case DB_XB: src = s.XB; cnt = B * BCW; break;
+        case DB_H1: src = s.H1 + (size_t)pass * B * H1; cnt = B * H1; break;
+        case DB_XH1: src = s.XH1 + (size_t)pass * B * H1; cnt = B * H1; break;
+        case DB_RS1: src = s.RS1 + (size_t)pass * B; cnt = B; break;
+        case DB_Z2: src = s.Z2 + (size_t)pass * zs * B * H2; cnt = zs * B * H2; break;
+        case DB_DH1: src = s.DH1 + (size_t)pass * zs * B * H1; cnt = zs * B * H1; break;
+        case DB_APRIME: src = s.APRIME; cnt = B * A; break;
+        case DB_PI: src = s.PI; cnt = B * A; break;
+        case DB_PIB: src = s.PIB; cnt = B * A; break;
+        case DB_ABC: src = s.ABC; cnt = B * A; break;
+        case DB_GPI: src = s.GPI; cnt = B * A; break;
+        case DB_Y: src = s.Y; cnt = B; break;
+        case DB_Q: src = s.Q; cnt = 2 * B; break;
+        case DB_TQ: src = s.TQ; cnt = 2 * B; break;
+        case DB_RLQ: src = s.RLQ; cnt = B; break;
+        case DB_SOFTQ: src = s.SOFTQ; cnt = B; break;
+        case DB_LP: src = s.LP; cnt = (size_t)MAX_CTAS * LP_WORDS; break;
+        default: return fail(HIRL_E_INVALID, "bad debug buffer id");
+    }
+    if (n_out) *n_out = cnt;
+    if (!dst) return 0;
+    if (n < cnt) return fail(HIRL_E_INVALID, "destination too small");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(dst, src, cnt * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- env -----------------------------------------------------------------------------------
+static int env_grid(long long n, int per_block) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (n + per_block - 1) / per_block;
+    return (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sms * 8));
+}
+int hirl_env_step_dev(const float *raw16_dev, int64_t n, float *obs13_dev, float *reward_dev, int32_t *flags_dev,
+                      unsigned long long *counters3_dev, void *stream) {
+    if (n < 0 || (n > 0 && (!raw16_dev || !obs13_dev || !reward_dev || !flags_dev))) return fail(HIRL_E_INVALID, "bad argument");
+    if (n == 0) return 0;
+    if (((uintptr_t)raw16_dev | (uintptr_t)obs13_dev) & 15) return fail(HIRL_E_INVALID, "raw/obs pointers must be 16-byte aligned");
+    env_step_kernel<<<env_grid(n, ENV_THREADS), ENV_THREADS, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(raw16_dev), n, obs13_dev,
+                                                                                         reward_dev, flags_dev, counters3_dev);
+    CU(cudaGetLastError());
+    return 0;
+}
+int hirl_env_step(int device, const float *raw16, int64_t n, float *obs13, float *reward, int32_t *flags, unsigned long long *counters3) {
+    if (n < 0 || (n > 0 && (!raw16 || !obs13 || !reward || !flags))) return fail(HIRL_E_INVALID, "bad argument");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(device));
+    float *d_raw = nullptr, *d_obs = nullptr, *d_rew = nullptr;
+    int32_t *d_fl = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    CU(cudaMalloc(&d_raw, (size_t)n * 64));
+    CU(cudaMalloc(&d_obs, (size_t)n * 52));
+    CU(cudaMalloc(&d_rew, (size_t)n * 4));
+    CU(cudaMalloc(&d_fl, (size_t)n * 4));
+    if (counters3) { CU(cudaMalloc(&d_cnt, 24)); CU(cudaMemcpy(d_cnt, counters3, 24, cudaMemcpyHostToDevice)); }
+    CU(cudaMemcpy(d_raw, raw16, (size_t)n * 64, cudaMemcpyHostToDevice));
+    int rc = hirl_env_step_dev(d_raw, n, d_obs, d_rew, d_fl, d_cnt, nullptr);
+    if (!rc) {
+        CU(cudaMemcpy(obs13, d_obs, (size_t)n * 52, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(reward, d_rew, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(flags, d_fl, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        if (counters3) CU(cudaMemcpy(counters3, d_cnt, 24, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_raw); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_fl); cudaFree(d_cnt);
+    return rc;
+}
+int hirl_env_offline_dev(const float *s13_dev, const float *a4_dev, const float *s2_13_dev, int64_t n, float *reward_dev, int8_t *success_dev,
+                         uint8_t *done_dev, void *stream) {
+    if (n < 0 || (n > 0 && (!s13_dev || !a4_dev || !s2_13_dev || !reward_dev || !success_dev || !done_dev))) return fail(HIRL_E_INVALID, "bad argument");
+    if (n == 0) return 0;
+    env_offline_kernel<<<env_grid(n, ENV_THREADS), ENV_THREADS, 0, (cudaStream_t)stream>>>(s13_dev, a4_dev, s2_13_dev, n, reward_dev,
+                                                                                            reinterpret_cast<signed char *>(success_dev), done_dev);
+    CU(cudaGetLastError());
+    return 0;
+}
+int hirl_env_offline(int device, const float *s13, const float *a4, const float *s2_13, int64_t n, float *reward, int8_t *success, uint8_t *done) {
+    if (n < 0 || (n > 0 && (!s13 || !a4 || !s2_13 || !reward || !success || !done))) return fail(HIRL_E_INVALID, "bad argument");
+    if (n == 0) return 0;
+    CU(cudaSetDevice(device));
+    float *d_s = nullptr, *d_a = nullptr, *d_s2 = nullptr, *d_r = nullptr;
+    int8_t *d_su = nullptr;
+    uint8_t *d_d = nullptr;
+    CU(cudaMalloc(&d_s, (size_t)n * 52)); CU(cudaMalloc(&d_a, (size_t)n * 16)); CU(cudaMalloc(&d_s2, (size_t)n * 52));
+    CU(cudaMalloc(&d_r, (size_t)n * 4)); CU(cudaMalloc(&d_su, (size_t)n)); CU(cudaMalloc(&d_d, (size_t)n));
+    CU(cudaMemcpy(d_s, s13, (size_t)n * 52, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_a, a4, (size_t)n * 16, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_s2, s2_13, (size_t)n * 52, cudaMemcpyHostToDevice));
+    int rc = hirl_env_offline_dev(d_s, d_a, d_s2, n, d_r, d_su, d_d, nullptr);
+    if (!rc) {
+        CU(cudaMemcpy(reward, d_r, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(success, d_su, (size_t)n, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(done, d_d, (size_t)n, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_s); cudaFree(d_a); cudaFree(d_s2); cudaFree(d_r); cudaFree(d_su); cudaFree(d_d);
+    return rc;
+}
+
+// train_all.py:287-306.  The reward/flag pass over all consecutive pairs runs on the GPU; the
+// data-dependent "skip the row after a terminal next-state" walk is a sequential scan over n
+// bytes on the host (it has a loop-carried dependence and costs microseconds).
+int hirl_expert_scan(int device, const float *states13, const float *actions4, int n, float *out_rows32, int8_t *out_success, int *n_rows_out) {
+    if (!states13 || !actions4 || !out_rows32 || !out_success || !n_rows_out || n < 0) return fail(HIRL_E_INVALID, "bad argument");
+    *n_rows_out = 0;
+    if (n < 2) return 0;
+    const int m = n - 1;
+    std::vector<float> r(m);
+    std::vector<int8_t> su(m);
+    std::vector<uint8_t> d(m);
+    if (int rc = hirl_env_offline(device, states13, actions4, states13 + S, m, r.data(), su.data(), d.data())) return rc;
+    int kept = 0;
+    for (int i = 0; i < m;) {
+        float *row = out_rows32 + (size_t)kept * ROW;
+        std::memcpy(row, states13 + (size_t)i * S, S * 4);
+        std::memcpy(row + S, actions4 + (size_t)i * A, A * 4);
+        std::memcpy(row + SA, states13 + (size_t)(i + 1) * S, S * 4);
+        row[30] = r[i];
+        row[31] = d[i] ? 1.f : 0.f;
+        out_success[kept] = su[i];
+        ++kept;
+        i += d[i] ? 2 : 1;
+    }
+    *n_rows_out = kept;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1086 @@
+// update.cuh -- device code of the fused HIRL update (reference hirl/agents/HIRL.py:221-334).
+//
+// One learn() call is a fixed sequence of stages (enum Stage in common.cuh) executed by a
+// "team" of CTAs that synchronise with a team barrier:
+//   R stages  one warp per batch row: gather, 13/17->256 first layers, LayerNorm, heads,
+//             losses and the backward passes through heads / LayerNorms (warp-shuffle
+//             reductions, column sums through shared-memory tiles, per-CTA partial
+//             gradients that are reduced in a fixed order -> run-to-run deterministic)
+//   G stages  the 256<->512 contractions as 64x64 FP32-FMA tiles from shared memory
+//             (forward NT, dX NN, dW TN), optional split-K for small batches
+// The same stage functions serve the single-agent grid-wide kernel (team = whole grid) and
+// the ensemble kernel (team = one thread-block cluster per replica).
+#pragma once
+#include "common.cuh"
+
+namespace hirl {
+
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr int TS = 68;                       // padded row stride of a 16x64 operand tile
+constexpr int GEMM_SMEM_FLOATS = 4 * 16 * TS;  // A,B double buffered
+constexpr int TILE_ROWS = WARPS;             // rows per row-stage chunk
+constexpr int ROWSTAGE_SMEM_FLOATS = 4 * TILE_ROWS * H2 + 64 + TILE_ROWS * 32;
+constexpr int SMEM_FLOATS = ROWSTAGE_SMEM_FLOATS > GEMM_SMEM_FLOATS ? ROWSTAGE_SMEM_FLOATS : GEMM_SMEM_FLOATS;
+constexpr size_t SMEM_BYTES = SMEM_FLOATS * sizeof(float);
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ float act_f(float pre, float slope) { return pre > 0.f ? pre : pre * slope; }
+__device__ __forceinline__ float act_g(float pre, float slope) { return pre > 0.f ? 1.f : slope; }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// A team is the set of CTAs that cooperate on one agent's update.
+struct Team {
+    int rank, size;
+    unsigned *count, *gen_ptr;
+    unsigned gen;
+};
+
+// sense-reversing barrier over global memory; the acquire side invalidates this SM's L1 so
+// plain loads issued afterwards observe everything the other CTAs wrote before arriving.
+__device__ __forceinline__ void team_sync(Team &t) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned arrived = atomicAdd(t.count, 1u);
+        if (arrived == (unsigned)t.size - 1u) {
+            atomicExch(t.count, 0u);
+            __threadfence();
+            atomicAdd(t.gen_ptr, 1u);
+        } else {
+            while (ld_acquire_u32(t.gen_ptr) == t.gen) {
+            }
+        }
+        __threadfence();
+    }
+    t.gen += 1u;
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// row-wise building blocks (one warp = one batch row)
+// ---------------------------------------------------------------------------------------------
+// first layer + LayerNorm + activation: h1 = act(LN(W1 x + b1))   (HIRL.py:61,64,131)
+// lane owns outputs n = lane + 32 j.
+template <class L>
+__device__ __forceinline__ void l1_row(const float *tw, const float (&x)[L::k0], float slope, int lane,
+                                       float *h1_out, float *xh_out, float *rs_out) {
+    float z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = tw[L::B1 + lane + 32 * j];
+#pragma unroll
+    for (int k = 0; k < L::k0; ++k) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = fmaf(x[k], tw[L::W1T + k * H1 + lane + 32 * j], z[j]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += z[j];
+    const float mean = warp_sum(s) * (1.f / H1);
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float d = z[j] - mean;
+        v = fmaf(d, d, v);
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(v) * (1.f / H1) + LN_EPS);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int n = lane + 32 * j;
+        const float xh = (z[j] - mean) * rstd;
+        h1_out[n] = act_f(fmaf(xh, tw[L::G1 + n], tw[L::BE1 + n]), slope);
+        if (xh_out) xh_out[n] = xh;
+    }
+    if (rs_out && lane == 0) *rs_out = rstd;
+}
+
+// loads a 512-wide row, summing the split-K partial buffers in a fixed order.
+// lane owns columns c(e) = 4*lane + 128*(e/4) + e%4.
+__device__ __forceinline__ void load_row512(const float *row, int nsplit, size_t split_stride, int lane, float (&v)[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 t = ldcg4(row + 4 * lane + 128 * j);
+        v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+    for (int s = 1; s < nsplit; ++s) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 t = ldcg4(row + s * split_stride + 4 * lane + 128 * j);
+            v[4 * j + 0] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+        }
+    }
+}
+__device__ __forceinline__ void store_row512(float *row, int lane, const float (&v)[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st4(row + 4 * lane + 128 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+}
+__device__ __forceinline__ void load_vec512(const float *p, int lane, float (&v)[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 t = ld4(p + 4 * lane + 128 * j);
+        v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+}
+
+// LayerNorm2 + activation + output layer of one row: z (pre-LN, bias included) -> xh, h, out
+template <class L>
+__device__ __forceinline__ void head_forward(const float *tw, const float (&z)[16], float slope, int lane,
+                                             float (&xh)[16], float (&h)[16], float &rstd, float (&out)[L::nout]) {
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) s += z[e];
+    const float mean = warp_sum(s) * (1.f / H2);
+    float v = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        const float d = z[e] - mean;
+        v = fmaf(d, d, v);
+    }
+    rstd = 1.f / sqrtf(warp_sum(v) * (1.f / H2) + LN_EPS);
+    float g[16], be[16];
+    load_vec512(tw + L::G2, lane, g);
+    load_vec512(tw + L::BE2, lane, be);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        xh[e] = (z[e] - mean) * rstd;
+        h[e] = act_f(fmaf(xh[e], g[e], be[e]), slope);
+    }
+#pragma unroll
+    for (int o = 0; o < L::nout; ++o) {
+        float w[16];
+        load_vec512(tw + L::W3 + o * H2, lane, w);
+        float p = 0.f;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) p = fmaf(h[e], w[e], p);
+        out[o] = warp_sum(p) + tw[L::B3 + o];
+    }
+}
+
+// backward of the same block: given d(out) returns dz (grad of the pre-LN row) and dy (grad
+// at the LayerNorm output = grad of gamma*xh+beta); the caller turns dy/xh/h into the
+// parameter gradients.
+template <class L>
+__device__ __forceinline__ void head_backward(const float *tw, const float (&xh)[16], float rstd, const float (&dout)[L::nout],
+                                              float slope, int lane, float (&dz)[16], float (&dy)[16]) {
+    float g[16], be[16];
+    load_vec512(tw + L::G2, lane, g);
+    load_vec512(tw + L::BE2, lane, be);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) dy[e] = 0.f;
+#pragma unroll
+    for (int o = 0; o < L::nout; ++o) {
+        float w[16];
+        load_vec512(tw + L::W3 + o * H2, lane, w);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dy[e] = fmaf(dout[o], w[e], dy[e]);
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        dy[e] *= act_g(fmaf(xh[e], g[e], be[e]), slope);
+        dz[e] = dy[e] * g[e];  // d xhat
+        s1 += dz[e];
+        s2 = fmaf(dz[e], xh[e], s2);
+    }
+    s1 = warp_sum(s1) * (1.f / H2);
+    s2 = warp_sum(s2) * (1.f / H2);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) dz[e] = rstd * (dz[e] - s1 - xh[e] * s2);
+}
+
+// backward through activation + LayerNorm1 of one row.  lane owns n = lane + 32 j.
+// in: dh (grad at h1), xh, rstd.  out: dz (grad of W1 x + b1), dy (grad at LN output).
+template <class L>
+__device__ __forceinline__ void ln1_backward(const float *tw, const float (&dh)[8], const float (&xh)[8], float rstd,
+                                             float slope, int lane, float (&dz)[8], float (&dy)[8]) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int n = lane + 32 * j;
+        const float g = tw[L::G1 + n];
+        dy[j] = dh[j] * act_g(fmaf(xh[j], g, tw[L::BE1 + n]), slope);
+        dz[j] = dy[j] * g;
+        s1 += dz[j];
+        s2 = fmaf(dz[j], xh[j], s2);
+    }
+    s1 = warp_sum(s1) * (1.f / H1);
+    s2 = warp_sum(s2) * (1.f / H1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] = rstd * (dz[j] - s1 - xh[j] * s2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32 tile GEMM: C[64x64] (+split) = sum_k A . B, three operand arrangements
+// ---------------------------------------------------------------------------------------------
+enum { GEMM_NT = 0, GEMM_NN = 1, GEMM_TN = 2 };
+struct GemmJob {
+    const float *A, *B, *A2, *B2, *bias;
+    float *C;
+    int lda, ldb, ldc, M, N, K, K2, mode, nsplit;
+    size_t csplit;  // element stride between split-K partial outputs
+};
+
+// operand whose reduction index is contiguous (row r = output index)
+__device__ __forceinline__ float4 load_kmajor(const float *P, int ld, int r0, int R, int k0, int K, int tid) {
+    const int r = r0 + (tid >> 2), k = k0 + 4 * (tid & 3);
+    if (r < R && k < K) return ldcg4(P + (size_t)r * ld + k);
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void store_kmajor(float *T, float4 v, int tid) {
+    const int r = tid >> 2, kq = 4 * (tid & 3);
+    T[(kq + 0) * TS + r] = v.x;
+    T[(kq + 1) * TS + r] = v.y;
+    T[(kq + 2) * TS + r] = v.z;
+    T[(kq + 3) * TS + r] = v.w;
+}
+// operand whose output index is contiguous (row = reduction index)
+__device__ __forceinline__ float4 load_rmajor(const float *P, int ld, int c0, int Cn, int k0, int K, int tid) {
+    const int k = k0 + (tid >> 4), c = c0 + 4 * (tid & 15);
+    if (k < K && c < Cn) return ldcg4(P + (size_t)k * ld + c);
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void store_rmajor(float *T, float4 v, int tid) { st4(T + (tid >> 4) * TS + 4 * (tid & 15), v); }
+
+template <int MODE>
+__device__ __forceinline__ void gemm_tile(const GemmJob &J, int tm, int tn, int split, float *smem) {
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = tm * 64, n0 = tn * 64;
+    float *As = smem, *Bs = smem + 2 * 16 * TS;
+    const int nk1 = (J.K + 15) >> 4, nk2 = (J.K2 + 15) >> 4, nk = nk1 + nk2;
+    const int kt_begin = (int)(((long long)nk * split) / J.nsplit), kt_end = (int)(((long long)nk * (split + 1)) / J.nsplit);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    auto fetch = [&](int kt, float4 &ra, float4 &rb) {
+        const bool second = kt >= nk1;
+        const float *Ap = second ? J.A2 : J.A, *Bp = second ? J.B2 : J.B;
+        const int K = second ? J.K2 : J.K, k0 = (second ? kt - nk1 : kt) << 4;
+        if (MODE == GEMM_TN) ra = load_rmajor(Ap, J.lda, m0, J.M, k0, K, tid);
+        else ra = load_kmajor(Ap, J.lda, m0, J.M, k0, K, tid);
+        if (MODE == GEMM_NT) rb = load_kmajor(Bp, J.ldb, n0, J.N, k0, K, tid);
+        else rb = load_rmajor(Bp, J.ldb, n0, J.N, k0, K, tid);
+    };
+    auto stash = [&](int buf, const float4 &ra, const float4 &rb) {
+        if (MODE == GEMM_TN) store_rmajor(As + buf * 16 * TS, ra, tid);
+        else store_kmajor(As + buf * 16 * TS, ra, tid);
+        if (MODE == GEMM_NT) store_kmajor(Bs + buf * 16 * TS, rb, tid);
+        else store_rmajor(Bs + buf * 16 * TS, rb, tid);
+    };
+
+    float4 ra, rb;
+    __syncthreads();  // previous user of this shared memory is done
+    if (kt_begin < kt_end) {
+        fetch(kt_begin, ra, rb);
+        stash(0, ra, rb);
+    }
+    __syncthreads();
+    for (int kt = kt_begin; kt < kt_end; ++kt) {
+        const int buf = (kt - kt_begin) & 1;
+        const bool more = kt + 1 < kt_end;
+        if (more) fetch(kt + 1, ra, rb);
+        const float *a = As + buf * 16 * TS + ty * 4, *b = Bs + buf * 16 * TS + tx * 4;
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 av = ld4(a + kk * TS), bv = ld4(b + kk * TS);
+            const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+        if (more) stash(buf ^ 1, ra, rb);
+        __syncthreads();
+    }
+    // epilogue
+    float *C = J.C + (size_t)split * J.csplit;
+    const int n = n0 + tx * 4;
+    if (n < J.N) {
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (J.bias && split == 0) bias = ld4(J.bias + n);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + ty * 4 + i;
+            if (m < J.M) st4(C + (size_t)m * J.ldc + n, make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w));
+        }
+    }
+}
+
+constexpr int MAX_JOBS = 8;
+__device__ __forceinline__ void run_gemm_jobs(const GemmJob *jobs, int njobs, const Team &tm, float *smem) {
+    int start[MAX_JOBS + 1];
+    int total = 0;
+    for (int j = 0; j < njobs; ++j) {
+        start[j] = total;
+        total += ((jobs[j].M + 63) >> 6) * ((jobs[j].N + 63) >> 6) * jobs[j].nsplit;
+    }
+    start[njobs] = total;
+    for (int t = tm.rank; t < total; t += tm.size) {
+        int j = 0;
+        while (t >= start[j + 1]) ++j;
+        const GemmJob &J = jobs[j];
+        const int ntn = (J.N + 63) >> 6, ntm = (J.M + 63) >> 6;
+        int local = t - start[j];
+        const int split = local / (ntm * ntn);
+        local -= split * ntm * ntn;
+        const int tmi = local / ntn, tni = local - tmi * ntn;
+        if (J.mode == GEMM_NT) gemm_tile<GEMM_NT>(J, tmi, tni, split, smem);
+        else if (J.mode == GEMM_NN) gemm_tile<GEMM_NN>(J, tmi, tni, split, smem);
+        else gemm_tile<GEMM_TN>(J, tmi, tni, split, smem);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scratch addressing
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float *H1p(const AgentCtx &c, int pass) { return c.sc.H1 + (size_t)pass * c.B * H1; }
+__device__ __forceinline__ float *XH1p(const AgentCtx &c, int slot) { return c.sc.XH1 + (size_t)slot * c.B * H1; }
+__device__ __forceinline__ float *RS1p(const AgentCtx &c, int slot) { return c.sc.RS1 + (size_t)slot * c.B; }
+__device__ __forceinline__ size_t z2_split_stride(const AgentCtx &c) { return (size_t)c.B * H2; }
+__device__ __forceinline__ float *Z2p(const AgentCtx &c, int pass) { return c.sc.Z2 + (size_t)pass * c.zsplit * c.B * H2; }
+__device__ __forceinline__ size_t dh1_split_stride(const AgentCtx &c) { return (size_t)c.B * H1; }
+__device__ __forceinline__ float *DH1p(const AgentCtx &c, int slot) { return c.sc.DH1 + (size_t)slot * c.zsplit * c.B * H1; }
+__device__ __forceinline__ int g1_split(const AgentCtx &c, const hirl_step_t &st) { return c.ns[st.do_actor ? NS_G1_ACTOR : NS_G1]; }
+__device__ __forceinline__ float slope_of(const AgentCtx &c) { return c.activation == HIRL_ACT_LEAKY_RELU ? 0.01f : 0.f; }
+
+// fixed-order sum of one word of the per-CTA partial block
+__device__ __forceinline__ float lp_sum(const AgentCtx &c, const Team &tm, int word) {
+    float s = 0.f;
+    for (int r = 0; r < tm.size; ++r) s += __ldcg(c.sc.LP + r * LP_WORDS + word);
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// R0: gather + first layers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_r0(const AgentCtx &c, const hirl_step_t &st, int step, const Team &tm) {
+    const int B = c.B, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
+    const float slope = slope_of(c);
+    int passes[6];
+    int np = 0;
+    passes[np++] = P_TA; passes[np++] = P_C1; passes[np++] = P_C2;
+    if (st.do_actor) {
+        passes[np++] = P_A;
+        if (st.mode == 0) { passes[np++] = P_AB; passes[np++] = P_BC; }
+    }
+    const int32_t *ion = c.idx_online + (size_t)step * B, *iex = c.idx_expert + (size_t)step * B, *ibc = c.idx_bc + (size_t)step * B;
+    for (int task = tm.rank; task < nchunks * np; task += tm.size) {
+        const int pass = passes[task / nchunks];
+        const int b = (task % nchunks) * TILE_ROWS + warp;
+        if (b >= B) continue;
+        float w;
+        if (pass == P_AB) {
+            const float *src = c.bctab + (size_t)__ldg(ibc + b) * BCW;
+            w = lane < BCW ? __ldg(src + lane) : 0.f;
+            if (lane < BCW) c.sc.XB[(size_t)b * BCW + lane] = w;
+        } else {
+            const float *src = b < st.n_online ? c.online + (size_t)__ldg(ion + b) * ROW
+                                               : c.expert + (size_t)__ldg(iex + (b - st.n_online)) * ROW;
+            w = __ldg(src + lane);
+            if (pass == P_C1) c.sc.X[(size_t)b * ROW + lane] = w;
+        }
+        if (pass == P_C1 || pass == P_C2) {
+            float x[SA];
+#pragma unroll
+            for (int k = 0; k < SA; ++k) x[k] = __shfl_sync(0xffffffffu, w, k);
+            const int slot = bwd_slot(pass);
+            l1_row<CriticL>(c.critic + (pass == P_C2 ? CriticL::SIZE : 0), x, slope, lane, H1p(c, pass) + (size_t)b * H1,
+                            XH1p(c, slot) + (size_t)b * H1, RS1p(c, slot) + b);
+        } else {
+            float x[S];
+            const int off = pass == P_TA ? SA : 0;  // target actor reads next_state
+#pragma unroll
+            for (int k = 0; k < S; ++k) x[k] = __shfl_sync(0xffffffffu, w, off + k);
+            const float *net = pass == P_TA ? c.tactor : pass == P_BC ? c.bc : c.actor;
+            const int slot = bwd_slot(pass);
+            l1_row<ActorL>(net, x, slope, lane, H1p(c, pass) + (size_t)b * H1,
+                           slot >= 0 ? XH1p(c, slot) + (size_t)b * H1 : nullptr, slot >= 0 ? RS1p(c, slot) + b : nullptr);
+        }
+    }
+}
+
+// second-layer forward GEMM job: Z2[pass] = H1[pass] . W2^T + b2
+template <class L>
+__device__ __forceinline__ GemmJob fwd_job(const AgentCtx &c, int pass, const float *tw, int nsplit) {
+    GemmJob J;
+    J.A = H1p(c, pass); J.lda = H1;
+    J.B = tw + L::W2; J.ldb = H1;
+    J.A2 = J.B2 = nullptr; J.K2 = 0;
+    J.bias = tw + L::B2;
+    J.C = Z2p(c, pass); J.ldc = H2;
+    J.M = c.B; J.N = H2; J.K = H1;
+    J.mode = GEMM_NT; J.nsplit = nsplit; J.csplit = z2_split_stride(c);
+    return J;
+}
+// dH1[slot] = dZ2[pass] . W2
+template <class L>
+__device__ __forceinline__ GemmJob dx_job(const AgentCtx &c, int pass, const float *tw, int nsplit) {
+    GemmJob J;
+    J.A = Z2p(c, pass); J.lda = H2;
+    J.B = tw + L::W2; J.ldb = H1;
+    J.A2 = J.B2 = nullptr; J.K2 = 0;
+    J.bias = nullptr;
+    J.C = DH1p(c, bwd_slot(pass)); J.ldc = H1;
+    J.M = c.B; J.N = H1; J.K = H2;
+    J.mode = GEMM_NN; J.nsplit = nsplit; J.csplit = dh1_split_stride(c);
+    return J;
+}
+// dW2 = dZ2[pass]^T . H1[pass]  (+ second branch)
+template <class L>
+__device__ __forceinline__ GemmJob dw_job(const AgentCtx &c, int pass, int pass2, float *gtw) {
+    GemmJob J;
+    J.A = Z2p(c, pass); J.lda = H2;
+    J.B = H1p(c, pass); J.ldb = H1;
+    J.K = c.B;
+    if (pass2 >= 0) { J.A2 = Z2p(c, pass2); J.B2 = H1p(c, pass2); J.K2 = c.B; }
+    else { J.A2 = J.B2 = nullptr; J.K2 = 0; }
+    J.bias = nullptr;
+    J.C = gtw + L::W2; J.ldc = H1;
+    J.M = H2; J.N = H1;
+    J.mode = GEMM_TN; J.nsplit = 1; J.csplit = 0;
+    return J;
+}
+
+__device__ __forceinline__ void stage_g1(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+    GemmJob jobs[MAX_JOBS];
+    int n = 0;
+    const int ns = g1_split(c, st);
+    jobs[n++] = fwd_job<ActorL>(c, P_TA, c.tactor, ns);
+    jobs[n++] = fwd_job<CriticL>(c, P_C1, c.critic, ns);
+    jobs[n++] = fwd_job<CriticL>(c, P_C2, c.critic + CriticL::SIZE, ns);
+    if (st.do_actor) {
+        jobs[n++] = fwd_job<ActorL>(c, P_A, c.actor, ns);
+        if (st.mode == 0) {
+            jobs[n++] = fwd_job<ActorL>(c, P_AB, c.actor, ns);
+            jobs[n++] = fwd_job<ActorL>(c, P_BC, c.bc, ns);
+        }
+    }
+    run_gemm_jobs(jobs, n, tm, smem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// R1: target-actor head -> a' -> first layers of the target critic; actor-side heads
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_r1(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+    const int B = c.B, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
+    const float slope = slope_of(c);
+    const int nkinds = st.do_actor ? (st.mode == 0 ? 4 : 2) : 1;
+    for (int task = tm.rank; task < nchunks * nkinds; task += tm.size) {
+        const int kind = task / nchunks;
+        const int b = (task % nchunks) * TILE_ROWS + warp;
+        if (b >= B) continue;
+        const int pass = kind == 0 ? P_TA : kind == 1 ? P_A : kind == 2 ? P_AB : P_BC;
+        const float *net = kind == 0 ? c.tactor : kind == 3 ? c.bc : c.actor;
+        float z[16], xh[16], h[16], rstd, out[A];
+        load_row512(Z2p(c, pass) + (size_t)b * H2, g1_split(c, st), z2_split_stride(c), lane, z);
+        head_forward<ActorL>(net, z, slope, lane, xh, h, rstd, out);
+        float a4[A];
+#pragma unroll
+        for (int j = 0; j < A; ++j) a4[j] = tanhf(out[j]);
+        if (kind == 0) {
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+                const float nz = fminf(fmaxf(st.noise[j], -c.noise_clamp), c.noise_clamp);   // HIRL.py:266
+                a4[j] = fminf(fmaxf(a4[j] + nz, -1.f), 1.f);                                   // HIRL.py:267
+            }
+            if (lane < A) c.sc.APRIME[(size_t)b * A + lane] = a4[lane];
+            const float w = c.sc.X[(size_t)b * ROW + lane];
+            float x[SA];
+#pragma unroll
+            for (int k = 0; k < S; ++k) x[k] = __shfl_sync(0xffffffffu, w, SA + k);
+#pragma unroll
+            for (int j = 0; j < A; ++j) x[S + j] = a4[j];
+            l1_row<CriticL>(c.tcritic, x, slope, lane, H1p(c, P_TC1) + (size_t)b * H1, nullptr, nullptr);
+            l1_row<CriticL>(c.tcritic + CriticL::SIZE, x, slope, lane, H1p(c, P_TC2) + (size_t)b * H1, nullptr, nullptr);
+        } else {
+            float *dst = kind == 1 ? c.sc.PI : kind == 2 ? c.sc.PIB : c.sc.ABC;
+            if (lane < A) dst[(size_t)b * A + lane] = a4[lane];
+        }
+    }
+}
+
+__device__ __forceinline__ void stage_g2(const AgentCtx &c, const Team &tm, float *smem) {
+    GemmJob jobs[MAX_JOBS];
+    jobs[0] = fwd_job<CriticL>(c, P_TC1, c.tcritic, c.ns[NS_G2]);
+    jobs[1] = fwd_job<CriticL>(c, P_TC2, c.tcritic + CriticL::SIZE, c.ns[NS_G2]);
+    run_gemm_jobs(jobs, 2, tm, smem);
+}
+
+// shared-memory carve-up of the row stages
+struct RowSmem {
+    float *t0, *t1, *t2, *t3;  // [TILE_ROWS][H2] column-sum tiles
+    float *red;                // [64] small reductions
+    float *aux;                // [TILE_ROWS][32] per-row side values
+};
+__device__ __forceinline__ RowSmem row_smem(float *smem) {
+    RowSmem r;
+    r.t0 = smem; r.t1 = smem + TILE_ROWS * H2; r.t2 = smem + 2 * TILE_ROWS * H2; r.t3 = smem + 3 * TILE_ROWS * H2;
+    r.red = smem + 4 * TILE_ROWS * H2;
+    r.aux = r.red + 64;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// R2: TD target (HIRL.py:270-274), critic heads, loss (HIRL.py:284), backward to dz2
+//   CTAs are split into two groups, one per critic tower.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_r2(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+    const int B = c.B, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
+    const float slope = slope_of(c);
+    const int gsize = tm.size >> 1, tower = tm.rank & 1, grank = tm.rank >> 1;
+    RowSmem sm = row_smem(smem);
+    float loss_acc = 0.f;
+    if (grank < gsize) {
+        const float *tw = c.critic + tower * CriticL::SIZE;
+        const int pass = tower ? P_C2 : P_C1;
+        float a_db2[2] = {0.f, 0.f}, a_dg2[2] = {0.f, 0.f}, a_dbe2[2] = {0.f, 0.f}, a_dw3[2] = {0.f, 0.f}, a_db3 = 0.f;
+        for (int chunk = grank; chunk < nchunks; chunk += gsize) {
+            const int b = chunk * TILE_ROWS + warp;
+            float dz[16], t1v[16], t2v[16], t3v[16], dq = 0.f;
+            if (b < B) {
+                float z[16], xh[16], h[16], rstd, o1[1], o2[1];
+                load_row512(Z2p(c, P_TC1) + (size_t)b * H2, c.ns[NS_G2], z2_split_stride(c), lane, z);
+                head_forward<CriticL>(c.tcritic, z, slope, lane, xh, h, rstd, o1);
+                load_row512(Z2p(c, P_TC2) + (size_t)b * H2, c.ns[NS_G2], z2_split_stride(c), lane, z);
+                head_forward<CriticL>(c.tcritic + CriticL::SIZE, z, slope, lane, xh, h, rstd, o2);
+                const float r = c.sc.X[(size_t)b * ROW + 30], d = c.sc.X[(size_t)b * ROW + 31];
+                const float tq = fminf(o1[0], o2[0]);
+                const float y = __fadd_rn(r, __fmul_rn(__fmul_rn(c.gamma, tq), __fsub_rn(1.f, d)));   // HIRL.py:274
+                load_row512(Z2p(c, pass) + (size_t)b * H2, g1_split(c, st), z2_split_stride(c), lane, z);
+                float q[1];
+                head_forward<CriticL>(tw, z, slope, lane, xh, h, rstd, q);
+                const float delta = q[0] - y;
+                if (lane == 0) {
+                    loss_acc = fmaf(delta, delta, loss_acc);
+                    c.sc.Q[(size_t)tower * B + b] = q[0];
+                    c.sc.TQ[(size_t)tower * B + b] = tower ? o2[0] : o1[0];
+                    if (tower == 0) c.sc.Y[b] = y;
+                }
+                dq = (2.f / (float)B) * delta;  // mse_loss backward, mean reduction
+                float dout[1] = {dq}, dy[16];
+                head_backward<CriticL>(tw, xh, rstd, dout, slope, lane, dz, dy);
+                store_row512(Z2p(c, pass) + (size_t)b * H2, lane, dz);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { t1v[e] = dy[e] * xh[e]; t2v[e] = dy[e]; t3v[e] = dq * h[e]; }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) dz[e] = t1v[e] = t2v[e] = t3v[e] = 0.f;
+            }
+            store_row512(sm.t0 + warp * H2, lane, dz);
+            store_row512(sm.t1 + warp * H2, lane, t1v);
+            store_row512(sm.t2 + warp * H2, lane, t2v);
+            store_row512(sm.t3 + warp * H2, lane, t3v);
+            if (lane == 0) sm.aux[warp * 32] = dq;
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int col = tid + u * THREADS;
+#pragma unroll
+                for (int w = 0; w < TILE_ROWS; ++w) {
+                    a_db2[u] += sm.t0[w * H2 + col];
+                    a_dg2[u] += sm.t1[w * H2 + col];
+                    a_dbe2[u] += sm.t2[w * H2 + col];
+                    a_dw3[u] += sm.t3[w * H2 + col];
+                }
+            }
+            if (tid == 0)
+                for (int w = 0; w < TILE_ROWS; ++w) a_db3 += sm.aux[w * 32];
+            __syncthreads();
+        }
+        const int P = gsize < nchunks ? gsize : nchunks;
+        if (grank < P) {
+            float *part = c.sc.PART_C + ((size_t)grank * 2 + tower) * CriticL::SMALL;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int col = tid + u * THREADS;
+                part[CriticL::small_index(CriticL::B2) + col] = a_db2[u];
+                part[CriticL::small_index(CriticL::G2) + col] = a_dg2[u];
+                part[CriticL::small_index(CriticL::BE2) + col] = a_dbe2[u];
+                part[CriticL::small_index(CriticL::W3) + col] = a_dw3[u];
+            }
+            if (tid < 32) part[CriticL::small_index(CriticL::B3) + tid] = tid == 0 ? a_db3 : 0.f;
+        }
+    }
+    // per-CTA loss partial (fixed order over warps)
+    if (lane == 0) sm.red[warp] = loss_acc;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int w = 0; w < WARPS; ++w) s += sm.red[w];
+        c.sc.LP[tm.rank * LP_WORDS + 0] = s;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void stage_g3(const AgentCtx &c, const Team &tm, float *smem) {
+    GemmJob jobs[MAX_JOBS];
+    jobs[0] = dw_job<CriticL>(c, P_C1, -1, c.g_critic);
+    jobs[1] = dw_job<CriticL>(c, P_C2, -1, c.g_critic + CriticL::SIZE);
+    jobs[2] = dx_job<CriticL>(c, P_C1, c.critic, c.ns[NS_G3DX]);
+    jobs[3] = dx_job<CriticL>(c, P_C2, c.critic + CriticL::SIZE, c.ns[NS_G3DX]);
+    run_gemm_jobs(jobs, 4, tm, smem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm1 / first-layer backward for one group of rows; accumulates per-thread column sums.
+//   xsrc: row-major inputs (ld words per row), x = first L::k0 words.
+// ---------------------------------------------------------------------------------------------
+template <class L>
+struct Ln1Acc {
+    float db1 = 0.f, dg1 = 0.f, dbe1 = 0.f, dw[L::k0];
+    __device__ Ln1Acc() {
+#pragma unroll
+        for (int k = 0; k < L::k0; ++k) dw[k] = 0.f;
+    }
+};
+template <class L>
+__device__ __forceinline__ void ln1_bwd_rows(const AgentCtx &c, const float *tw, int slot, int nsplit, const float *xsrc, int xld,
+                                             int first_chunk, int chunk_step, Ln1Acc<L> &acc, const RowSmem &sm, float *gpi_out) {
+    const int B = c.B, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
+    const float slope = slope_of(c);
+    float *t_dz = sm.t0, *t_dg = sm.t0 + TILE_ROWS * H1, *t_dbe = sm.t0 + 2 * TILE_ROWS * H1;
+    for (int chunk = first_chunk; chunk < nchunks; chunk += chunk_step) {
+        const int b = chunk * TILE_ROWS + warp;
+        float dz[8], dy[8], xh[8];
+        float xw = 0.f;
+        if (b < B) {
+            float dh[8];
+            const float *dsrc = DH1p(c, slot) + (size_t)b * H1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dh[j] = __ldcg(dsrc + lane + 32 * j);
+            for (int s = 1; s < nsplit; ++s)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dh[j] += __ldcg(dsrc + s * dh1_split_stride(c) + lane + 32 * j);
+            const float *xs = XH1p(c, slot) + (size_t)b * H1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xh[j] = xs[lane + 32 * j];
+            const float rstd = RS1p(c, slot)[b];
+            ln1_backward<L>(tw, dh, xh, rstd, slope, lane, dz, dy);
+            if (xsrc && lane < L::k0) xw = xsrc[(size_t)b * xld + lane];
+            if (gpi_out) {  // gradient w.r.t. the action part of the critic input
+                float g[A];
+#pragma unroll
+                for (int j2 = 0; j2 < A; ++j2) {
+                    float p = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) p = fmaf(dz[j], tw[L::W1T + (S + j2) * H1 + lane + 32 * j], p);
+                    g[j2] = warp_sum(p);
+                }
+                if (lane < A) gpi_out[(size_t)b * A + lane] = g[lane];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dz[j] = dy[j] = xh[j] = 0.f;
+        }
+        if (xsrc) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = lane + 32 * j;
+                t_dz[warp * H1 + n] = dz[j];
+                t_dg[warp * H1 + n] = dy[j] * xh[j];
+                t_dbe[warp * H1 + n] = dy[j];
+            }
+            sm.aux[warp * 32 + lane] = xw;
+            __syncthreads();
+            if (tid < H1) {
+#pragma unroll
+                for (int w = 0; w < TILE_ROWS; ++w) {
+                    const float dzv = t_dz[w * H1 + tid];
+                    acc.db1 += dzv;
+                    acc.dg1 += t_dg[w * H1 + tid];
+                    acc.dbe1 += t_dbe[w * H1 + tid];
+#pragma unroll
+                    for (int k = 0; k < L::k0; ++k) acc.dw[k] = fmaf(dzv, sm.aux[w * 32 + k], acc.dw[k]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+template <class L>
+__device__ __forceinline__ void ln1_write_partial(float *part, const Ln1Acc<L> &acc) {
+    const int tid = threadIdx.x;
+    if (tid < H1) {
+        part[L::B1 + tid] = acc.db1;
+        part[L::G1 + tid] = acc.dg1;
+        part[L::BE1 + tid] = acc.dbe1;
+#pragma unroll
+        for (int k = 0; k < L::k0; ++k) part[L::W1T + k * H1 + tid] = acc.dw[k];
+    }
+}
+
+__device__ __forceinline__ void stage_r3(const AgentCtx &c, const Team &tm, float *smem) {
+    const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS;
+    const int gsize = tm.size >> 1, tower = tm.rank & 1, grank = tm.rank >> 1;
+    RowSmem sm = row_smem(smem);
+    if (grank < gsize) {
+        Ln1Acc<CriticL> acc;
+        ln1_bwd_rows<CriticL>(c, c.critic + tower * CriticL::SIZE, tower, c.ns[NS_G3DX], c.sc.X, ROW, grank, gsize, acc, sm, nullptr);
+        const int P = gsize < nchunks ? gsize : nchunks;
+        if (grank < P) ln1_write_partial<CriticL>(c.sc.PART_C + ((size_t)grank * 2 + tower) * CriticL::SMALL, acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam single-tensor arithmetic) and Polyak (HIRL.py:11-13)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adam_elem(float g, float &w, float &m, float &v, float neg_step, float bc2_sqrt) {
+    m = fmaf(0.1f, g - m, m);                                   // exp_avg.lerp_(grad, 1-beta1)
+    v = fmaf(__fmul_rn(0.001f, g), g, __fmul_rn(v, 0.999f));    // mul_(beta2).addcmul_(g, g, 1-beta2)
+    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), 1e-8f);
+    w = __fadd_rn(w, __fdiv_rn(__fmul_rn(neg_step, m), denom));  // addcdiv_(m, denom, -step_size)
+}
+__device__ __forceinline__ float polyak_elem(float t, float p, float tau, float one_minus_tau) {
+    return __fadd_rn(__fmul_rn(t, one_minus_tau), __fmul_rn(p, tau));
+}
+
+template <class L>
+__device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w, float *gw, float *m, float *v, const float *part,
+                                           int part_towers, int nslots, float neg_step, float bc2_sqrt, float *target, bool polyak,
+                                           float tau, float one_minus_tau) {
+    const int total = ntowers * L::SIZE;
+    for (int e = tm.rank * THREADS + threadIdx.x; e < total; e += tm.size * THREADS) {
+        const int tower = e / L::SIZE, off = e - tower * L::SIZE;
+        float g;
+        if (off >= L::W2 && off < L::B2) {
+            g = __ldcg(gw + e);
+        } else {
+            const int si = L::small_index(off);
+            g = 0.f;
+            for (int s = 0; s < nslots; ++s) g += __ldcg(part + ((size_t)s * part_towers + tower) * L::SMALL + si);
+            gw[e] = g;
+        }
+        float wv = w[e], mv = m[e], vv = v[e];
+        adam_elem(g, wv, mv, vv, neg_step, bc2_sqrt);
+        w[e] = wv; m[e] = mv; v[e] = vv;
+        if (polyak) target[e] = polyak_elem(target[e], wv, tau, one_minus_tau);
+    }
+}
+template <class L>
+__device__ __forceinline__ void polyak_arena(const Team &tm, int ntowers, const float *w, float *target, float tau, float one_minus_tau) {
+    const int total = ntowers * L::SIZE;
+    for (int e = tm.rank * THREADS + threadIdx.x; e < total; e += tm.size * THREADS)
+        target[e] = polyak_elem(target[e], w[e], tau, one_minus_tau);
+}
+
+__device__ __forceinline__ void stage_g4(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+    const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
+    const int P = gsize < nchunks ? gsize : nchunks;
+    adam_arena<CriticL>(tm, 2, c.critic, c.g_critic, c.m_critic, c.v_critic, c.sc.PART_C, 2, P, st.critic_neg_step,
+                        st.critic_bc2_sqrt, nullptr, false, 0.f, 0.f);
+    if (tm.rank == 0 && threadIdx.x == 0) {
+        // critic_loss = mse(Q1,y) + mse(Q2,y): even ranks hold tower 0, odd ranks tower 1
+        float s0 = 0.f, s1 = 0.f;
+        for (int r = 0; r < tm.size; ++r) {
+            const float v = __ldcg(c.sc.LP + r * LP_WORDS + 0);
+            if (r & 1) s1 += v; else s0 += v;
+        }
+        c.carry[0] = __fadd_rn(s0 / (float)c.B, s1 / (float)c.B);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// actor phase
+// ---------------------------------------------------------------------------------------------
+// R4: first layers of Q1(s, pi(s)) and Q1(s, a_bc) with the updated critic (HIRL.py:296, 302)
+__device__ __forceinline__ void stage_r4(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+    const int B = c.B, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
+    const float slope = slope_of(c);
+    const bool soft = st.mode == 0 && st.bc_weight_now == 100.f;
+    const int nkinds = soft ? 2 : 1;
+    for (int task = tm.rank; task < nchunks * nkinds; task += tm.size) {
+        const int kind = task / nchunks;
+        const int b = (task % nchunks) * TILE_ROWS + warp;
+        if (b >= B) continue;
+        const float w = c.sc.X[(size_t)b * ROW + lane];
+        const float *act = (kind == 0 ? c.sc.PI : c.sc.ABC) + (size_t)b * A;
+        float x[SA];
+#pragma unroll
+        for (int k = 0; k < S; ++k) x[k] = __shfl_sync(0xffffffffu, w, k);
+#pragma unroll
+        for (int j = 0; j < A; ++j) x[S + j] = act[j];
+        if (kind == 0)
+            l1_row<CriticL>(c.critic, x, slope, lane, H1p(c, P_QP) + (size_t)b * H1, XH1p(c, 4) + (size_t)b * H1, RS1p(c, 4) + b);
+        else
+            l1_row<CriticL>(c.critic, x, slope, lane, H1p(c, P_QS) + (size_t)b * H1, nullptr, nullptr);
+    }
+}
+__device__ __forceinline__ void stage_g5(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+    GemmJob jobs[MAX_JOBS];
+    int n = 0;
+    jobs[n++] = fwd_job<CriticL>(c, P_QP, c.critic, c.ns[NS_G5]);
+    if (st.mode == 0 && st.bc_weight_now == 100.f) jobs[n++] = fwd_job<CriticL>(c, P_QS, c.critic, c.ns[NS_G5]);
+    run_gemm_jobs(jobs, n, tm, smem);
+}
+// R5: Q heads, soft count (HIRL.py:303), rl_loss partial (HIRL.py:297), backward of Q1(s,pi) with
+// the unit upstream gradient -1/B; the (1-w) factor is applied where it meets the actor (R6).
+__device__ __forceinline__ void stage_r5(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+    const int B = c.B, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
+    const float slope = slope_of(c);
+    const bool soft = st.mode == 0 && st.bc_weight_now == 100.f;
+    RowSmem sm = row_smem(smem);
+    float cnt = 0.f, sum_q = 0.f;
+    for (int chunk = tm.rank; chunk < nchunks; chunk += tm.size) {
+        const int b = chunk * TILE_ROWS + warp;
+        if (b >= B) continue;
+        float z[16], xh[16], h[16], rstd, q[1];
+        float softq = 0.f;
+        if (soft) {
+            float rs2, qs[1];
+            load_row512(Z2p(c, P_QS) + (size_t)b * H2, c.ns[NS_G5], z2_split_stride(c), lane, z);
+            head_forward<CriticL>(c.critic, z, slope, lane, xh, h, rs2, qs);
+            softq = qs[0];
+        }
+        load_row512(Z2p(c, P_QP) + (size_t)b * H2, c.ns[NS_G5], z2_split_stride(c), lane, z);
+        head_forward<CriticL>(c.critic, z, slope, lane, xh, h, rstd, q);
+        if (lane == 0) {
+            c.sc.RLQ[b] = q[0];
+            sum_q += q[0];
+            if (soft) {
+                c.sc.SOFTQ[b] = softq;
+                cnt += softq > q[0] ? 1.f : 0.f;
+            }
+        }
+        float dout[1] = {-1.f / (float)B}, dz[16], dy[16];
+        head_backward<CriticL>(c.critic, xh, rstd, dout, slope, lane, dz, dy);
+        store_row512(Z2p(c, P_QP) + (size_t)b * H2, lane, dz);
+    }
+    if (lane == 0) { sm.red[warp] = cnt; sm.red[8 + warp] = sum_q; }
+    __syncthreads();
+    if (tid == 0) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int w = 0; w < WARPS; ++w) { s0 += sm.red[w]; s1 += sm.red[8 + w]; }
+        c.sc.LP[tm.rank * LP_WORDS + 1] = s0;
+        c.sc.LP[tm.rank * LP_WORDS + 2] = s1;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void stage_g6(const AgentCtx &c, const Team &tm, float *smem) {
+    GemmJob jobs[MAX_JOBS];
+    jobs[0] = dx_job<CriticL>(c, P_QP, c.critic, c.ns[NS_G6]);
+    run_gemm_jobs(jobs, 1, tm, smem);
+}
+
+// the behaviour-cloning weight of this call (HIRL.py:292-308), evaluated identically by every CTA
+struct BcWeight { float w, one_minus_w, count; };
+__device__ __forceinline__ BcWeight bc_weight_of(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+    BcWeight r;
+    r.count = 0.f;
+    double w = (double)st.bc_weight_now;
+    if (st.mode != 0) w = 0.0;
+    else if (st.bc_weight_now == 100.f) {
+        r.count = lp_sum(c, tm, 1);
+        const float mean = st.force_soft_weight >= 0.f ? st.force_soft_weight : r.count / (float)c.B;  // .float().mean()
+        w = (double)mean + (double)st.bc_warm_up;
+    }
+    if (w > 1.0) w = 1.0;
+    r.w = (float)w;
+    r.one_minus_w = (float)(1.0 - w);
+    return r;
+}
+
+// R6: group 0: d pi from the critic, actor head backward on batch states (rl branch);
+//     group 1: BC loss (HIRL.py:310-311) and actor head backward on expert states.
+__device__ __forceinline__ void stage_r6(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+    const int B = c.B, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
+    const float slope = slope_of(c);
+    const int gsize = tm.size >> 1, branch = tm.rank & 1, grank = tm.rank >> 1;
+    RowSmem sm = row_smem(smem);
+    if (tid == 0) {
+        const BcWeight b0 = bc_weight_of(c, st, tm);
+        sm.red[32] = b0.w; sm.red[33] = b0.one_minus_w;
+    }
+    __syncthreads();
+    BcWeight bw;
+    bw.w = sm.red[32]; bw.one_minus_w = sm.red[33]; bw.count = 0.f;
+    float bc_sq = 0.f, fire_sq = 0.f;
+    const bool active = grank < gsize && (branch == 0 || st.mode == 0);
+    if (active) {
+        // ---- step 1 (branch 0): LayerNorm1 backward of Q1(s,pi) -> unit gradient w.r.t. pi
+        if (branch == 0) {
+            Ln1Acc<CriticL> unused;
+            ln1_bwd_rows<CriticL>(c, c.critic, 4, c.ns[NS_G6], nullptr, 0, grank, gsize, unused, sm, c.sc.GPI);
+            __syncwarp();
+        }
+        const int pass = branch ? P_AB : P_A;
+        float a_db2[2] = {0.f, 0.f}, a_dg2[2] = {0.f, 0.f}, a_dbe2[2] = {0.f, 0.f}, a_dw3[A][2], a_db3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < A; ++j) a_dw3[j][0] = a_dw3[j][1] = 0.f;
+        for (int chunk = grank; chunk < nchunks; chunk += gsize) {
+            const int b = chunk * TILE_ROWS + warp;
+            float dz[16], t1v[16], t2v[16], hv[16], dpre[A] = {0.f, 0.f, 0.f, 0.f};
+            if (b < B) {
+                float z[16], xh[16], rstd, out[A];
+                load_row512(Z2p(c, pass) + (size_t)b * H2, c.ns[NS_G1_ACTOR], z2_split_stride(c), lane, z);
+                head_forward<ActorL>(c.actor, z, slope, lane, xh, hv, rstd, out);
+#pragma unroll
+                for (int j = 0; j < A; ++j) {
+                    const float pi = tanhf(out[j]);
+                    float dpi;
+                    if (branch == 0) {
+                        dpi = bw.one_minus_w * c.sc.GPI[(size_t)b * A + j];
+                    } else {
+                        const float diff = pi - c.sc.XB[(size_t)b * BCW + S + j];
+                        if (lane == 0) {
+                            bc_sq = fmaf(diff, diff, bc_sq);
+                            if (j == 3) fire_sq = fmaf(diff, diff, fire_sq);
+                        }
+                        dpi = ((2.f / (float)(A * B)) * diff) * (bw.w * c.loss_lambda);
+                    }
+                    dpre[j] = dpi * (1.f - pi * pi);   // tanh backward
+                }
+                float dy[16];
+                head_backward<ActorL>(c.actor, xh, rstd, dpre, slope, lane, dz, dy);
+                store_row512(Z2p(c, pass) + (size_t)b * H2, lane, dz);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { t1v[e] = dy[e] * xh[e]; t2v[e] = dy[e]; }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) dz[e] = t1v[e] = t2v[e] = hv[e] = 0.f;
+            }
+            store_row512(sm.t0 + warp * H2, lane, dz);
+            store_row512(sm.t1 + warp * H2, lane, t1v);
+            store_row512(sm.t2 + warp * H2, lane, t2v);
+            store_row512(sm.t3 + warp * H2, lane, hv);
+            if (lane < A) sm.aux[warp * 32 + lane] = dpre[lane];
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int col = tid + u * THREADS;
+#pragma unroll
+                for (int w = 0; w < TILE_ROWS; ++w) {
+                    a_db2[u] += sm.t0[w * H2 + col];
+                    a_dg2[u] += sm.t1[w * H2 + col];
+                    a_dbe2[u] += sm.t2[w * H2 + col];
+                    const float hh = sm.t3[w * H2 + col];
+#pragma unroll
+                    for (int j = 0; j < A; ++j) a_dw3[j][u] = fmaf(sm.aux[w * 32 + j], hh, a_dw3[j][u]);
+                }
+            }
+            if (tid < A)
+                for (int w = 0; w < TILE_ROWS; ++w) a_db3 += sm.aux[w * 32 + tid];
+            __syncthreads();
+        }
+        const int P = gsize < nchunks ? gsize : nchunks;
+        if (grank < P) {
+            float *part = c.sc.PART_A + ((size_t)branch * P + grank) * ActorL::SMALL;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int col = tid + u * THREADS;
+                part[ActorL::small_index(ActorL::B2) + col] = a_db2[u];
+                part[ActorL::small_index(ActorL::G2) + col] = a_dg2[u];
+                part[ActorL::small_index(ActorL::BE2) + col] = a_dbe2[u];
+#pragma unroll
+                for (int j = 0; j < A; ++j) part[ActorL::small_index(ActorL::W3) + j * H2 + col] = a_dw3[j][u];
+            }
+            if (tid < 32) part[ActorL::small_index(ActorL::B3) + tid] = tid < A ? a_db3 : 0.f;
+        }
+    }
+    if (lane == 0) { sm.red[warp] = bc_sq; sm.red[8 + warp] = fire_sq; }
+    __syncthreads();
+    if (tid == 0) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int w = 0; w < WARPS; ++w) { s0 += sm.red[w]; s1 += sm.red[8 + w]; }
+        c.sc.LP[tm.rank * LP_WORDS + 3] = s0;
+        c.sc.LP[tm.rank * LP_WORDS + 4] = s1;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void stage_g7(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+    GemmJob jobs[MAX_JOBS];
+    int n = 0;
+    jobs[n++] = dw_job<ActorL>(c, P_A, st.mode == 0 ? P_AB : -1, c.g_actor);
+    jobs[n++] = dx_job<ActorL>(c, P_A, c.actor, c.ns[NS_G7DX]);
+    if (st.mode == 0) jobs[n++] = dx_job<ActorL>(c, P_AB, c.actor, c.ns[NS_G7DX]);
+    run_gemm_jobs(jobs, n, tm, smem);
+}
+__device__ __forceinline__ void stage_r7(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+    const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS;
+    const int gsize = tm.size >> 1, branch = tm.rank & 1, grank = tm.rank >> 1;
+    RowSmem sm = row_smem(smem);
+    if (grank < gsize && (branch == 0 || st.mode == 0)) {
+        Ln1Acc<ActorL> acc;
+        ln1_bwd_rows<ActorL>(c, c.actor, branch ? 3 : 2, c.ns[NS_G7DX], branch ? c.sc.XB : c.sc.X, branch ? BCW : ROW, grank, gsize, acc, sm, nullptr);
+        const int P = gsize < nchunks ? gsize : nchunks;
+        if (grank < P) ln1_write_partial<ActorL>(c.sc.PART_A + ((size_t)branch * P + grank) * ActorL::SMALL, acc);
+    }
+}
+__device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+    const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
+    const int P = gsize < nchunks ? gsize : nchunks;
+    const int nslots = st.mode == 0 ? 2 * P : P;
+    const float tau = c.tau, omt = (float)(1.0 - (double)c.tau);
+    adam_arena<ActorL>(tm, 1, c.actor, c.g_actor, c.m_actor, c.v_actor, c.sc.PART_A, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
+                       c.tactor, st.do_polyak != 0, tau, omt);
+    if (st.do_polyak) polyak_arena<CriticL>(tm, 2, c.critic, c.tcritic, tau, omt);
+    if (tm.rank == 0 && threadIdx.x == 0) {
+        const BcWeight bw = bc_weight_of(c, st, tm);
+        const float rl_loss = -(lp_sum(c, tm, 2) / (float)c.B);                           // HIRL.py:297
+        float bc_loss = 0.f, fire = 0.f;
+        if (st.mode == 0) {
+            bc_loss = __fmul_rn(lp_sum(c, tm, 3) / (float)(A * c.B), c.loss_lambda);       // HIRL.py:311
+            fire = lp_sum(c, tm, 4) / (float)c.B;                                          // HIRL.py:319 (x lambda on the host, in double)
+        }
+        c.carry[1] = __fadd_rn(__fmul_rn(bc_loss, bw.w), __fmul_rn(rl_loss, bw.one_minus_w));  // HIRL.py:321
+        c.carry[2] = bc_loss;
+        c.carry[3] = rl_loss;
+        c.carry[4] = fire;
+        c.carry[5] = bw.w;
+        c.carry[6] = bw.count;
+    }
+}
+
+// one full learn() call for one agent; returns true when the debug stop point was reached
+__device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm, float *smem, int stop_after) {
+    const hirl_step_t st = c.steps[step];
+#define HIRL_STAGE(id, call)                    \
+    call;                                       \
+    team_sync(tm);                              \
+    if (stop_after == (id)) return true;
+    HIRL_STAGE(ST_R0, stage_r0(c, st, step, tm))
+    HIRL_STAGE(ST_G1, stage_g1(c, st, tm, smem))
+    HIRL_STAGE(ST_R1, stage_r1(c, st, tm))
+    HIRL_STAGE(ST_G2, stage_g2(c, tm, smem))
+    HIRL_STAGE(ST_R2, stage_r2(c, st, tm, smem))
+    HIRL_STAGE(ST_G3, stage_g3(c, tm, smem))
+    HIRL_STAGE(ST_R3, stage_r3(c, tm, smem))
+    HIRL_STAGE(ST_G4, stage_g4(c, st, tm))
+    if (st.do_actor) {
+        HIRL_STAGE(ST_R4, stage_r4(c, st, tm))
+        HIRL_STAGE(ST_G5, stage_g5(c, st, tm, smem))
+        HIRL_STAGE(ST_R5, stage_r5(c, st, tm, smem))
+        HIRL_STAGE(ST_G6, stage_g6(c, tm, smem))
+        HIRL_STAGE(ST_R6, stage_r6(c, st, tm, smem))
+        HIRL_STAGE(ST_G7, stage_g7(c, st, tm, smem))
+        HIRL_STAGE(ST_R7, stage_r7(c, st, tm, smem))
+        HIRL_STAGE(ST_G8, stage_g8(c, st, tm))
+    }
+#undef HIRL_STAGE
+    if (tm.rank == 0 && threadIdx.x < HIRL_OUT_SCALARS) c.out_scalars[(size_t)step * HIRL_OUT_SCALARS + threadIdx.x] = c.carry[threadIdx.x];
+    return false;
+}
+
+}  // namespace hirl

@@ -298,7 +298,7 @@ class OracleAgent:
             Sb, Ab = bc_s_all[idx_bc], bc_a_all[idx_bc]
 
         # -- TD target (HIRL.py:264-274) ----------------------------------------------------
-        a_next = self.targetActor(S2)
+        a_next = self.targetActor(S2, rec, "ta.")
         if "noise" in forced:
             noise = torch.as_tensor(forced["noise"], dtype=torch.float32)
         else:
@@ -306,7 +306,7 @@ class OracleAgent:
         raw_noise = noise.clone()
         noise = noise.clamp(-self.TD3LearningNoiseClamp, self.TD3LearningNoiseClamp).to(self.dtype)
         a_next = (a_next + noise).clamp(-1, +1)
-        tq1, tq2 = self.targetCritic(S2, a_next)
+        tq1, tq2 = self.targetCritic(S2, a_next, rec, "tc.")
         tq_min = torch.min(tq1, tq2)
         y = R.reshape(-1, 1) + (self.gamma * tq_min * ((1 - D).reshape(-1, 1))).detach()
         self.last_draws = {"online": idx_on, "expert": idx_ex, "bc": idx_bc, "noise": raw_noise.numpy()}
@@ -317,7 +317,7 @@ class OracleAgent:
         self.critic.optimizer.zero_grad()
         self.critic_loss.backward()
         if rec is not None:
-            rec["y"] = y
+            rec["y"], rec["a_next"], rec["tq1"], rec["tq2"], rec["q1"], rec["q2"] = y, a_next, tq1, tq2, q1, q2
             rec["critic.grads"] = {k: p.grad.clone() for k, p in self.critic.named_parameters()}
             rec["S"], rec["A"], rec["S2"], rec["R"], rec["D"] = S, A, S2, R, D
         self.critic.optimizer.step()
@@ -327,12 +327,12 @@ class OracleAgent:
             if self.mode == "HIRL":
                 self.bc_weight = bc_weight_now
                 pi = self.actor(S, rec, "actor.")
-                rl_q = self.critic.onlyQ1(S, pi)
+                rl_q = self.critic.onlyQ1(S, pi, rec, "qp.")
                 self.rl_loss = -rl_q.mean()
                 if self.bc_weight == SOFT_SENTINEL:
                     with torch.no_grad():
-                        a_soft = self.bc_actor(S)
-                    soft_q = self.critic.onlyQ1(S, a_soft)
+                        a_soft = self.bc_actor(S, rec, "bc.")
+                    soft_q = self.critic.onlyQ1(S, a_soft, rec, "qs.")
                     w = (soft_q > rl_q).float().mean().detach().item()
                     if rec is not None:
                         rec["soft_q"], rec["rl_q"] = soft_q.detach(), rl_q.detach()
@@ -353,6 +353,9 @@ class OracleAgent:
             self.actor_loss.backward()
             if rec is not None:
                 rec["actor.grads"] = {k: p.grad.clone() for k, p in self.actor.named_parameters()}
+                rec["pi"] = pi
+                if self.mode == "HIRL":
+                    rec["pi_bc"], rec["rl_q_all"] = pi_bc, rl_q
                 rec["Sb"], rec["Ab"] = (Sb, Ab) if self.mode == "HIRL" else (None, None)
             self.actor.optimizer.step()
             self.update_count += 1
