@@ -91,6 +91,21 @@ __global__ void __launch_bounds__(THREADS) act_kernel(const float *net, const fl
     }
 }
 
+// register-resident FFMA chains: the FP32 roofline denominator (see hirl_measure_fp32_peak)
+__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, float a, float b) {
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = threadIdx.x * 1e-3f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
+    if (s == 123.456f) out[0] = s;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -639,6 +654,33 @@ int hirl_expert_scan(int device, const float *states13, const float *actions4, i
         i += d[i] ? 2 : 1;
     }
     *n_rows_out = kept;
+    return 0;
+}
+
+int hirl_measure_fp32_peak(int device, double *tflops_out) {
+    if (!tflops_out) return fail(HIRL_E_INVALID, "null argument");
+    CU(cudaSetDevice(device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    float *d = nullptr;
+    CU(cudaMalloc(&d, 4));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int iters = 1 << 14, blocks = sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU(cudaEventRecord(e0));
+        fma_peak_kernel<<<blocks, 256>>>(d, iters, 0.999f, 0.001f);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 16 * iters * 256.0 * blocks;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops_out = best;
     return 0;
 }
 

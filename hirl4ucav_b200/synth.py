@@ -53,3 +53,24 @@ def raw_states(rng: np.random.Generator, n: int) -> np.ndarray:
         raw[rng.integers(0, n, k), 1] = v
     raw[rng.integers(0, n, k), 14] = 0.0
     return raw
+
+
+def fill_agent(agent, n_online: int, n_expert_rows_hint: int = 0, data_seed: int = 1234, expert_states=None, expert_actions=None):
+    """Fills an agent's online ring with n_online self-consistent synthetic transitions (reward /
+    done / step_success from the offline reward kernel) and its expert ring from the expert table
+    (the batched form of train_all.py:287-306).  Everything numerical runs on the GPU."""
+    from .environments import harfang_math as hm
+    rng = np.random.default_rng(data_seed + 1)
+    s, a, s2 = env_states(rng, n_online), env_actions(rng, n_online), env_states(rng, n_online)
+    r, succ, done = hm.offline_reward(s, a, s2, agent.device.index)
+    rows = np.empty((n_online, 32), np.float32)
+    rows[:, 0:13], rows[:, 13:17], rows[:, 17:30] = s, a, s2
+    rows[:, 30], rows[:, 31] = r, done
+    agent.buffer.store_rows(rows, succ)
+    if expert_states is not None:
+        hm.fill_expert_buffer(agent, expert_states, expert_actions)
+
+
+def expert_table(n: int, data_seed: int = 1234):
+    rng = np.random.default_rng(data_seed)
+    return env_states(rng, n), env_actions(rng, n, expert=True)

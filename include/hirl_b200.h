@@ -168,6 +168,11 @@ int hirl_env_offline(int device, const float *s13, const float *a4, const float 
 int hirl_expert_scan(int device, const float *states13, const float *actions4, int n, float *out_rows32,
                      int8_t *out_success, int *n_rows_out);
 
+/* ---- measurement helper -----------------------------------------------------------------
+ * Register-resident FFMA loop on every SM, timed with CUDA events: the FP32-FMA roofline
+ * denominator for the batch-256 update (MEASURED_PEAKS.json has HBM and bf16 only). */
+int hirl_measure_fp32_peak(int device, double *tflops_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,293 @@
+"""GPU: the fused update through the C ABI against the oracle (torch fp32, bit-identical to the
+unmodified reference), its fp64 twin, and the reference's own frozen outputs.
+
+Tolerances (stated, fp32 path):
+  * replay/expert/BC index streams, noise stream, soft count: exact
+  * per-step teacher-forced losses / gradients / updated weights: rel-L2 <= 1e-5 against torch fp32
+    on ordinary steps.  A step where torch-fp32 itself is more than 3e-6 away from the fp64 twin
+    (a ReLU mask / soft-count tie flipped by summation order) is a "tie step": there
+    only the envelope  err(cuda, fp64) <= 4 * err(torch32, fp64) + 1e-7  is required.
+  * free-running drift: within 5x the natural fp32-vs-fp64 drift of the reference, same run.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from hirl4ucav_b200 import _lib
+from hirl4ucav_b200.agents.HIRL import Agent
+from hirl4ucav_b200.agents.TD3 import Agent as TD3Agent
+from oracle import scenarios
+from oracle.hirl_oracle import OracleActor, OracleAgent
+
+pytestmark = pytest.mark.gpu
+NETS = (("actor", 0), ("targetActor", 1), ("critic", 2), ("targetCritic", 3))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def grads_flat(rec, key):
+    return np.concatenate([v.double().reshape(-1).numpy() for v in rec[key].values()])
+
+
+def sync_to_oracle(ag, orc, o64=None):
+    """Teacher forcing: every implementation continues from the fp32 oracle's state."""
+    for w, _ in NETS + (("bc_actor", 4),):
+        if orc.nets().get(w) is None:
+            continue
+        getattr(ag, w).load_state_dict(orc.nets()[w].state_dict())
+        if o64 is not None:
+            o64.nets()[w].load_state_dict({k: t.double() for k, t in orc.nets()[w].state_dict().items()})
+    ag.push_parameters()
+    for w, nid in (("actor", _lib.NET_ACTOR), ("critic", _lib.NET_CRITIC)):
+        net = orc.nets()[w]
+        if net.optimizer.state:
+            m, v = orc.adam_state(w)
+            ag.import_adam(nid, m, v, ag._actor_t if w == "actor" else ag._critic_t)
+            if o64 is not None:
+                for p32, p64 in zip(net.parameters(), o64.nets()[w].parameters()):
+                    s32 = net.optimizer.state[p32]
+                    s64 = o64.nets()[w].optimizer.state[p64]
+                    s64["exp_avg"].copy_(s32["exp_avg"].double())
+                    s64["exp_avg_sq"].copy_(s32["exp_avg_sq"].double())
+
+
+def check_step(tag, got, ref32, ref64, tol=1e-5):
+    e_c32, e_c64, e_o64 = rel(got, ref32), rel(got, ref64), rel(ref32, ref64)
+    assert e_c64 <= 4 * e_o64 + 1e-7, f"{tag}: outside the fp32 envelope: cuda-f64 {e_c64:.2e} vs torch32-f64 {e_o64:.2e}"
+    if e_o64 <= 3e-6:
+        assert e_c32 <= tol, f"{tag}: rel-L2 {e_c32:.2e} vs torch fp32 (> {tol})"
+    return e_c32
+
+
+@pytest.mark.parametrize("B,bcw,en,steps", [(32, 100, 8, 12), (32, 0.5, 0, 12), (256, 100, 64, 12), (100, 100, 33, 6), (5, 0.3, 2, 6)])
+def test_teacher_forced_parity(B, bcw, en, steps):
+    sc = scenarios.make_scenario(max(1000, 4 * B), max(600, 3 * B))
+    orc = scenarios.build_agent(OracleAgent, sc, B, 0)
+    o64 = scenarios.build_agent(OracleAgent, sc, B, 0, dtype=torch.float64)
+    ag = scenarios.build_agent(Agent, sc, B, 0)
+    for w, nid in NETS + (("bc_actor", 4),):
+        assert np.array_equal(ag.export_flat(nid).astype(np.float64), orc.flat(w)), f"seeded init differs: {w}"
+    scenarios.seed_all(1)
+    worst = 0.0
+    for t in range(steps):
+        r32, r64 = {}, {}
+        actor_step = orc.actorTrainable
+        out32 = orc.learn(bcw, en, 0, rec=r32)
+        d = orc.last_draws
+        forced = {"online": d["online"], "expert": d["expert"], "bc": d["bc"], "noise": d["noise"]}
+        tie_count = actor_step and bcw == 100 and r32["soft_count_margin"] < 1e-5
+        if actor_step and bcw == 100:
+            forced64 = dict(forced)
+            out64 = o64.learn(bcw, en, 0, forced=forced64, rec=r64, force_soft_weight=out32[5])
+        else:
+            out64 = o64.learn(bcw, en, 0, forced=forced, rec=r64)
+        out = ag.learn(bcw, en, 0, forced=forced)
+        # scalars (HIRL.py:334)
+        for j, nm in enumerate(("critic_loss", "actor_loss", "bc_loss", "rl_loss")):
+            a, b, c = float(out[j]), float(out32[j]), float(out64[j])
+            assert abs(a - b) <= 1e-5 * abs(b) + 4 * abs(b - c) + 1e-6, f"step {t} {nm}: {a} vs {b}"
+        assert abs(out[4] - out32[4]) <= 1e-5 * abs(out32[4]) + 1e-6
+        if not tie_count:
+            assert out[5] == out32[5], f"step {t}: bc_weight {out[5]} vs {out32[5]}"    # soft count is exact
+        worst = max(worst, check_step(f"step {t} critic grads", ag.export_grads(_lib.NET_CRITIC), grads_flat(r32, "critic.grads"),
+                                      grads_flat(r64, "critic.grads")))
+        if actor_step and not tie_count:
+            worst = max(worst, check_step(f"step {t} actor grads", ag.export_grads(_lib.NET_ACTOR), grads_flat(r32, "actor.grads"),
+                                          grads_flat(r64, "actor.grads")))
+        if not tie_count:
+            for w, nid in NETS:
+                check_step(f"step {t} weights {w}", ag.export_flat(nid), orc.flat(w), o64.flat(w), tol=2e-6)
+        sync_to_oracle(ag, orc, o64)
+    print(f"B={B}: worst gradient rel-L2 vs torch fp32 over {steps} teacher-forced steps: {worst:.2e}")
+
+
+@pytest.mark.parametrize("name", ["soft32", "fixed32", "soft256"])
+def test_free_run_matches_reference_fixture(golden_dir, name):
+    """Same seeds as the unmodified reference: own RNG draws, own weights, 12 free-running calls."""
+    fx = np.load(os.path.join(golden_dir, f"agent_{name}.npz"))
+    B, steps, bcw, en = int(fx["batch"]), int(fx["steps"]), float(fx["bc_weight_now"]), int(fx["expert_num_now"])
+    sc = scenarios.make_scenario(int(fx["n_online"]), int(fx["n_expert"]))
+    ag = scenarios.build_agent(Agent, sc, B, int(fx["seed"]))
+    for w, nid in NETS + (("bc_actor", 4),):
+        assert float(ag.export_flat(nid).astype(np.float64).sum()) == float(fx[f"{w}.init_sum"])
+    scenarios.seed_all(int(fx["run_seed"]))
+    for t in range(steps):
+        out = ag.learn(bcw if bcw != 100 else 100, en, 0)
+        ref = fx["outs"][t]
+        assert np.array_equal(ag.last_draws["online"], fx["idx_online"][t]) and np.array_equal(ag.last_draws["noise"], fx["noise"][t])
+        for j in range(4):
+            assert abs(float(out[j]) - ref[j]) <= 2e-4 * abs(ref[j]) + 1e-5, f"step {t} out[{j}]: {float(out[j])} vs {ref[j]}"
+        assert abs(out[5] - ref[5]) <= 1.0 / B + 1e-12
+    for w, nid in NETS:
+        got = ag.export_flat(nid)[fx[f"{w}.probe_idx"]]
+        assert rel(got, fx[f"{w}.probe"]) <= 2e-4, w
+
+
+def test_learn_many_is_bit_identical_to_single_calls_and_deterministic():
+    sc = scenarios.make_scenario(2000, 600)
+    runs = []
+    for mode in ("single", "fused", "fused"):
+        ag = scenarios.build_agent(Agent, sc, 64, 3)
+        scenarios.seed_all(5)
+        if mode == "single":
+            outs = [ag.learn(100, 16, 0) for _ in range(12)]
+        else:
+            outs = ag.learn_many([(100, 16, 0)] * 12)
+        runs.append((np.array([[float(x) for x in o] for o in outs]), [ag.export_flat(nid) for _, nid in NETS]))
+    for other in runs[1:]:
+        assert np.array_equal(runs[0][0], other[0])
+        for a, b in zip(runs[0][1], other[1]):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("ns", ["1", "2", "4"])
+def test_split_k_variants_agree(ns, monkeypatch):
+    monkeypatch.setenv("HIRL_NSPLIT", ns)
+    sc = scenarios.make_scenario(1500, 600)
+    orc = scenarios.build_agent(OracleAgent, sc, 48, 0)
+    ag = scenarios.build_agent(Agent, sc, 48, 0)
+    scenarios.seed_all(2)
+    for t in range(6):
+        r32 = {}
+        ref = orc.learn(100, 10, 0, rec=r32)
+        d = orc.last_draws
+        out = ag.learn(100, 10, 0, forced={"online": d["online"], "expert": d["expert"], "bc": d["bc"], "noise": d["noise"]})
+        assert abs(float(out[0]) - float(ref[0])) <= 1e-5 * abs(float(ref[0]))
+        assert rel(ag.export_grads(_lib.NET_CRITIC), grads_flat(r32, "critic.grads")) <= 1e-5
+        sync_to_oracle(ag, orc)
+
+
+def test_target_update_schedule_matches_oracle():
+    sc = scenarios.make_scenario(1000, 600)
+    orc = scenarios.build_agent(OracleAgent, sc, 32, 0)
+    ag = scenarios.build_agent(Agent, sc, 32, 0)
+    scenarios.seed_all(4)
+    changed_o, changed_c = [], []
+    prev_o, prev_c = orc.flat("targetCritic").copy(), ag.export_flat(3).copy()
+    for t in range(12):
+        orc.learn(0.5, 4, 0)
+        d = orc.last_draws
+        ag.learn(0.5, 4, 0, forced={"online": d["online"], "expert": d["expert"], "bc": d["bc"], "noise": d["noise"]})
+        cur_o, cur_c = orc.flat("targetCritic"), ag.export_flat(3)
+        changed_o.append(not np.array_equal(cur_o, prev_o)); changed_c.append(not np.array_equal(cur_c, prev_c))
+        prev_o, prev_c = cur_o.copy(), cur_c.copy()
+        sync_to_oracle(ag, orc)
+    assert changed_o == changed_c and sum(changed_c) == 2
+    assert rel(ag.export_flat(3), orc.flat("targetCritic")) == 0.0 or rel(ag.export_flat(3), orc.flat("targetCritic")) < 1e-7
+
+
+def test_drift_envelope_300_steps():
+    B, steps = 256, 300
+    sc = scenarios.make_scenario(4000, 2000)
+    orc = scenarios.build_agent(OracleAgent, sc, B, 0)
+    o64 = scenarios.build_agent(OracleAgent, sc, B, 0, dtype=torch.float64)
+    ag = scenarios.build_agent(Agent, sc, B, 0)
+    scenarios.seed_all(9)
+    forced_all = []
+    marks = {}
+    for t in range(steps):
+        orc.learn(0.5, 64, 0)
+        d = orc.last_draws
+        f = {"online": d["online"], "expert": d["expert"], "bc": d["bc"], "noise": d["noise"]}
+        o64.learn(0.5, 64, 0, forced=f)
+        forced_all.append(f)
+        if t + 1 in (30, 100, 300):
+            marks[t + 1] = (orc.flat("critic").copy(), o64.flat("critic").copy(), orc.flat("actor").copy(), o64.flat("actor").copy())
+    done = 0
+    for t_mark in (30, 100, 300):
+        ag.learn_many([(0.5, 64, 0)] * (t_mark - done), forced=forced_all[done:t_mark])
+        done = t_mark
+        c32, c64, a32, a64 = marks[t_mark]
+        nat_c, nat_a = rel(c32, c64), rel(a32, a64)
+        got_c, got_a = rel(ag.export_flat(2), c64), rel(ag.export_flat(0), a64)
+        print(f"drift @{t_mark}: critic cuda-f64 {got_c:.2e} (torch32-f64 {nat_c:.2e}); actor {got_a:.2e} ({nat_a:.2e})")
+        assert got_c <= 5 * max(nat_c, 1e-5) and got_a <= 5 * max(nat_a, 1e-5)
+
+
+def test_checkpoints_interoperate_with_reference_shaped_modules(tmp_path):
+    sc = scenarios.make_scenario(800, 400)
+    ag = scenarios.build_agent(Agent, sc, 32, 0)
+    scenarios.seed_all(1)
+    ag.learn_many([(100, 8, 0)] * 6)
+    ag.saveCheckpoints("Agent7_", str(tmp_path))
+    sd = torch.load(str(tmp_path) + "\\Agent7_" + "Actor_Harfang_GYM")
+    assert list(sd) == ["full1.weight", "full1.bias", "layernorm1.weight", "layernorm1.bias", "full2.weight", "full2.bias",
+                        "layernorm2.weight", "layernorm2.bias", "final.weight", "final.bias"]
+    assert tuple(sd["full1.weight"].shape) == (256, 13) and tuple(sd["final.weight"].shape) == (4, 512)
+    ref_actor = OracleActor(1e-3, 13, 4, 256, 512, True, "x")
+    ref_actor.load_state_dict(sd)                      # loads into the reference-shaped module
+    s = sc["s"][:7]
+    want = ref_actor(torch.tensor(s, dtype=torch.float)).detach().numpy()
+    got = ag.act_batch(s)
+    assert np.abs(got - want).max() <= 2e-6
+    # round trip: a second agent restored from the files acts identically
+    ag2 = scenarios.build_agent(Agent, sc, 32, 1)
+    ag2.loadCheckpoints("Agent7_", str(tmp_path))
+    assert np.array_equal(ag2.act_batch(s), got)
+    for nid in range(4):
+        assert np.array_equal(ag2.export_flat(nid), ag.export_flat(nid))
+    # bc_actor file name = prefix + name (HIRL.py:180, 348)
+    torch.save(ref_actor.state_dict(), str(tmp_path) + "\\BC_" + "Harfang_GYM")
+    ag2.load_bc_actor("BC_", str(tmp_path))
+    assert np.array_equal(ag2.export_flat(4), ag.export_flat(0))
+    ag.save_training_state(str(tmp_path / "extra"))
+    ag2.load_training_state(str(tmp_path / "extra"))
+    assert ag2.update_count == ag.update_count and ag2._critic_t == ag._critic_t
+
+
+def test_choose_action_matches_oracle():
+    sc = scenarios.make_scenario(500, 300)
+    orc = scenarios.build_agent(OracleAgent, sc, 32, 0)
+    ag = scenarios.build_agent(Agent, sc, 32, 0)
+    s0 = sc["s"][11]
+    scenarios.seed_all(3)
+    want = [orc.chooseAction(s0), orc.chooseActionSmallNoise(s0), orc.chooseActionNoNoise(s0)]
+    scenarios.seed_all(3)
+    got = [ag.chooseAction(s0), ag.chooseActionSmallNoise(s0), ag.chooseActionNoNoise(s0)]
+    for g, w in zip(got, want):
+        assert g.shape == (4,) and g.dtype == np.float32 and np.abs(g - w).max() <= 1e-6
+    assert Agent.select_action is Agent.chooseAction and Agent.train is Agent.learn
+
+
+def test_td3_mode_matches_oracle():
+    sc = scenarios.make_scenario(2000, 300)
+    hp = scenarios.HP
+    scenarios.seed_all(0)
+    orc = OracleAgent(hp["actorLR"], hp["criticLR"], 13, 4, 256, 512, hp["tau"], hp["gamma"], 10 ** 5, 64, True, "Harfang_GYM",
+                      None, None, 0.0, False, mode="TD3")
+    scenarios.seed_all(0)
+    ag = TD3Agent(hp["actorLR"], hp["criticLR"], 13, 4, 256, 512, hp["tau"], hp["gamma"], 10 ** 5, 64, True, "Harfang_GYM")
+    for a in (orc, ag):
+        for i in range(2000):
+            a.store(sc["s"][i], sc["a"][i], sc["s2"][i], float(sc["r"][i]), bool(sc["d"][i]), int(sc["succ"][i]))
+    for w, nid in NETS:
+        assert np.array_equal(ag.export_flat(nid).astype(np.float64), orc.flat(w))
+    scenarios.seed_all(1)
+    for t in range(8):
+        r32 = {}
+        ref = orc.learn(rec=r32)
+        d = orc.last_draws
+        out = ag.learn(forced={"online": d["online"], "noise": d["noise"]})
+        assert abs(float(out[0]) - float(ref[0])) <= 1e-5 * abs(float(ref[0])) + 1e-6
+        assert abs(float(out[1]) - float(ref[1])) <= 1e-5 * abs(float(ref[1])) + 1e-6
+        assert rel(ag.export_grads(_lib.NET_CRITIC), grads_flat(r32, "critic.grads")) <= 1e-5
+        sync_to_oracle(ag, orc)
+
+
+def test_error_behaviour_matches_reference():
+    sc = scenarios.make_scenario(100, 80)
+    ag = scenarios.build_agent(Agent, sc, 32, 0)
+    with pytest.raises(TypeError):       # reference: Transition(*zip(*[])) when no online rows are drawn
+        ag.learn(0.5, 32, 0)
+    with pytest.raises(ValueError):      # reference: random.sample larger than population
+        scenarios.build_agent(Agent, scenarios.make_scenario(10, 80), 32, 0).learn(0.5, 0, 0)
+    with pytest.raises(NotImplementedError):
+        Agent(1e-3, 1e-3, 13, 4, 128, 128, 0.005, 0.99, 1000, 32, True, "x", sc["expert_states"], sc["expert_actions"], 0.5, True)
+    with pytest.raises(ValueError):      # np.random.choice(N, B, replace=False) with N < B
+        Agent(1e-3, 1e-3, 13, 4, 256, 512, 0.005, 0.99, 1000, 128, True, "x", sc["expert_states"][:50], sc["expert_actions"][:50],
+              0.5, True).learn(0.5, 0, 0)
