@@ -60,6 +60,7 @@ SYMBOLS = {
     "hirl_last_launch_count": (_i, [_vp]),
     "hirl_act": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "hirl_debug_stop_after": (_i, [_vp, _i]),
+    "hirl_debug_profile": (_i, [_vp, _i, _vp, _sz]),
     "hirl_debug_export": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_sz)]),
     "hirl_env_step_dev": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hirl_env_step": (_i, [_i, _vp, _i64, _vp, _vp, _vp, _vp]),

@@ -128,10 +128,11 @@ struct AgentCtx {
 
 struct LaunchCtx {
     AgentCtx agent;        // single-agent launch: the context travels as a kernel parameter
-    unsigned *bar_count;   // grid barrier arrival counter
-    unsigned *bar_gen;     // grid barrier generation
+    unsigned *bar_flags;   // [MAX_CTAS][32] barrier flags, zeroed before every launch
     int k_steps;
     int stop_after;        // debug: leave after this stage of step 0 (0 = never)
+    long long *prof;       // debug: [PROF_STEPS][ST_END][MAX_CTAS][2] SM-clock stamps (work done, barrier released)
 };
+constexpr int PROF_STEPS = 12;
 
 }  // namespace hirl

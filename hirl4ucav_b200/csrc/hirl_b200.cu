@@ -20,13 +20,19 @@ using namespace hirl;
 __global__ void __launch_bounds__(THREADS, 1) hirl_update_kernel(const __grid_constant__ LaunchCtx L) {
     extern __shared__ float4 smem4[];
     float *smem = reinterpret_cast<float *>(smem4);
-    const AgentCtx &ctx = L.agent;
-    Team tm;
-    tm.rank = blockIdx.x; tm.size = gridDim.x; tm.count = L.bar_count; tm.gen_ptr = L.bar_gen;
-    tm.gen = ld_acquire_u32(L.bar_gen);
+    // the context is read all over the (non-inlined) stage functions: keep it in shared memory,
+    // a generic-address load from the kernel-parameter window costs a global-memory round trip
+    __shared__ AgentCtx ctx;
+    {
+        const int *src = reinterpret_cast<const int *>(&L.agent);
+        int *dst = reinterpret_cast<int *>(&ctx);
+        for (int i = threadIdx.x; i < (int)(sizeof(AgentCtx) / sizeof(int)); i += THREADS) dst[i] = src[i];
+    }
     __syncthreads();
+    Team tm;
+    tm.rank = blockIdx.x; tm.size = gridDim.x; tm.flags = L.bar_flags; tm.gen = 0u;
     for (int step = 0; step < L.k_steps; ++step)
-        if (learn_step(ctx, step, tm, smem, step == 0 ? L.stop_after : 0)) return;
+        if (learn_step(ctx, step, tm, smem, step == 0 ? L.stop_after : 0, L.prof)) return;
 }
 
 // buffer.py:38-48 + HIRL.py:229-233 as a standalone op (the fused kernel gathers in stage R0)
@@ -132,6 +138,8 @@ struct hirl_agent {
     int32_t *d_ion = nullptr, *d_iex = nullptr, *d_ibc = nullptr;
     float *d_out = nullptr;
     int stop_after = 0, last_launches = 0;
+    long long *d_prof = nullptr;
+    bool prof_on = false;
     size_t scratch_elems[32];
 };
 
@@ -335,7 +343,7 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     if ((rc = dev_alloc(h, &h->d_ibc, K * B))) return rc;
     if ((rc = dev_alloc(h, &h->d_out, K * HIRL_OUT_SCALARS))) return rc;
     if ((rc = dev_alloc(h, &c.carry, 8))) return rc;
-    if ((rc = dev_alloc(h, &h->d_bar, 64))) return rc;
+    if ((rc = dev_alloc(h, &h->d_bar, (size_t)MAX_CTAS * FLAG_STRIDE))) return rc;
     *out = h;
     return 0;
 }
@@ -452,7 +460,9 @@ static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_de
     L.agent = h->h_ctx;
     AgentCtx &c = L.agent;
     c.steps = steps_dev; c.idx_online = ion; c.idx_expert = iex; c.idx_bc = ibc; c.out_scalars = out_dev;
-    L.bar_count = h->d_bar; L.bar_gen = h->d_bar + 32; L.k_steps = k_steps; L.stop_after = h->stop_after;
+    L.bar_flags = h->d_bar; L.k_steps = k_steps; L.stop_after = h->stop_after;
+    CU(cudaMemsetAsync(h->d_bar, 0, (size_t)MAX_CTAS * FLAG_STRIDE * sizeof(unsigned), stream));
+    L.prof = h->prof_on ? h->d_prof : nullptr;
     void *args[] = {&L};
     CU(cudaLaunchCooperativeKernel((void *)hirl_update_kernel, dim3(h->grid), dim3(THREADS), args, SMEM_BYTES, stream));
     h->last_launches = 1;
@@ -519,6 +529,21 @@ int hirl_act(hirl_agent_t *h, int replica, int net, const float *states13, int n
 int hirl_debug_stop_after(hirl_agent_t *h, int stage) {
     if (!h || stage < 0 || stage >= ST_END) return fail(HIRL_E_INVALID, "bad stage");
     h->stop_after = stage;
+    return 0;
+}
+int hirl_debug_profile(hirl_agent_t *h, int enable, long long *dst, size_t n) {
+    if (!h) return fail(HIRL_E_INVALID, "null handle");
+    const size_t cnt = (size_t)PROF_STEPS * ST_END * MAX_CTAS * 2;
+    CU(cudaSetDevice(h->cfg.device));
+    if (enable && !h->d_prof) {
+        if (int rc = dev_alloc(h, &h->d_prof, cnt)) return rc;
+    }
+    h->prof_on = enable != 0;
+    if (dst) {
+        if (n < cnt || !h->d_prof) return fail(HIRL_E_INVALID, "profile buffer not enabled or destination too small");
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaMemcpy(dst, h->d_prof, cnt * 8, cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 int hirl_debug_export(hirl_agent_t *h, int buffer_id, int pass, float *dst, size_t n, size_t *n_out) {

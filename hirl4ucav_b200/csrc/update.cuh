@@ -34,6 +34,19 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+#ifndef HIRL_TILE_LOAD_CG
+#define HIRL_TILE_LOAD_CG 0
+#endif
+// GEMM operand tiles: plain (L1-allocating, weak) loads by default.  Coherence is provided by
+// the team barrier (its acquire fence invalidates L1), so weak loads are safe and can be served
+// by the near L2 slice; -DHIRL_TILE_LOAD_CG=1 forces .cg (strong, home-slice) loads.
+__device__ __forceinline__ float4 ldtile4(const float *p) {
+#if HIRL_TILE_LOAD_CG
+    return ldcg4(p);
+#else
+    return ld4(p);
+#endif
+}
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 __device__ __forceinline__ float act_f(float pre, float slope) { return pre > 0.f ? pre : pre * slope; }
 __device__ __forceinline__ float act_g(float pre, float slope) { return pre > 0.f ? 1.f : slope; }
@@ -43,31 +56,48 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // A team is the set of CTAs that cooperate on one agent's update.
+constexpr int FLAG_STRIDE = 32;  // one 128 B line per CTA flag
 struct Team {
     int rank, size;
-    unsigned *count, *gen_ptr;
+    unsigned *flags;  // [size][FLAG_STRIDE], zeroed by the host before every launch
     unsigned gen;
 };
 
-// sense-reversing barrier over global memory; the acquire side invalidates this SM's L1 so
-// plain loads issued afterwards observe everything the other CTAs wrote before arriving.
+// All-to-all flag barrier: every CTA publishes its generation with one release store (no
+// atomics, no contended line) and warp 0 polls everybody's flag.  The trailing fence is the
+// acquire side: it also invalidates this SM's L1, so plain loads issued afterwards observe
+// everything the other CTAs wrote before arriving.
 __device__ __forceinline__ void team_sync(Team &t) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        unsigned arrived = atomicAdd(t.count, 1u);
-        if (arrived == (unsigned)t.size - 1u) {
-            atomicExch(t.count, 0u);
+    t.gen += 1u;
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) {
             __threadfence();
-            atomicAdd(t.gen_ptr, 1u);
-        } else {
-            while (ld_acquire_u32(t.gen_ptr) == t.gen) {
+            st_release_u32(t.flags + t.rank * FLAG_STRIDE, t.gen);
+        }
+        // all of this lane's flags are polled together (independent loads in flight)
+        bool pending = true;
+        while (pending) {
+            pending = false;
+#pragma unroll
+            for (int i = 0; i < (MAX_CTAS + 31) / 32; ++i) {
+                const int r = threadIdx.x + 32 * i;
+                if (r < t.size && (int)(ld_relaxed_u32(t.flags + r * FLAG_STRIDE) - t.gen) < 0) pending = true;
             }
+            pending = __any_sync(0xffffffffu, pending);
         }
         __threadfence();
     }
-    t.gen += 1u;
     __syncthreads();
 }
 
@@ -237,7 +267,7 @@ struct GemmJob {
 // operand whose reduction index is contiguous (row r = output index)
 __device__ __forceinline__ float4 load_kmajor(const float *P, int ld, int r0, int R, int k0, int K, int tid) {
     const int r = r0 + (tid >> 2), k = k0 + 4 * (tid & 3);
-    if (r < R && k < K) return ldcg4(P + (size_t)r * ld + k);
+    if (r < R && k < K) return ldtile4(P + (size_t)r * ld + k);
     return make_float4(0.f, 0.f, 0.f, 0.f);
 }
 __device__ __forceinline__ void store_kmajor(float *T, float4 v, int tid) {
@@ -250,7 +280,7 @@ __device__ __forceinline__ void store_kmajor(float *T, float4 v, int tid) {
 // operand whose output index is contiguous (row = reduction index)
 __device__ __forceinline__ float4 load_rmajor(const float *P, int ld, int c0, int Cn, int k0, int K, int tid) {
     const int k = k0 + (tid >> 4), c = c0 + 4 * (tid & 15);
-    if (k < K && c < Cn) return ldcg4(P + (size_t)k * ld + c);
+    if (k < K && c < Cn) return ldtile4(P + (size_t)k * ld + c);
     return make_float4(0.f, 0.f, 0.f, 0.f);
 }
 __device__ __forceinline__ void store_rmajor(float *T, float4 v, int tid) { st4(T + (tid >> 4) * TS + 4 * (tid & 15), v); }
@@ -284,17 +314,7 @@ __device__ __forceinline__ void gemm_tile(const GemmJob &J, int tm, int tn, int 
         else store_rmajor(Bs + buf * 16 * TS, rb, tid);
     };
 
-    float4 ra, rb;
-    __syncthreads();  // previous user of this shared memory is done
-    if (kt_begin < kt_end) {
-        fetch(kt_begin, ra, rb);
-        stash(0, ra, rb);
-    }
-    __syncthreads();
-    for (int kt = kt_begin; kt < kt_end; ++kt) {
-        const int buf = (kt - kt_begin) & 1;
-        const bool more = kt + 1 < kt_end;
-        if (more) fetch(kt + 1, ra, rb);
+    auto compute = [&](int buf) {
         const float *a = As + buf * 16 * TS + ty * 4, *b = Bs + buf * 16 * TS + tx * 4;
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
@@ -305,7 +325,26 @@ __device__ __forceinline__ void gemm_tile(const GemmJob &J, int tm, int tn, int 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
         }
-        if (more) stash(buf ^ 1, ra, rb);
+    };
+    // register prefetch two k-tiles ahead, double-buffered shared memory: a k-tile's global loads
+    // get two full compute iterations to land (L2 round trips are ~0.5 us on this part).
+    float4 ra0, rb0, ra1, rb1;
+    __syncthreads();  // previous user of this shared memory is done
+    if (kt_begin < kt_end) {
+        fetch(kt_begin, ra0, rb0);
+        stash(0, ra0, rb0);
+        if (kt_begin + 1 < kt_end) fetch(kt_begin + 1, ra1, rb1);
+    }
+    __syncthreads();
+    for (int kt = kt_begin; kt < kt_end; kt += 2) {
+        if (kt + 2 < kt_end) fetch(kt + 2, ra0, rb0);
+        compute(0);
+        if (kt + 1 < kt_end) stash(1, ra1, rb1);
+        __syncthreads();
+        if (kt + 1 >= kt_end) break;
+        if (kt + 3 < kt_end) fetch(kt + 3, ra1, rb1);
+        compute(1);
+        if (kt + 2 < kt_end) stash(0, ra0, rb0);
         __syncthreads();
     }
     // epilogue
@@ -359,17 +398,22 @@ __device__ __forceinline__ float *DH1p(const AgentCtx &c, int slot) { return c.s
 __device__ __forceinline__ int g1_split(const AgentCtx &c, const hirl_step_t &st) { return c.ns[st.do_actor ? NS_G1_ACTOR : NS_G1]; }
 __device__ __forceinline__ float slope_of(const AgentCtx &c) { return c.activation == HIRL_ACT_LEAKY_RELU ? 0.01f : 0.f; }
 
-// fixed-order sum of one word of the per-CTA partial block
-__device__ __forceinline__ float lp_sum(const AgentCtx &c, const Team &tm, int word) {
+// fixed-order sum of one word of the per-CTA partial block, evaluated by one full warp
+// (lane l adds ranks l, l+32, ... in order, then a fixed butterfly): deterministic, and the
+// loads of all ranks are in flight together instead of one L2 round trip per rank.
+// parity: -1 all ranks, 0 even ranks only, 1 odd ranks only.
+__device__ __forceinline__ float lp_sum(const AgentCtx &c, const Team &tm, int word, int parity = -1) {
+    const int lane = threadIdx.x & 31;
     float s = 0.f;
-    for (int r = 0; r < tm.size; ++r) s += __ldcg(c.sc.LP + r * LP_WORDS + word);
-    return s;
+    for (int r = lane; r < tm.size; r += 32)
+        if (parity < 0 || (r & 1) == parity) s += c.sc.LP[r * LP_WORDS + word];
+    return warp_sum(s);
 }
 
 // ---------------------------------------------------------------------------------------------
 // R0: gather + first layers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_r0(const AgentCtx &c, const hirl_step_t &st, int step, const Team &tm) {
+__device__ __noinline__ void stage_r0(const AgentCtx &c, const hirl_step_t &st, int step, const Team &tm) {
     const int B = c.B, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
     const float slope = slope_of(c);
@@ -458,7 +502,7 @@ __device__ __forceinline__ GemmJob dw_job(const AgentCtx &c, int pass, int pass2
     return J;
 }
 
-__device__ __forceinline__ void stage_g1(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+__device__ __noinline__ void stage_g1(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
     int n = 0;
     const int ns = g1_split(c, st);
@@ -478,7 +522,7 @@ __device__ __forceinline__ void stage_g1(const AgentCtx &c, const hirl_step_t &s
 // ---------------------------------------------------------------------------------------------
 // R1: target-actor head -> a' -> first layers of the target critic; actor-side heads
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_r1(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+__device__ __noinline__ void stage_r1(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
     const int B = c.B, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
     const float slope = slope_of(c);
@@ -517,7 +561,7 @@ __device__ __forceinline__ void stage_r1(const AgentCtx &c, const hirl_step_t &s
     }
 }
 
-__device__ __forceinline__ void stage_g2(const AgentCtx &c, const Team &tm, float *smem) {
+__device__ __noinline__ void stage_g2(const AgentCtx &c, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
     jobs[0] = fwd_job<CriticL>(c, P_TC1, c.tcritic, c.ns[NS_G2]);
     jobs[1] = fwd_job<CriticL>(c, P_TC2, c.tcritic + CriticL::SIZE, c.ns[NS_G2]);
@@ -542,7 +586,7 @@ __device__ __forceinline__ RowSmem row_smem(float *smem) {
 // R2: TD target (HIRL.py:270-274), critic heads, loss (HIRL.py:284), backward to dz2
 //   CTAs are split into two groups, one per critic tower.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_r2(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+__device__ __noinline__ void stage_r2(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
     const int B = c.B, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
     const float slope = slope_of(c);
@@ -631,7 +675,7 @@ __device__ __forceinline__ void stage_r2(const AgentCtx &c, const hirl_step_t &s
     __syncthreads();
 }
 
-__device__ __forceinline__ void stage_g3(const AgentCtx &c, const Team &tm, float *smem) {
+__device__ __noinline__ void stage_g3(const AgentCtx &c, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
     jobs[0] = dw_job<CriticL>(c, P_C1, -1, c.g_critic);
     jobs[1] = dw_job<CriticL>(c, P_C2, -1, c.g_critic + CriticL::SIZE);
@@ -729,7 +773,7 @@ __device__ __forceinline__ void ln1_write_partial(float *part, const Ln1Acc<L> &
     }
 }
 
-__device__ __forceinline__ void stage_r3(const AgentCtx &c, const Team &tm, float *smem) {
+__device__ __noinline__ void stage_r3(const AgentCtx &c, const Team &tm, float *smem) {
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS;
     const int gsize = tm.size >> 1, tower = tm.rank & 1, grank = tm.rank >> 1;
     RowSmem sm = row_smem(smem);
@@ -783,19 +827,15 @@ __device__ __forceinline__ void polyak_arena(const Team &tm, int ntowers, const 
         target[e] = polyak_elem(target[e], w[e], tau, one_minus_tau);
 }
 
-__device__ __forceinline__ void stage_g4(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+__device__ __noinline__ void stage_g4(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
     const int P = gsize < nchunks ? gsize : nchunks;
     adam_arena<CriticL>(tm, 2, c.critic, c.g_critic, c.m_critic, c.v_critic, c.sc.PART_C, 2, P, st.critic_neg_step,
                         st.critic_bc2_sqrt, nullptr, false, 0.f, 0.f);
-    if (tm.rank == 0 && threadIdx.x == 0) {
+    if (tm.rank == tm.size - 1 && threadIdx.x < 32) {
         // critic_loss = mse(Q1,y) + mse(Q2,y): even ranks hold tower 0, odd ranks tower 1
-        float s0 = 0.f, s1 = 0.f;
-        for (int r = 0; r < tm.size; ++r) {
-            const float v = __ldcg(c.sc.LP + r * LP_WORDS + 0);
-            if (r & 1) s1 += v; else s0 += v;
-        }
-        c.carry[0] = __fadd_rn(s0 / (float)c.B, s1 / (float)c.B);
+        const float s0 = lp_sum(c, tm, 0, 0), s1 = lp_sum(c, tm, 0, 1);
+        if (threadIdx.x == 0) c.carry[0] = __fadd_rn(s0 / (float)c.B, s1 / (float)c.B);
     }
 }
 
@@ -803,7 +843,7 @@ __device__ __forceinline__ void stage_g4(const AgentCtx &c, const hirl_step_t &s
 // actor phase
 // ---------------------------------------------------------------------------------------------
 // R4: first layers of Q1(s, pi(s)) and Q1(s, a_bc) with the updated critic (HIRL.py:296, 302)
-__device__ __forceinline__ void stage_r4(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+__device__ __noinline__ void stage_r4(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
     const int B = c.B, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
     const float slope = slope_of(c);
@@ -826,7 +866,7 @@ __device__ __forceinline__ void stage_r4(const AgentCtx &c, const hirl_step_t &s
             l1_row<CriticL>(c.critic, x, slope, lane, H1p(c, P_QS) + (size_t)b * H1, nullptr, nullptr);
     }
 }
-__device__ __forceinline__ void stage_g5(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+__device__ __noinline__ void stage_g5(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
     int n = 0;
     jobs[n++] = fwd_job<CriticL>(c, P_QP, c.critic, c.ns[NS_G5]);
@@ -835,7 +875,7 @@ __device__ __forceinline__ void stage_g5(const AgentCtx &c, const hirl_step_t &s
 }
 // R5: Q heads, soft count (HIRL.py:303), rl_loss partial (HIRL.py:297), backward of Q1(s,pi) with
 // the unit upstream gradient -1/B; the (1-w) factor is applied where it meets the actor (R6).
-__device__ __forceinline__ void stage_r5(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+__device__ __noinline__ void stage_r5(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
     const int B = c.B, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
     const float slope = slope_of(c);
@@ -877,13 +917,14 @@ __device__ __forceinline__ void stage_r5(const AgentCtx &c, const hirl_step_t &s
     }
     __syncthreads();
 }
-__device__ __forceinline__ void stage_g6(const AgentCtx &c, const Team &tm, float *smem) {
+__device__ __noinline__ void stage_g6(const AgentCtx &c, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
     jobs[0] = dx_job<CriticL>(c, P_QP, c.critic, c.ns[NS_G6]);
     run_gemm_jobs(jobs, 1, tm, smem);
 }
 
 // the behaviour-cloning weight of this call (HIRL.py:292-308), evaluated identically by every CTA
+// (call with a full warp: the soft count is a warp-collective sum)
 struct BcWeight { float w, one_minus_w, count; };
 __device__ __forceinline__ BcWeight bc_weight_of(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
     BcWeight r;
@@ -903,15 +944,15 @@ __device__ __forceinline__ BcWeight bc_weight_of(const AgentCtx &c, const hirl_s
 
 // R6: group 0: d pi from the critic, actor head backward on batch states (rl branch);
 //     group 1: BC loss (HIRL.py:310-311) and actor head backward on expert states.
-__device__ __forceinline__ void stage_r6(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+__device__ __noinline__ void stage_r6(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
     const int B = c.B, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
     const float slope = slope_of(c);
     const int gsize = tm.size >> 1, branch = tm.rank & 1, grank = tm.rank >> 1;
     RowSmem sm = row_smem(smem);
-    if (tid == 0) {
-        const BcWeight b0 = bc_weight_of(c, st, tm);
-        sm.red[32] = b0.w; sm.red[33] = b0.one_minus_w;
+    if (tid < 32) {
+        const BcWeight b0 = bc_weight_of(c, st, tm);   // warp-collective
+        if (tid == 0) { sm.red[32] = b0.w; sm.red[33] = b0.one_minus_w; }
     }
     __syncthreads();
     BcWeight bw;
@@ -1009,7 +1050,7 @@ __device__ __forceinline__ void stage_r6(const AgentCtx &c, const hirl_step_t &s
     }
     __syncthreads();
 }
-__device__ __forceinline__ void stage_g7(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+__device__ __noinline__ void stage_g7(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
     int n = 0;
     jobs[n++] = dw_job<ActorL>(c, P_A, st.mode == 0 ? P_AB : -1, c.g_actor);
@@ -1017,7 +1058,7 @@ __device__ __forceinline__ void stage_g7(const AgentCtx &c, const hirl_step_t &s
     if (st.mode == 0) jobs[n++] = dx_job<ActorL>(c, P_AB, c.actor, c.ns[NS_G7DX]);
     run_gemm_jobs(jobs, n, tm, smem);
 }
-__device__ __forceinline__ void stage_r7(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+__device__ __noinline__ void stage_r7(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS;
     const int gsize = tm.size >> 1, branch = tm.rank & 1, grank = tm.rank >> 1;
     RowSmem sm = row_smem(smem);
@@ -1028,7 +1069,7 @@ __device__ __forceinline__ void stage_r7(const AgentCtx &c, const hirl_step_t &s
         if (grank < P) ln1_write_partial<ActorL>(c.sc.PART_A + ((size_t)branch * P + grank) * ActorL::SMALL, acc);
     }
 }
-__device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+__device__ __noinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
     const int P = gsize < nchunks ? gsize : nchunks;
     const int nslots = st.mode == 0 ? 2 * P : P;
@@ -1036,7 +1077,7 @@ __device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &s
     adam_arena<ActorL>(tm, 1, c.actor, c.g_actor, c.m_actor, c.v_actor, c.sc.PART_A, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
                        c.tactor, st.do_polyak != 0, tau, omt);
     if (st.do_polyak) polyak_arena<CriticL>(tm, 2, c.critic, c.tcritic, tau, omt);
-    if (tm.rank == 0 && threadIdx.x == 0) {
+    if (tm.rank == tm.size - 1 && threadIdx.x < 32) {
         const BcWeight bw = bc_weight_of(c, st, tm);
         const float rl_loss = -(lp_sum(c, tm, 2) / (float)c.B);                           // HIRL.py:297
         float bc_loss = 0.f, fire = 0.f;
@@ -1044,21 +1085,33 @@ __device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &s
             bc_loss = __fmul_rn(lp_sum(c, tm, 3) / (float)(A * c.B), c.loss_lambda);       // HIRL.py:311
             fire = lp_sum(c, tm, 4) / (float)c.B;                                          // HIRL.py:319 (x lambda on the host, in double)
         }
+        if (threadIdx.x == 0) {
         c.carry[1] = __fadd_rn(__fmul_rn(bc_loss, bw.w), __fmul_rn(rl_loss, bw.one_minus_w));  // HIRL.py:321
         c.carry[2] = bc_loss;
         c.carry[3] = rl_loss;
         c.carry[4] = fire;
         c.carry[5] = bw.w;
         c.carry[6] = bw.count;
+        }
     }
 }
 
 // one full learn() call for one agent; returns true when the debug stop point was reached
-__device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm, float *smem, int stop_after) {
-    const hirl_step_t st = c.steps[step];
-#define HIRL_STAGE(id, call)                    \
-    call;                                       \
-    team_sync(tm);                              \
+__device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm, float *smem, int stop_after, long long *prof) {
+    __shared__ hirl_step_t st;
+    if (threadIdx.x < (int)(sizeof(hirl_step_t) / sizeof(int)))
+        reinterpret_cast<int *>(&st)[threadIdx.x] = reinterpret_cast<const int *>(c.steps + step)[threadIdx.x];
+    __syncthreads();
+    if (prof && step >= PROF_STEPS) prof = nullptr;
+    if (prof) {
+        prof += ((size_t)step * ST_END * MAX_CTAS + tm.rank) * 2;
+        if (threadIdx.x == 0) prof[1] = clock64();   // stage 0 slot: step start
+    }
+#define HIRL_STAGE(id, call)                                                            \
+    call;                                                                               \
+    if (prof && threadIdx.x == 0) prof[(size_t)(id) * MAX_CTAS * 2] = clock64();        \
+    team_sync(tm);                                                                      \
+    if (prof && threadIdx.x == 0) prof[(size_t)(id) * MAX_CTAS * 2 + 1] = clock64();    \
     if (stop_after == (id)) return true;
     HIRL_STAGE(ST_R0, stage_r0(c, st, step, tm))
     HIRL_STAGE(ST_G1, stage_g1(c, st, tm, smem))
@@ -1079,7 +1132,7 @@ __device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm
         HIRL_STAGE(ST_G8, stage_g8(c, st, tm))
     }
 #undef HIRL_STAGE
-    if (tm.rank == 0 && threadIdx.x < HIRL_OUT_SCALARS) c.out_scalars[(size_t)step * HIRL_OUT_SCALARS + threadIdx.x] = c.carry[threadIdx.x];
+    if (tm.rank == tm.size - 1 && threadIdx.x < HIRL_OUT_SCALARS) c.out_scalars[(size_t)step * HIRL_OUT_SCALARS + threadIdx.x] = c.carry[threadIdx.x];
     return false;
 }
 

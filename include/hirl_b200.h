@@ -146,6 +146,10 @@ int hirl_debug_stop_after(hirl_agent_t *h, int stage);
 /* copy a scratch buffer to the host; returns its element count in *n_out when dst==NULL */
 int hirl_debug_export(hirl_agent_t *h, int buffer_id, int pass, float *dst, size_t n, size_t *n_out);
 
+/* per-stage SM-clock stamps of the first 12 steps of a launch: [12][17 stages][160 CTAs][2]
+ * (work finished, barrier released); enable!=0 switches recording on, dst!=NULL copies out */
+int hirl_debug_profile(hirl_agent_t *h, int enable, long long *dst, size_t n);
+
 /* ---- Harfang env math (hirl/environments/HarfangEnv_GYM.py) ----------------------------
  * raw state = 16 words: p_ally[3] e_ally[3] p_opp[3] e_opp[3] target_angle_deg health
  * action_fire flags(u32: b0 locked_prev b1 locked_now b2 missile_prev b3 missile_now
