@@ -100,6 +100,7 @@ struct Scratch {
     float *PART_C;   // [MAX_CTAS][2][CriticL::SMALL]
     float *PART_A;   // [MAX_CTAS][ActorL::SMALL]
     float *LP;       // [MAX_CTAS][LP_WORDS]
+    float *GW2B;     // [H2][H1] actor dW2 of the expert-state branch
 };
 
 // Everything one replica's update needs.  Passed to the kernel by value (per-replica array in

@@ -244,7 +244,7 @@ static double stage_makespan(const std::vector<JobShape> &jobs, int ns, int ctas
     int t = 0;
     for (const JobShape &j : jobs) {
         const int n = j.splittable ? j.tiles * ns : j.tiles;
-        const double c = j.splittable ? j.cost / ns + 1.0 : j.cost + 1.0;  // +1: per-tile prologue/epilogue
+        const double c = j.splittable ? j.cost / ns + 2.0 : j.cost + 2.0;  // +2: per-tile prologue/epilogue
         for (int i = 0; i < n; ++i, ++t) load[t % ctas] += c;
     }
     return *std::max_element(load.begin(), load.end());
@@ -254,7 +254,7 @@ static int pick_split(const std::vector<JobShape> &jobs, int ctas, int forced) {
     int best = 1;
     double best_t = 1e300;
     for (int ns = 1; ns <= MAX_SPLIT; ns *= 2) {
-        const double t = stage_makespan(jobs, ns, ctas) * (1.0 + 0.05 * (ns - 1));  // partial-sum traffic penalty
+        const double t = stage_makespan(jobs, ns, ctas) * (1.0 + 0.03 * (ns - 1));  // partial-sum traffic penalty
         if (t < best_t - 1e-9) { best_t = t; best = ns; }
     }
     return best;
@@ -305,7 +305,7 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     c.ns[NS_G3DX] = pick_split({{32, kb, false}, {32, kb, false}, dx, dx}, h->grid, forced);
     c.ns[NS_G5] = pick_split({fwd, fwd}, h->grid, forced);
     c.ns[NS_G6] = pick_split({dx}, h->grid, forced);
-    c.ns[NS_G7DX] = pick_split({{32, 2 * kb, false}, dx, dx}, h->grid, forced);
+    c.ns[NS_G7DX] = pick_split({{32, kb, false}, {32, kb, false}, dx, dx}, h->grid, forced);
     c.zsplit = 1;
     for (int i = 0; i < NS_COUNT; ++i) c.zsplit = std::max(c.zsplit, c.ns[i]);
 
@@ -334,6 +334,7 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     SCR(Y, DB_Y, B) SCR(Q, DB_Q, 2 * B) SCR(TQ, DB_TQ, 2 * B) SCR(RLQ, DB_RLQ, B) SCR(SOFTQ, DB_SOFTQ, B)
     SCR(LP, DB_LP, (size_t)MAX_CTAS * LP_WORDS)
 #undef SCR
+    if ((rc = dev_alloc(h, &s.GW2B, (size_t)H2 * H1))) return rc;
     if ((rc = dev_alloc(h, &s.PART_C, (size_t)MAX_CTAS * 2 * CriticL::SMALL))) return rc;
     if ((rc = dev_alloc(h, &s.PART_A, (size_t)MAX_CTAS * ActorL::SMALL))) return rc;
     const size_t K = cfg->max_steps;

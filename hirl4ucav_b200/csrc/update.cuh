@@ -258,9 +258,9 @@ __device__ __forceinline__ void ln1_backward(const float *tw, const float (&dh)[
 // ---------------------------------------------------------------------------------------------
 enum { GEMM_NT = 0, GEMM_NN = 1, GEMM_TN = 2 };
 struct GemmJob {
-    const float *A, *B, *A2, *B2, *bias;
+    const float *A, *B, *bias;
     float *C;
-    int lda, ldb, ldc, M, N, K, K2, mode, nsplit;
+    int lda, ldb, ldc, M, N, K, mode, nsplit;
     size_t csplit;  // element stride between split-K partial outputs
 };
 
@@ -285,78 +285,80 @@ __device__ __forceinline__ float4 load_rmajor(const float *P, int ld, int c0, in
 }
 __device__ __forceinline__ void store_rmajor(float *T, float4 v, int tid) { st4(T + (tid >> 4) * TS + 4 * (tid & 15), v); }
 
+// One 64x64 output tile over k-tiles [kt_begin, kt_end).  Deliberately a small stand-alone
+// function with scalar arguments: inlined into the big stage functions the register allocator
+// spilled the prefetch registers, which exposed a full L2 round trip per k-tile.
 template <int MODE>
-__device__ __forceinline__ void gemm_tile(const GemmJob &J, int tm, int tn, int split, float *smem) {
+__device__ __noinline__ void gemm_tile(const float *__restrict__ Ap, int lda, const float *__restrict__ Bp, int ldb, float *__restrict__ C,
+                                       int ldc, const float *__restrict__ bias, int M, int N, int K, int m0, int n0, int kt_begin,
+                                       int kt_end, float *smem) {
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = tm * 64, n0 = tn * 64;
     float *As = smem, *Bs = smem + 2 * 16 * TS;
-    const int nk1 = (J.K + 15) >> 4, nk2 = (J.K2 + 15) >> 4, nk = nk1 + nk2;
-    const int kt_begin = (int)(((long long)nk * split) / J.nsplit), kt_end = (int)(((long long)nk * (split + 1)) / J.nsplit);
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    auto fetch = [&](int kt, float4 &ra, float4 &rb) {
-        const bool second = kt >= nk1;
-        const float *Ap = second ? J.A2 : J.A, *Bp = second ? J.B2 : J.B;
-        const int K = second ? J.K2 : J.K, k0 = (second ? kt - nk1 : kt) << 4;
-        if (MODE == GEMM_TN) ra = load_rmajor(Ap, J.lda, m0, J.M, k0, K, tid);
-        else ra = load_kmajor(Ap, J.lda, m0, J.M, k0, K, tid);
-        if (MODE == GEMM_NT) rb = load_kmajor(Bp, J.ldb, n0, J.N, k0, K, tid);
-        else rb = load_rmajor(Bp, J.ldb, n0, J.N, k0, K, tid);
-    };
-    auto stash = [&](int buf, const float4 &ra, const float4 &rb) {
-        if (MODE == GEMM_TN) store_rmajor(As + buf * 16 * TS, ra, tid);
-        else store_kmajor(As + buf * 16 * TS, ra, tid);
-        if (MODE == GEMM_NT) store_kmajor(Bs + buf * 16 * TS, rb, tid);
-        else store_rmajor(Bs + buf * 16 * TS, rb, tid);
-    };
-
-    auto compute = [&](int buf) {
-        const float *a = As + buf * 16 * TS + ty * 4, *b = Bs + buf * 16 * TS + tx * 4;
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            const float4 av = ld4(a + kk * TS), bv = ld4(b + kk * TS);
-            const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
-        }
-    };
+#define HIRL_FETCH(kt, ra, rb)                                                                                      \
+    {                                                                                                               \
+        const int k0_ = (kt) << 4;                                                                                  \
+        ra = (MODE == GEMM_TN) ? load_rmajor(Ap, lda, m0, M, k0_, K, tid) : load_kmajor(Ap, lda, m0, M, k0_, K, tid); \
+        rb = (MODE == GEMM_NT) ? load_kmajor(Bp, ldb, n0, N, k0_, K, tid) : load_rmajor(Bp, ldb, n0, N, k0_, K, tid); \
+    }
+#define HIRL_STASH(buf, ra, rb)                                                      \
+    {                                                                                \
+        if (MODE == GEMM_TN) store_rmajor(As + (buf) * 16 * TS, ra, tid);            \
+        else store_kmajor(As + (buf) * 16 * TS, ra, tid);                            \
+        if (MODE == GEMM_NT) store_kmajor(Bs + (buf) * 16 * TS, rb, tid);            \
+        else store_rmajor(Bs + (buf) * 16 * TS, rb, tid);                            \
+    }
+#define HIRL_COMPUTE(buf)                                                                        \
+    {                                                                                            \
+        const float *a_ = As + (buf) * 16 * TS + ty * 4, *b_ = Bs + (buf) * 16 * TS + tx * 4;    \
+        float4 av = ld4(a_), bv = ld4(b_);                                                       \
+        _Pragma("unroll") for (int kk = 0; kk < 16; ++kk) {                                      \
+            float4 an = av, bn = bv;                                                             \
+            if (kk + 1 < 16) { an = ld4(a_ + (kk + 1) * TS); bn = ld4(b_ + (kk + 1) * TS); }     \
+            const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};      \
+            _Pragma("unroll") for (int i = 0; i < 4; ++i)                                        \
+                _Pragma("unroll") for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]); \
+            av = an; bv = bn;                                                                    \
+        }                                                                                        \
+    }
     // register prefetch two k-tiles ahead, double-buffered shared memory: a k-tile's global loads
-    // get two full compute iterations to land (L2 round trips are ~0.5 us on this part).
+    // get two full compute iterations to land.
     float4 ra0, rb0, ra1, rb1;
     __syncthreads();  // previous user of this shared memory is done
     if (kt_begin < kt_end) {
-        fetch(kt_begin, ra0, rb0);
-        stash(0, ra0, rb0);
-        if (kt_begin + 1 < kt_end) fetch(kt_begin + 1, ra1, rb1);
+        HIRL_FETCH(kt_begin, ra0, rb0)
+        HIRL_STASH(0, ra0, rb0)
+        if (kt_begin + 1 < kt_end) HIRL_FETCH(kt_begin + 1, ra1, rb1)
     }
     __syncthreads();
     for (int kt = kt_begin; kt < kt_end; kt += 2) {
-        if (kt + 2 < kt_end) fetch(kt + 2, ra0, rb0);
-        compute(0);
-        if (kt + 1 < kt_end) stash(1, ra1, rb1);
+        if (kt + 2 < kt_end) HIRL_FETCH(kt + 2, ra0, rb0)
+        HIRL_COMPUTE(0)
+        if (kt + 1 < kt_end) HIRL_STASH(1, ra1, rb1)
         __syncthreads();
         if (kt + 1 >= kt_end) break;
-        if (kt + 3 < kt_end) fetch(kt + 3, ra1, rb1);
-        compute(1);
-        if (kt + 2 < kt_end) stash(0, ra0, rb0);
+        if (kt + 3 < kt_end) HIRL_FETCH(kt + 3, ra1, rb1)
+        HIRL_COMPUTE(1)
+        if (kt + 2 < kt_end) HIRL_STASH(0, ra0, rb0)
         __syncthreads();
     }
+#undef HIRL_FETCH
+#undef HIRL_STASH
+#undef HIRL_COMPUTE
     // epilogue
-    float *C = J.C + (size_t)split * J.csplit;
     const int n = n0 + tx * 4;
-    if (n < J.N) {
-        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (J.bias && split == 0) bias = ld4(J.bias + n);
+    if (n < N) {
+        float4 bv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) bv4 = ld4(bias + n);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int m = m0 + ty * 4 + i;
-            if (m < J.M) st4(C + (size_t)m * J.ldc + n, make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w));
+            if (m < M) st4(C + (size_t)m * ldc + n, make_float4(acc[i][0] + bv4.x, acc[i][1] + bv4.y, acc[i][2] + bv4.z, acc[i][3] + bv4.w));
         }
     }
 }
@@ -379,9 +381,13 @@ __device__ __forceinline__ void run_gemm_jobs(const GemmJob *jobs, int njobs, co
         const int split = local / (ntm * ntn);
         local -= split * ntm * ntn;
         const int tmi = local / ntn, tni = local - tmi * ntn;
-        if (J.mode == GEMM_NT) gemm_tile<GEMM_NT>(J, tmi, tni, split, smem);
-        else if (J.mode == GEMM_NN) gemm_tile<GEMM_NN>(J, tmi, tni, split, smem);
-        else gemm_tile<GEMM_TN>(J, tmi, tni, split, smem);
+        const int nk = (J.K + 15) >> 4;
+        const int kb = (int)(((long long)nk * split) / J.nsplit), ke = (int)(((long long)nk * (split + 1)) / J.nsplit);
+        float *Cs = J.C + (size_t)split * J.csplit;
+        const float *bias = split == 0 ? J.bias : nullptr;
+        if (J.mode == GEMM_NT) gemm_tile<GEMM_NT>(J.A, J.lda, J.B, J.ldb, Cs, J.ldc, bias, J.M, J.N, J.K, tmi * 64, tni * 64, kb, ke, smem);
+        else if (J.mode == GEMM_NN) gemm_tile<GEMM_NN>(J.A, J.lda, J.B, J.ldb, Cs, J.ldc, bias, J.M, J.N, J.K, tmi * 64, tni * 64, kb, ke, smem);
+        else gemm_tile<GEMM_TN>(J.A, J.lda, J.B, J.ldb, Cs, J.ldc, bias, J.M, J.N, J.K, tmi * 64, tni * 64, kb, ke, smem);
     }
 }
 
@@ -466,7 +472,6 @@ __device__ __forceinline__ GemmJob fwd_job(const AgentCtx &c, int pass, const fl
     GemmJob J;
     J.A = H1p(c, pass); J.lda = H1;
     J.B = tw + L::W2; J.ldb = H1;
-    J.A2 = J.B2 = nullptr; J.K2 = 0;
     J.bias = tw + L::B2;
     J.C = Z2p(c, pass); J.ldc = H2;
     J.M = c.B; J.N = H2; J.K = H1;
@@ -479,7 +484,6 @@ __device__ __forceinline__ GemmJob dx_job(const AgentCtx &c, int pass, const flo
     GemmJob J;
     J.A = Z2p(c, pass); J.lda = H2;
     J.B = tw + L::W2; J.ldb = H1;
-    J.A2 = J.B2 = nullptr; J.K2 = 0;
     J.bias = nullptr;
     J.C = DH1p(c, bwd_slot(pass)); J.ldc = H1;
     J.M = c.B; J.N = H1; J.K = H2;
@@ -488,15 +492,13 @@ __device__ __forceinline__ GemmJob dx_job(const AgentCtx &c, int pass, const flo
 }
 // dW2 = dZ2[pass]^T . H1[pass]  (+ second branch)
 template <class L>
-__device__ __forceinline__ GemmJob dw_job(const AgentCtx &c, int pass, int pass2, float *gtw) {
+__device__ __forceinline__ GemmJob dw_job(const AgentCtx &c, int pass, float *dst) {
     GemmJob J;
     J.A = Z2p(c, pass); J.lda = H2;
     J.B = H1p(c, pass); J.ldb = H1;
     J.K = c.B;
-    if (pass2 >= 0) { J.A2 = Z2p(c, pass2); J.B2 = H1p(c, pass2); J.K2 = c.B; }
-    else { J.A2 = J.B2 = nullptr; J.K2 = 0; }
     J.bias = nullptr;
-    J.C = gtw + L::W2; J.ldc = H1;
+    J.C = dst; J.ldc = H1;
     J.M = H2; J.N = H1;
     J.mode = GEMM_TN; J.nsplit = 1; J.csplit = 0;
     return J;
@@ -677,8 +679,8 @@ __device__ __noinline__ void stage_r2(const AgentCtx &c, const hirl_step_t &st, 
 
 __device__ __noinline__ void stage_g3(const AgentCtx &c, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
-    jobs[0] = dw_job<CriticL>(c, P_C1, -1, c.g_critic);
-    jobs[1] = dw_job<CriticL>(c, P_C2, -1, c.g_critic + CriticL::SIZE);
+    jobs[0] = dw_job<CriticL>(c, P_C1, c.g_critic + CriticL::W2);
+    jobs[1] = dw_job<CriticL>(c, P_C2, c.g_critic + CriticL::SIZE + CriticL::W2);
     jobs[2] = dx_job<CriticL>(c, P_C1, c.critic, c.ns[NS_G3DX]);
     jobs[3] = dx_job<CriticL>(c, P_C2, c.critic + CriticL::SIZE, c.ns[NS_G3DX]);
     run_gemm_jobs(jobs, 4, tm, smem);
@@ -799,7 +801,7 @@ __device__ __forceinline__ float polyak_elem(float t, float p, float tau, float 
 }
 
 template <class L>
-__device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w, float *gw, float *m, float *v, const float *part,
+__device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w, float *gw, const float *gw2b, float *m, float *v, const float *part,
                                            int part_towers, int nslots, float neg_step, float bc2_sqrt, float *target, bool polyak,
                                            float tau, float one_minus_tau) {
     const int total = ntowers * L::SIZE;
@@ -808,6 +810,7 @@ __device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w
         float g;
         if (off >= L::W2 && off < L::B2) {
             g = __ldcg(gw + e);
+            if (gw2b) { g += __ldcg(gw2b + (off - L::W2)); gw[e] = g; }
         } else {
             const int si = L::small_index(off);
             g = 0.f;
@@ -830,7 +833,7 @@ __device__ __forceinline__ void polyak_arena(const Team &tm, int ntowers, const 
 __device__ __noinline__ void stage_g4(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
     const int P = gsize < nchunks ? gsize : nchunks;
-    adam_arena<CriticL>(tm, 2, c.critic, c.g_critic, c.m_critic, c.v_critic, c.sc.PART_C, 2, P, st.critic_neg_step,
+    adam_arena<CriticL>(tm, 2, c.critic, c.g_critic, nullptr, c.m_critic, c.v_critic, c.sc.PART_C, 2, P, st.critic_neg_step,
                         st.critic_bc2_sqrt, nullptr, false, 0.f, 0.f);
     if (tm.rank == tm.size - 1 && threadIdx.x < 32) {
         // critic_loss = mse(Q1,y) + mse(Q2,y): even ranks hold tower 0, odd ranks tower 1
@@ -1053,7 +1056,9 @@ __device__ __noinline__ void stage_r6(const AgentCtx &c, const hirl_step_t &st, 
 __device__ __noinline__ void stage_g7(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
     int n = 0;
-    jobs[n++] = dw_job<ActorL>(c, P_A, st.mode == 0 ? P_AB : -1, c.g_actor);
+    // the two branches' dW2 go to separate buffers (twice the tiles in flight); Adam adds them
+    jobs[n++] = dw_job<ActorL>(c, P_A, c.g_actor + ActorL::W2);
+    if (st.mode == 0) jobs[n++] = dw_job<ActorL>(c, P_AB, c.sc.GW2B);
     jobs[n++] = dx_job<ActorL>(c, P_A, c.actor, c.ns[NS_G7DX]);
     if (st.mode == 0) jobs[n++] = dx_job<ActorL>(c, P_AB, c.actor, c.ns[NS_G7DX]);
     run_gemm_jobs(jobs, n, tm, smem);
@@ -1074,7 +1079,7 @@ __device__ __noinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, 
     const int P = gsize < nchunks ? gsize : nchunks;
     const int nslots = st.mode == 0 ? 2 * P : P;
     const float tau = c.tau, omt = (float)(1.0 - (double)c.tau);
-    adam_arena<ActorL>(tm, 1, c.actor, c.g_actor, c.m_actor, c.v_actor, c.sc.PART_A, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
+    adam_arena<ActorL>(tm, 1, c.actor, c.g_actor, st.mode == 0 ? c.sc.GW2B : nullptr, c.m_actor, c.v_actor, c.sc.PART_A, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
                        c.tactor, st.do_polyak != 0, tau, omt);
     if (st.do_polyak) polyak_arena<CriticL>(tm, 2, c.critic, c.tcritic, tau, omt);
     if (tm.rank == tm.size - 1 && threadIdx.x < 32) {
