@@ -136,4 +136,12 @@ struct LaunchCtx {
 };
 constexpr int PROF_STEPS = 12;
 
+// Ensemble launch: R independent replicas processed by n_teams teams of team_size CTAs; replica r is
+// handled by team r % n_teams (its AgentCtx.sc points at that team's scratch).
+struct EnsembleLaunch {
+    const AgentCtx *agents;  // [replicas] in global memory
+    unsigned *bar_flags;     // [n_teams][team_size][32]
+    int replicas, n_teams, team_size, k_steps;
+};
+
 }  // namespace hirl

@@ -35,6 +35,28 @@ __global__ void __launch_bounds__(THREADS, 1) hirl_update_kernel(const __grid_co
         if (learn_step(ctx, step, tm, smem, step == 0 ? L.stop_after : 0, L.prof)) return;
 }
 
+// Ensemble form (BASELINE config 4): the grid is cut into teams of team_size CTAs; every team runs
+// whole replicas (k_steps learn() calls each) with team-local barriers, so replicas never wait for
+// each other and no CTA idles while another replica has tiles left.
+__global__ void __launch_bounds__(THREADS, 1) hirl_ensemble_kernel(const __grid_constant__ EnsembleLaunch L) {
+    extern __shared__ float4 smem4[];
+    float *smem = reinterpret_cast<float *>(smem4);
+    __shared__ AgentCtx ctx;
+    const int team = blockIdx.x / L.team_size;
+    if (team >= L.n_teams) return;
+    Team tm;
+    tm.rank = blockIdx.x % L.team_size; tm.size = L.team_size;
+    tm.flags = L.bar_flags + (size_t)team * L.team_size * FLAG_STRIDE; tm.gen = 0u;
+    for (int r = team; r < L.replicas; r += L.n_teams) {
+        __syncthreads();
+        const int *src = reinterpret_cast<const int *>(L.agents + r);
+        int *dst = reinterpret_cast<int *>(&ctx);
+        for (int i = threadIdx.x; i < (int)(sizeof(AgentCtx) / sizeof(int)); i += THREADS) dst[i] = src[i];
+        __syncthreads();
+        for (int step = 0; step < L.k_steps; ++step) learn_step(ctx, step, tm, smem, 0, nullptr);
+    }
+}
+
 // buffer.py:38-48 + HIRL.py:229-233 as a standalone op (the fused kernel gathers in stage R0)
 __global__ void gather_kernel(const float *__restrict__ online, const float *__restrict__ expert, const int32_t *__restrict__ idx_on,
                               int n_on, const int32_t *__restrict__ idx_ex, int n_ex, float *__restrict__ out) {
@@ -131,9 +153,12 @@ struct hirl_agent {
     int sm_count = 0, grid = 0;
     cudaStream_t stream = nullptr;
     std::vector<void *> allocs;
-    AgentCtx h_ctx;            // replica 0 (ensembles: array, later)
+    std::vector<AgentCtx> ctxs;          // one per replica (ctxs[r].sc = scratch of team r % n_teams)
+    std::vector<float *> online, expert;  // per-replica replay tables
+    AgentCtx *d_ctxs = nullptr;           // device copy of ctxs (ensemble launches)
+    int n_teams = 1, team_size = 0;       // replicas > 1: teams of team_size CTAs
     unsigned *d_bar = nullptr;
-    float *online = nullptr, *expert = nullptr, *bctab = nullptr;
+    float *bctab = nullptr;               // expert (s,a) table, shared read-only by all replicas
     hirl_step_t *d_steps = nullptr;
     int32_t *d_ion = nullptr, *d_iex = nullptr, *d_ibc = nullptr;
     float *d_out = nullptr;
@@ -194,8 +219,9 @@ static_assert(tower_flat<ActorL>() == HIRL_ACTOR_PARAMS, "actor flat size");
 static_assert(2 * tower_flat<CriticL>() == HIRL_CRITIC_PARAMS, "critic flat size");
 
 static bool is_critic(int net) { return net == HIRL_NET_CRITIC || net == HIRL_NET_TARGET_CRITIC; }
-static int net_ptr(hirl_agent *h, int net, int kind /*0 w,1 g,2 m,3 v*/, float **out) {
-    AgentCtx &c = h->h_ctx;
+static int net_ptr(hirl_agent *h, int replica, int net, int kind /*0 w,1 g,2 m,3 v*/, float **out) {
+    if (replica < 0 || replica >= (int)h->ctxs.size()) return fail(HIRL_E_INVALID, "replica index out of range");
+    AgentCtx &c = h->ctxs[replica];
     float *p = nullptr;
     if (kind == 0) p = net == HIRL_NET_ACTOR ? c.actor : net == HIRL_NET_TARGET_ACTOR ? c.tactor : net == HIRL_NET_CRITIC ? c.critic
                    : net == HIRL_NET_TARGET_CRITIC ? c.tcritic : net == HIRL_NET_BC_ACTOR ? c.bc : nullptr;
@@ -205,9 +231,9 @@ static int net_ptr(hirl_agent *h, int net, int kind /*0 w,1 g,2 m,3 v*/, float *
     *out = p;
     return 0;
 }
-static int flat_import(hirl_agent *h, int net, int kind, const float *src, size_t n) {
+static int flat_import(hirl_agent *h, int replica, int net, int kind, const float *src, size_t n) {
     float *d;
-    if (int rc = net_ptr(h, net, kind, &d)) return rc;
+    if (int rc = net_ptr(h, replica, net, kind, &d)) return rc;
     const bool cr = is_critic(net);
     if (n != (cr ? (size_t)HIRL_CRITIC_PARAMS : (size_t)HIRL_ACTOR_PARAMS)) return fail(HIRL_E_INVALID, "flat parameter vector has the wrong length");
     std::vector<float> tmp(cr ? CRITIC_SIZE : ACTOR_SIZE);
@@ -220,9 +246,9 @@ static int flat_import(hirl_agent *h, int net, int kind, const float *src, size_
     CU(cudaMemcpy(d, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
     return 0;
 }
-static int flat_export(hirl_agent *h, int net, int kind, float *dst, size_t n) {
+static int flat_export(hirl_agent *h, int replica, int net, int kind, float *dst, size_t n) {
     float *d;
-    if (int rc = net_ptr(h, net, kind, &d)) return rc;
+    if (int rc = net_ptr(h, replica, net, kind, &d)) return rc;
     const bool cr = is_critic(net);
     if (n != (cr ? (size_t)HIRL_CRITIC_PARAMS : (size_t)HIRL_ACTOR_PARAMS)) return fail(HIRL_E_INVALID, "flat parameter vector has the wrong length");
     std::vector<float> tmp(cr ? CRITIC_SIZE : ACTOR_SIZE);
@@ -269,7 +295,7 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     if (!cfg || !out) return fail(HIRL_E_INVALID, "null argument");
     if (cfg->batch < 1 || cfg->online_capacity < 1 || cfg->expert_capacity < 1 || cfg->bc_rows < 0 || cfg->max_steps < 1)
         return fail(HIRL_E_INVALID, "batch/capacities/max_steps must be positive");
-    if (cfg->replicas != 1) return fail(HIRL_E_UNSUPPORTED, "replicas != 1: use the ensemble entry points");
+    if (cfg->replicas < 1 || cfg->replicas > 4096) return fail(HIRL_E_INVALID, "replicas must be in [1, 4096]");
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(HIRL_E_INVALID, "no such CUDA device");
@@ -288,63 +314,88 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     if (const char *g = getenv("HIRL_GRID")) h->grid = std::max(2, std::min(h->grid, atoi(g)) & ~1);
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 
-    AgentCtx &c = h->h_ctx;
-    std::memset(&c, 0, sizeof(c));
+    const int R = cfg->replicas;
     const size_t B = cfg->batch;
-    c.B = cfg->batch;
-    c.activation = cfg->activation;
-    c.gamma = cfg->gamma; c.tau = cfg->tau; c.noise_clamp = cfg->noise_clamp; c.loss_lambda = cfg->loss_lambda;
+    int team_ctas = h->grid;  // CTAs that cooperate on one agent
+    if (R > 1) {
+        h->team_size = getenv("HIRL_TEAM") ? std::max(2, atoi(getenv("HIRL_TEAM")) & ~1) : 8;
+        h->team_size = std::min(h->team_size, h->grid);
+        h->n_teams = std::min(h->grid / h->team_size, R);
+        team_ctas = h->team_size;
+    }
+    AgentCtx proto;
+    std::memset(&proto, 0, sizeof(proto));
+    proto.B = cfg->batch;
+    proto.activation = cfg->activation;
+    proto.gamma = cfg->gamma; proto.tau = cfg->tau; proto.noise_clamp = cfg->noise_clamp; proto.loss_lambda = cfg->loss_lambda;
     // split-K factors (unit = one 64x64 output tile over the layer's full K)
     const int forced = getenv("HIRL_NSPLIT") ? atoi(getenv("HIRL_NSPLIT")) : 0;
     const int tm = (cfg->batch + 63) / 64;
     const double kb = std::ceil(cfg->batch / 16.0);                  // k-tiles of a batch-long reduction
     const JobShape fwd{tm * 8, 16.0, true}, dx{tm * 4, 32.0, true};  // K=256 / K=512 in 16-wide k-tiles
-    c.ns[NS_G1] = pick_split({fwd, fwd, fwd}, h->grid, forced);
-    c.ns[NS_G1_ACTOR] = pick_split({fwd, fwd, fwd, fwd, fwd, fwd}, h->grid, forced);
-    c.ns[NS_G2] = pick_split({fwd, fwd}, h->grid, forced);
-    c.ns[NS_G3DX] = pick_split({{32, kb, false}, {32, kb, false}, dx, dx}, h->grid, forced);
-    c.ns[NS_G5] = pick_split({fwd, fwd}, h->grid, forced);
-    c.ns[NS_G6] = pick_split({dx}, h->grid, forced);
-    c.ns[NS_G7DX] = pick_split({{32, kb, false}, {32, kb, false}, dx, dx}, h->grid, forced);
-    c.zsplit = 1;
-    for (int i = 0; i < NS_COUNT; ++i) c.zsplit = std::max(c.zsplit, c.ns[i]);
+    proto.ns[NS_G1] = pick_split({fwd, fwd, fwd}, team_ctas, forced);
+    proto.ns[NS_G1_ACTOR] = pick_split({fwd, fwd, fwd, fwd, fwd, fwd}, team_ctas, forced);
+    proto.ns[NS_G2] = pick_split({fwd, fwd}, team_ctas, forced);
+    proto.ns[NS_G3DX] = pick_split({{32, kb, false}, {32, kb, false}, dx, dx}, team_ctas, forced);
+    proto.ns[NS_G5] = pick_split({fwd, fwd}, team_ctas, forced);
+    proto.ns[NS_G6] = pick_split({dx}, team_ctas, forced);
+    proto.ns[NS_G7DX] = pick_split({{32, kb, false}, {32, kb, false}, dx, dx}, team_ctas, forced);
+    proto.zsplit = 1;
+    for (int i = 0; i < NS_COUNT; ++i) proto.zsplit = std::max(proto.zsplit, proto.ns[i]);
 
     int rc = 0;
-    float *arena = nullptr;
-    const size_t arena_n = 6 * (size_t)ACTOR_SIZE + 5 * (size_t)CRITIC_SIZE;
-    if ((rc = dev_alloc(h, &arena, arena_n))) return rc;
-    float *p = arena;
-    c.actor = p; p += ACTOR_SIZE; c.tactor = p; p += ACTOR_SIZE; c.bc = p; p += ACTOR_SIZE;
-    c.g_actor = p; p += ACTOR_SIZE; c.m_actor = p; p += ACTOR_SIZE; c.v_actor = p; p += ACTOR_SIZE;
-    c.critic = p; p += CRITIC_SIZE; c.tcritic = p; p += CRITIC_SIZE;
-    c.g_critic = p; p += CRITIC_SIZE; c.m_critic = p; p += CRITIC_SIZE; c.v_critic = p; p += CRITIC_SIZE;
-    if ((rc = dev_alloc(h, &h->online, (size_t)cfg->online_capacity * ROW))) return rc;
-    if ((rc = dev_alloc(h, &h->expert, (size_t)cfg->expert_capacity * ROW))) return rc;
     if ((rc = dev_alloc(h, &h->bctab, (size_t)std::max(cfg->bc_rows, 1) * BCW))) return rc;
-    c.online = h->online; c.expert = h->expert; c.bctab = h->bctab;
-    Scratch &s = c.sc;
+    // scratch: one set per team
+    std::vector<Scratch> team_sc(h->n_teams);
     size_t *se = h->scratch_elems;
+    for (int t = 0; t < h->n_teams; ++t) {
+        Scratch &s = team_sc[t];
 #define SCR(field, id, n)                                        \
     if ((rc = dev_alloc(h, &s.field, (n)))) return rc;            \
     se[id] = (n);
-    SCR(X, DB_X, B * ROW) SCR(XB, DB_XB, B * BCW)
-    SCR(H1, DB_H1, (size_t)N_PASS * B * H1) SCR(XH1, DB_XH1, (size_t)N_BWD * B * H1) SCR(RS1, DB_RS1, (size_t)N_BWD * B)
-    SCR(Z2, DB_Z2, (size_t)N_PASS * c.zsplit * B * H2) SCR(DH1, DB_DH1, (size_t)N_BWD * c.zsplit * B * H1)
-    SCR(APRIME, DB_APRIME, B * A) SCR(PI, DB_PI, B * A) SCR(PIB, DB_PIB, B * A) SCR(ABC, DB_ABC, B * A) SCR(GPI, DB_GPI, B * A)
-    SCR(Y, DB_Y, B) SCR(Q, DB_Q, 2 * B) SCR(TQ, DB_TQ, 2 * B) SCR(RLQ, DB_RLQ, B) SCR(SOFTQ, DB_SOFTQ, B)
-    SCR(LP, DB_LP, (size_t)MAX_CTAS * LP_WORDS)
+        SCR(X, DB_X, B * ROW) SCR(XB, DB_XB, B * BCW)
+        SCR(H1, DB_H1, (size_t)N_PASS * B * H1) SCR(XH1, DB_XH1, (size_t)N_BWD * B * H1) SCR(RS1, DB_RS1, (size_t)N_BWD * B)
+        SCR(Z2, DB_Z2, (size_t)N_PASS * proto.zsplit * B * H2) SCR(DH1, DB_DH1, (size_t)N_BWD * proto.zsplit * B * H1)
+        SCR(APRIME, DB_APRIME, B * A) SCR(PI, DB_PI, B * A) SCR(PIB, DB_PIB, B * A) SCR(ABC, DB_ABC, B * A) SCR(GPI, DB_GPI, B * A)
+        SCR(Y, DB_Y, B) SCR(Q, DB_Q, 2 * B) SCR(TQ, DB_TQ, 2 * B) SCR(RLQ, DB_RLQ, B) SCR(SOFTQ, DB_SOFTQ, B)
+        SCR(LP, DB_LP, (size_t)MAX_CTAS * LP_WORDS)
 #undef SCR
-    if ((rc = dev_alloc(h, &s.GW2B, (size_t)H2 * H1))) return rc;
-    if ((rc = dev_alloc(h, &s.PART_C, (size_t)MAX_CTAS * 2 * CriticL::SMALL))) return rc;
-    if ((rc = dev_alloc(h, &s.PART_A, (size_t)MAX_CTAS * ActorL::SMALL))) return rc;
-    const size_t K = cfg->max_steps;
+        const int slots = R > 1 ? h->team_size : MAX_CTAS;
+        if ((rc = dev_alloc(h, &s.GW2B, (size_t)H2 * H1))) return rc;
+        if ((rc = dev_alloc(h, &s.PART_C, (size_t)slots * 2 * CriticL::SMALL))) return rc;
+        if ((rc = dev_alloc(h, &s.PART_A, (size_t)slots * ActorL::SMALL))) return rc;
+    }
+    // per-replica state: parameter arena, replay tables, carried scalars
+    h->ctxs.assign(R, proto);
+    h->online.assign(R, nullptr);
+    h->expert.assign(R, nullptr);
+    const size_t arena_n = 6 * (size_t)ACTOR_SIZE + 5 * (size_t)CRITIC_SIZE;
+    for (int r = 0; r < R; ++r) {
+        AgentCtx &c = h->ctxs[r];
+        float *arena = nullptr;
+        if ((rc = dev_alloc(h, &arena, arena_n))) return rc;
+        float *p = arena;
+        c.actor = p; p += ACTOR_SIZE; c.tactor = p; p += ACTOR_SIZE; c.bc = p; p += ACTOR_SIZE;
+        c.g_actor = p; p += ACTOR_SIZE; c.m_actor = p; p += ACTOR_SIZE; c.v_actor = p; p += ACTOR_SIZE;
+        c.critic = p; p += CRITIC_SIZE; c.tcritic = p; p += CRITIC_SIZE;
+        c.g_critic = p; p += CRITIC_SIZE; c.m_critic = p; p += CRITIC_SIZE; c.v_critic = p; p += CRITIC_SIZE;
+        if ((rc = dev_alloc(h, &h->online[r], (size_t)cfg->online_capacity * ROW))) return rc;
+        if ((rc = dev_alloc(h, &h->expert[r], (size_t)cfg->expert_capacity * ROW))) return rc;
+        c.online = h->online[r]; c.expert = h->expert[r]; c.bctab = h->bctab;
+        c.sc = team_sc[r % h->n_teams];
+        if ((rc = dev_alloc(h, &c.carry, 8))) return rc;
+    }
+    const size_t K = (size_t)cfg->max_steps * R;
     if ((rc = dev_alloc(h, &h->d_steps, K))) return rc;
     if ((rc = dev_alloc(h, &h->d_ion, K * B))) return rc;
     if ((rc = dev_alloc(h, &h->d_iex, K * B))) return rc;
     if ((rc = dev_alloc(h, &h->d_ibc, K * B))) return rc;
     if ((rc = dev_alloc(h, &h->d_out, K * HIRL_OUT_SCALARS))) return rc;
-    if ((rc = dev_alloc(h, &c.carry, 8))) return rc;
     if ((rc = dev_alloc(h, &h->d_bar, (size_t)MAX_CTAS * FLAG_STRIDE))) return rc;
+    if (R > 1) {
+        if ((rc = dev_alloc(h, &h->d_ctxs, (size_t)R))) return rc;
+        CU(cudaFuncSetAttribute(hirl_ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    }
     *out = h;
     return 0;
 }
@@ -360,34 +411,34 @@ int hirl_agent_destroy(hirl_agent_t *h) {
 int hirl_agent_sm_count(hirl_agent_t *h) { return h ? h->grid : 0; }
 
 int hirl_params_import(hirl_agent_t *h, int replica, int net, const float *src, size_t n) {
-    if (!h || !src || replica != 0) return fail(HIRL_E_INVALID, "bad handle/replica");
-    return flat_import(h, net, 0, src, n);
+    if (!h || !src) return fail(HIRL_E_INVALID, "null argument");
+    return flat_import(h, replica, net, 0, src, n);
 }
 int hirl_params_export(hirl_agent_t *h, int replica, int net, float *dst, size_t n) {
-    if (!h || !dst || replica != 0) return fail(HIRL_E_INVALID, "bad handle/replica");
-    return flat_export(h, net, 0, dst, n);
+    if (!h || !dst) return fail(HIRL_E_INVALID, "null argument");
+    return flat_export(h, replica, net, 0, dst, n);
 }
 int hirl_adam_import(hirl_agent_t *h, int replica, int net, const float *m, const float *v, size_t n) {
-    if (!h || !m || !v || replica != 0) return fail(HIRL_E_INVALID, "bad handle/replica");
-    if (int rc = flat_import(h, net, 2, m, n)) return rc;
-    return flat_import(h, net, 3, v, n);
+    if (!h || !m || !v) return fail(HIRL_E_INVALID, "null argument");
+    if (int rc = flat_import(h, replica, net, 2, m, n)) return rc;
+    return flat_import(h, replica, net, 3, v, n);
 }
 int hirl_adam_export(hirl_agent_t *h, int replica, int net, float *m, float *v, size_t n) {
-    if (!h || !m || !v || replica != 0) return fail(HIRL_E_INVALID, "bad handle/replica");
-    if (int rc = flat_export(h, net, 2, m, n)) return rc;
-    return flat_export(h, net, 3, v, n);
+    if (!h || !m || !v) return fail(HIRL_E_INVALID, "null argument");
+    if (int rc = flat_export(h, replica, net, 2, m, n)) return rc;
+    return flat_export(h, replica, net, 3, v, n);
 }
 int hirl_grads_export(hirl_agent_t *h, int replica, int net, float *dst, size_t n) {
-    if (!h || !dst || replica != 0) return fail(HIRL_E_INVALID, "bad handle/replica");
-    return flat_export(h, net, 1, dst, n);
+    if (!h || !dst) return fail(HIRL_E_INVALID, "null argument");
+    return flat_export(h, replica, net, 1, dst, n);
 }
 
 int hirl_store_rows(hirl_agent_t *h, int replica, int buffer, int first_slot, int n_rows, const float *rows32) {
-    if (!h || !rows32 || replica != 0) return fail(HIRL_E_INVALID, "bad handle/replica");
+    if (!h || !rows32 || replica < 0 || replica >= (int)h->ctxs.size()) return fail(HIRL_E_INVALID, "bad handle/replica");
     const int cap = buffer == HIRL_BUF_ONLINE ? h->cfg.online_capacity : buffer == HIRL_BUF_EXPERT ? h->cfg.expert_capacity : -1;
     if (cap < 0) return fail(HIRL_E_INVALID, "bad buffer selector");
     if (n_rows < 0 || n_rows > cap || first_slot < 0 || first_slot >= cap) return fail(HIRL_E_INVALID, "row range outside the ring");
-    float *base = buffer == HIRL_BUF_ONLINE ? h->online : h->expert;
+    float *base = buffer == HIRL_BUF_ONLINE ? h->online[replica] : h->expert[replica];
     CU(cudaSetDevice(h->cfg.device));
     const int first = std::min(n_rows, cap - first_slot);
     CU(cudaMemcpyAsync(base + (size_t)first_slot * ROW, rows32, (size_t)first * ROW * 4, cudaMemcpyHostToDevice, h->stream));
@@ -411,7 +462,7 @@ int hirl_bc_table_set(hirl_agent_t *h, const float *states13, const float *actio
 
 int hirl_gather(hirl_agent_t *h, int replica, const int32_t *idx_online, int n_online, const int32_t *idx_expert, int n_expert,
                 float *out_rows32) {
-    if (!h || !out_rows32 || replica != 0 || n_online < 0 || n_expert < 0) return fail(HIRL_E_INVALID, "bad argument");
+    if (!h || !out_rows32 || replica < 0 || replica >= (int)h->ctxs.size() || n_online < 0 || n_expert < 0) return fail(HIRL_E_INVALID, "bad argument");
     const int n = n_online + n_expert;
     if (n == 0) return 0;
     for (int i = 0; i < n_online; ++i)
@@ -425,7 +476,7 @@ int hirl_gather(hirl_agent_t *h, int replica, const int32_t *idx_online, int n_o
     CU(cudaMalloc(&d_out, (size_t)n * ROW * 4));
     if (n_online) CU(cudaMemcpyAsync(d_idx, idx_online, (size_t)n_online * 4, cudaMemcpyHostToDevice, h->stream));
     if (n_expert) CU(cudaMemcpyAsync(d_idx + n_online, idx_expert, (size_t)n_expert * 4, cudaMemcpyHostToDevice, h->stream));
-    gather_kernel<<<std::min((n + 7) / 8, 4 * h->sm_count), 256, 0, h->stream>>>(h->online, h->expert, d_idx, n_online, d_idx + n_online, n_expert, d_out);
+    gather_kernel<<<std::min((n + 7) / 8, 4 * h->sm_count), 256, 0, h->stream>>>(h->online[replica], h->expert[replica], d_idx, n_online, d_idx + n_online, n_expert, d_out);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out_rows32, d_out, (size_t)n * ROW * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -455,24 +506,43 @@ int hirl_gather_bc(hirl_agent_t *h, const int32_t *idx_bc, int n, float *out_sta
     return 0;
 }
 
+// steps/idx/out are device arrays with a leading [replicas] dimension of stride max(k_steps)
 static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_dev, const int32_t *ion, const int32_t *iex, const int32_t *ibc,
                          float *out_dev, cudaStream_t stream) {
-    LaunchCtx L;
-    L.agent = h->h_ctx;
-    AgentCtx &c = L.agent;
-    c.steps = steps_dev; c.idx_online = ion; c.idx_expert = iex; c.idx_bc = ibc; c.out_scalars = out_dev;
-    L.bar_flags = h->d_bar; L.k_steps = k_steps; L.stop_after = h->stop_after;
+    const int R = (int)h->ctxs.size();
+    const size_t B = h->cfg.batch;
     CU(cudaMemsetAsync(h->d_bar, 0, (size_t)MAX_CTAS * FLAG_STRIDE * sizeof(unsigned), stream));
-    L.prof = h->prof_on ? h->d_prof : nullptr;
-    void *args[] = {&L};
-    CU(cudaLaunchCooperativeKernel((void *)hirl_update_kernel, dim3(h->grid), dim3(THREADS), args, SMEM_BYTES, stream));
+    if (R == 1) {
+        LaunchCtx L;
+        L.agent = h->ctxs[0];
+        AgentCtx &c = L.agent;
+        c.steps = steps_dev; c.idx_online = ion; c.idx_expert = iex; c.idx_bc = ibc; c.out_scalars = out_dev;
+        L.bar_flags = h->d_bar; L.k_steps = k_steps; L.stop_after = h->stop_after;
+        L.prof = h->prof_on ? h->d_prof : nullptr;
+        void *args[] = {&L};
+        CU(cudaLaunchCooperativeKernel((void *)hirl_update_kernel, dim3(h->grid), dim3(THREADS), args, SMEM_BYTES, stream));
+    } else {
+        std::vector<AgentCtx> tmp(h->ctxs);
+        for (int r = 0; r < R; ++r) {
+            AgentCtx &c = tmp[r];
+            const size_t o = (size_t)r * k_steps;
+            c.steps = steps_dev + o; c.idx_online = ion + o * B; c.idx_expert = iex + o * B; c.idx_bc = ibc + o * B;
+            c.out_scalars = out_dev + o * HIRL_OUT_SCALARS;
+        }
+        CU(cudaMemcpyAsync(h->d_ctxs, tmp.data(), sizeof(AgentCtx) * R, cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));  // tmp is pageable host memory
+        EnsembleLaunch L;
+        L.agents = h->d_ctxs; L.bar_flags = h->d_bar; L.replicas = R; L.n_teams = h->n_teams; L.team_size = h->team_size; L.k_steps = k_steps;
+        void *args[] = {&L};
+        CU(cudaLaunchCooperativeKernel((void *)hirl_ensemble_kernel, dim3(h->n_teams * h->team_size), dim3(THREADS), args, SMEM_BYTES, stream));
+    }
     h->last_launches = 1;
     return 0;
 }
 
 static int check_steps(hirl_agent *h, int k_steps, const hirl_step_t *steps) {
     if (k_steps < 1 || k_steps > h->cfg.max_steps) return fail(HIRL_E_INVALID, "k_steps outside [1, cfg.max_steps]");
-    for (int k = 0; k < k_steps; ++k) {
+    for (int k = 0; k < k_steps * (int)h->ctxs.size(); ++k) {
         const hirl_step_t &s = steps[k];
         if (s.n_online < 0 || s.n_expert < 0 || s.n_online + s.n_expert != h->cfg.batch)
             return fail(HIRL_E_INVALID, "n_online + n_expert must equal the batch size");
@@ -486,7 +556,7 @@ int hirl_learn(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, const int
                const int32_t *idx_bc, float *out_scalars) {
     if (!h || !steps || !idx_online || !out_scalars) return fail(HIRL_E_INVALID, "null argument");
     if (int rc = check_steps(h, k_steps, steps)) return rc;
-    const size_t B = h->cfg.batch, K = k_steps;
+    const size_t B = h->cfg.batch, K = (size_t)k_steps * h->ctxs.size();
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaMemcpyAsync(h->d_steps, steps, K * sizeof(hirl_step_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_ion, idx_online, K * B * 4, cudaMemcpyHostToDevice, h->stream));
@@ -509,11 +579,11 @@ int hirl_learn_dev(hirl_agent_t *h, int k_steps, const hirl_step_t *steps_dev, c
 int hirl_last_launch_count(hirl_agent_t *h) { return h ? h->last_launches : 0; }
 
 int hirl_act(hirl_agent_t *h, int replica, int net, const float *states13, int n, float *actions4) {
-    if (!h || !states13 || !actions4 || replica != 0 || n < 0) return fail(HIRL_E_INVALID, "bad argument");
+    if (!h || !states13 || !actions4 || n < 0) return fail(HIRL_E_INVALID, "bad argument");
     if (is_critic(net)) return fail(HIRL_E_INVALID, "hirl_act needs an actor network");
     if (n == 0) return 0;
     float *w;
-    if (int rc = net_ptr(h, net, 0, &w)) return rc;
+    if (int rc = net_ptr(h, replica, net, 0, &w)) return rc;
     CU(cudaSetDevice(h->cfg.device));
     float *d_s = nullptr, *d_a = nullptr;
     CU(cudaMalloc(&d_s, (size_t)n * S * 4));
@@ -549,8 +619,8 @@ int hirl_debug_profile(hirl_agent_t *h, int enable, long long *dst, size_t n) {
 }
 int hirl_debug_export(hirl_agent_t *h, int buffer_id, int pass, float *dst, size_t n, size_t *n_out) {
     if (!h) return fail(HIRL_E_INVALID, "null handle");
-    const Scratch &s = h->h_ctx.sc;
-    const size_t B = h->cfg.batch, zs = h->h_ctx.zsplit;
+    const Scratch &s = h->ctxs[0].sc;
+    const size_t B = h->cfg.batch, zs = h->ctxs[0].zsplit;
     const float *src = nullptr;
     size_t cnt = 0;
     switch (buffer_id) {

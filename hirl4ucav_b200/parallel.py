@@ -1,0 +1,60 @@
+"""Host-side sharding for multi-GPU runs (one process per GPU, launched by torchrun).
+
+The hot path shards only where it is naturally independent:
+  * agent updates: independent replicas / seeds, R/k per GPU, NO data-path collective;
+  * env pass: contiguous chunks of N/k states per GPU, no exchange.
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) is used for the timing barrier, the
+max-over-ranks reduction and gathering small result records -- plumbing, not the product.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_rank():
+    """(rank, local_rank, world_size) from the torchrun environment (defaults: single process)."""
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def shard_range(n: int, world: int, rank: int):
+    """Contiguous [start, stop) of n items for `rank`; sizes differ by at most one, order preserved."""
+    if not 0 <= rank < world:
+        raise ValueError("rank outside the world")
+    base, extra = divmod(n, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def replica_seeds(base_seed: int, n_replicas: int, world: int, rank: int):
+    """Seeds of the replicas this rank owns: replica i always gets base_seed + i, wherever it runs,
+    so a k-GPU run reproduces the 1-GPU run replica by replica."""
+    a, b = shard_range(n_replicas, world, rank)
+    return [base_seed + i for i in range(a, b)]
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def gather_records(record):
+    """List of every rank's small Python record on every rank (rank order)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [record]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, record)
+    return out

@@ -1,0 +1,64 @@
+"""CPU, world_size 2, gloo: the host logic of the N>1 path (sharding, reductions, record gather)."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hirl4ucav_b200 import parallel
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 8, 1024, 10_000_001):
+        for world in (1, 2, 3, 4, 8):
+            spans = [parallel.shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_replica_seeds_do_not_depend_on_world_size():
+    one = parallel.replica_seeds(100, 1024, 1, 0)
+    for world in (2, 4, 8):
+        many = sum((parallel.replica_seeds(100, 1024, world, r) for r in range(world)), [])
+        assert many == one
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert parallel.env_rank() == (rank, rank, world)
+        # replicas: each rank "runs" its shard; the per-replica records are identical to a 1-rank run
+        seeds = parallel.replica_seeds(7, 10, world, rank)
+        recs = [{"seed": s, "value": float(np.random.default_rng(s).random())} for s in seeds]
+        allr = sum(parallel.gather_records(recs), [])
+        t_max = parallel.max_over_ranks(1.0 + rank)
+        total = parallel.sum_over_ranks(len(seeds))
+        # env shards: contiguous chunks, checksum of checksums equals the global checksum
+        x = np.arange(1001, dtype=np.int64)
+        a, b = parallel.shard_range(x.size, world, rank)
+        chk = parallel.sum_over_ranks(float(x[a:b].sum()))
+        q.put((rank, [r["seed"] for r in allr], [r["value"] for r in allr], t_max, total, chk))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_run_matches_single_rank():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    single_seeds = parallel.replica_seeds(7, 10, 1, 0)
+    single_vals = [float(np.random.default_rng(s).random()) for s in single_seeds]
+    for rank, seeds, vals, t_max, total, chk in out:
+        assert seeds == single_seeds and vals == single_vals      # replica i is the same wherever it runs
+        assert t_max == 2.0 and total == 10.0 and chk == float(np.arange(1001).sum())
