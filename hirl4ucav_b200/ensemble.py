@@ -1,0 +1,194 @@
+"""R independent HIRL agents ("replicas", BASELINE.json config 4) updated by ONE persistent launch.
+
+Each replica is a complete agent of the reference (hirl/agents/HIRL.py:148-190): its own five
+networks, Adam state, replay rings and its own three RNG streams, seeded exactly like a single run
+with ``set_seed(seed)`` (hirl/utils/seed.py:5-10) -- replica i behaves like ``Agent`` constructed
+under that seed.  Only the read-only expert (s, a) table is shared.  On the device the grid is cut
+into teams of CTAs; each team runs whole replicas with team-local barriers
+(csrc/hirl_b200.cu: hirl_ensemble_kernel).  No collective: replicas shard over GPUs with
+``parallel.shard_range``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random
+
+import numpy as np
+import torch
+
+from . import _lib, nets
+from .agents.HIRL import SOFT_SENTINEL, _adam_scalars
+
+
+class _Streams:
+    """The reference's three host RNG streams for one replica (private generators, same sequences
+    as the global ones after set_seed(seed))."""
+
+    def __init__(self, seed):
+        self.py = random.Random(seed)
+        self.np = np.random.RandomState(seed)
+        self.torch = torch.Generator().manual_seed(seed)
+
+    def reseed(self, seed):
+        self.py.seed(seed)
+        self.np.seed(seed)
+        self.torch.manual_seed(seed)
+
+
+class AgentEnsemble(object):
+    def __init__(self, seeds, actorLR, criticLR, tau, gamma, bufferSize, batchSize, expert_states, expert_actions,
+                 expert_warm_up=True, name="Harfang_GYM", device=None, max_fused_steps=64):
+        self.R = len(seeds)
+        self.seeds = list(seeds)
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.batchSize, self.bufferSize = int(batchSize), int(bufferSize)
+        self.actorLR, self.criticLR, self.tau, self.gamma = actorLR, criticLR, tau, gamma
+        self.expert_warm_up = expert_warm_up
+        self.loss_lambda = 10000
+        self.target_update_freq = 3
+        self.actionDim = 4
+        self.TD3LearningNoise, self.TD3LearningNoiseClamp = 0.2, 0.5
+        self.actorTrainable = True
+        self.update_count = 0
+        self._critic_t = self._actor_t = 0
+        self._max_steps = int(max_fused_steps)
+        self.n_expert = len(expert_states)
+        cfg = _lib.Config(device=self.device.index, batch=self.batchSize, online_capacity=self.bufferSize,
+                          expert_capacity=self.n_expert + 10, bc_rows=self.n_expert, max_steps=self._max_steps,
+                          activation=_lib.ACT_RELU, replicas=self.R, gamma=gamma, tau=tau,
+                          noise_clamp=self.TD3LearningNoiseClamp, loss_lambda=float(self.loss_lambda))
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        _lib.check(self._lib.hirl_agent_create(C.byref(cfg), C.byref(self._h)))
+        es, ea = _lib.f32c(expert_states), _lib.f32c(expert_actions)
+        _lib.check(self._lib.hirl_bc_table_set(self._h, _lib.ptr(es), _lib.ptr(ea), self.n_expert))
+        self.streams = []
+        self.online_len = [0] * self.R
+        self.expert_len = [0] * self.R
+        for r, seed in enumerate(self.seeds):
+            # initial weights: the reference's construction order under torch.manual_seed(seed)
+            with torch.random.fork_rng(devices=[]):
+                torch.manual_seed(seed)
+                actor = nets.make_actor(13, 4, 256, 512, "Actor_" + name)
+                nets.make_actor(13, 4, 256, 512, "TargetActor_" + name)      # drawn, then overwritten (hard_update)
+                critic = nets.make_critic(13, 4, 256, 512, "Critic_" + name)
+                nets.make_critic(13, 4, 256, 512, "TargetCritic_" + name)
+                bc = nets.make_actor(13, 4, 256, 512, name)
+            for net_id, mod in ((_lib.NET_ACTOR, actor), (_lib.NET_TARGET_ACTOR, actor), (_lib.NET_CRITIC, critic),
+                                (_lib.NET_TARGET_CRITIC, critic), (_lib.NET_BC_ACTOR, bc)):
+                v = mod.flat()
+                _lib.check(self._lib.hirl_params_import(self._h, r, net_id, _lib.ptr(v), v.size))
+            self.streams.append(_Streams(seed))
+        K, B, R = self._max_steps, self.batchSize, self.R
+        pin = torch.cuda.is_available()
+        mk = lambda shape, dt: torch.zeros(shape, dtype=dt, pin_memory=pin)
+        self._steps_t = mk((R * K * _lib.STEP_DTYPE.itemsize,), torch.uint8)
+        self._on_t, self._ex_t, self._bc_t = mk((R, K, B), torch.int32), mk((R, K, B), torch.int32), mk((R, K, B), torch.int32)
+        self._out_t = mk((R, K, _lib.OUT_SCALARS), torch.float32)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._lib.hirl_agent_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ---- data ---------------------------------------------------------------------------------
+    def store_rows(self, replica, rows32, expert=False):
+        """Appends pre-packed 32-word rows to one replica's online / expert ring (no wrap handling
+        beyond the ring itself: rows are written at the current length modulo capacity)."""
+        rows32 = _lib.f32c(rows32).reshape(-1, 32)
+        cap = self.n_expert + 10 if expert else self.bufferSize
+        lens = self.expert_len if expert else self.online_len
+        first = lens[replica] % cap
+        _lib.check(self._lib.hirl_store_rows(self._h, replica, _lib.BUF_EXPERT if expert else _lib.BUF_ONLINE, first,
+                                             rows32.shape[0], _lib.ptr(rows32)))
+        lens[replica] = min(cap, lens[replica] + rows32.shape[0])
+
+    def reseed(self, offset=1):
+        """set_seed(seed + offset) for every replica's streams (what bench/tests do before the timed loop)."""
+        for s, seed in zip(self.streams, self.seeds):
+            s.reseed(seed + offset)
+
+    def export_flat(self, replica, net_id):
+        n = _lib.CRITIC_PARAMS if net_id in (_lib.NET_CRITIC, _lib.NET_TARGET_CRITIC) else _lib.ACTOR_PARAMS
+        out = np.empty(n, np.float32)
+        _lib.check(self._lib.hirl_params_export(self._h, replica, net_id, _lib.ptr(out), n))
+        return out
+
+    # ---- update -------------------------------------------------------------------------------
+    def draw(self, calls):
+        """Pre-draws the index / noise streams of len(calls) consecutive learn() calls for every replica
+        (reference order per call: online sample, expert sample, BC choice, noise)."""
+        K, B, R = len(calls), self.batchSize, self.R
+        if K > self._max_steps:
+            raise ValueError("more calls than max_fused_steps")
+        steps = self._steps_t.numpy().view(_lib.STEP_DTYPE)[: R * K].reshape(R, K)
+        on, ex, bc = self._on_t.numpy(), self._ex_t.numpy(), self._bc_t.numpy()
+        flags = []
+        trainable, upd, ct, at = self.actorTrainable, self.update_count, self._critic_t, self._actor_t
+        sched = []
+        for _ in range(K):
+            do_actor = trainable
+            ct += 1
+            if do_actor:
+                at += 1
+                upd += 1
+            sched.append((do_actor, do_actor and upd % self.target_update_freq == 0, _adam_scalars(self.criticLR, ct),
+                          _adam_scalars(self.actorLR, at) if do_actor else (0.0, 0.0)))
+            trainable = not trainable
+        self.actorTrainable, self.update_count, self._critic_t, self._actor_t = trainable, upd, ct, at
+        mean, std = torch.zeros(self.actionDim), torch.ones(self.actionDim) * self.TD3LearningNoise
+        for r in range(R):
+            st = self.streams[r]
+            for k, (bcw, en, warm) in enumerate(calls):
+                n_ex = int(en) if (self.expert_warm_up and en) else 0
+                n_on = B - n_ex
+                if n_on <= 0:
+                    raise TypeError("expert_num_now == batchSize leaves no online rows")
+                on[r, k, :n_on] = st.py.sample(range(self.online_len[r]), n_on)
+                if n_ex:
+                    ex[r, k, :n_ex] = st.py.sample(range(self.expert_len[r]), n_ex)
+                bc[r, k, :] = st.np.choice(self.n_expert, B, replace=False)
+                s = steps[r, k]
+                s["n_online"], s["n_expert"] = n_on, n_ex
+                s["do_actor"], s["do_polyak"] = int(sched[k][0]), int(sched[k][1])
+                s["bc_weight_now"], s["bc_warm_up"], s["force_soft_weight"] = bcw, warm, -1.0
+                s["noise"] = torch.normal(mean=mean, std=std, generator=st.torch).numpy()
+                s["critic_neg_step"], s["critic_bc2_sqrt"] = sched[k][2]
+                s["actor_neg_step"], s["actor_bc2_sqrt"] = sched[k][3]
+                s["mode"] = 0
+        return K
+
+    def launch(self, K):
+        """hirl_learn over the staged streams: [R][K] everything, host buffers."""
+        R, B = self.R, self.batchSize
+        st = np.ascontiguousarray(self._steps_t.numpy().view(_lib.STEP_DTYPE)[: R * K])
+        on = np.ascontiguousarray(self._on_t.numpy()[:, :K]); ex = np.ascontiguousarray(self._ex_t.numpy()[:, :K])
+        bc = np.ascontiguousarray(self._bc_t.numpy()[:, :K])
+        out = np.empty((R, K, _lib.OUT_SCALARS), np.float32)
+        _lib.check(self._lib.hirl_learn(self._h, K, st.ctypes.data_as(C.c_void_p), _lib.ptr(on), _lib.ptr(ex), _lib.ptr(bc),
+                                        _lib.ptr(out)))
+        return out
+
+    def learn_many(self, calls):
+        """All replicas execute the same call sequence; returns scalars [R][K][8] (critic_loss, actor_loss,
+        bc_loss, rl_loss, fire_mse, bc_weight, soft_count, -)."""
+        K = self.draw(list(calls))
+        return self.launch(K)
+
+    def device_streams(self, K):
+        """Device copies of the staged streams + a launcher (bench: inputs resident in HBM)."""
+        R = self.R
+        dev = self.device
+        st = torch.from_numpy(np.ascontiguousarray(self._steps_t.numpy()[: R * K * 64])).to(dev)
+        on = self._on_t[:, :K].contiguous().to(dev); ex = self._ex_t[:, :K].contiguous().to(dev); bc = self._bc_t[:, :K].contiguous().to(dev)
+        out = torch.zeros((R, K, 8), dtype=torch.float32, device=dev)
+
+        def launch():
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(self._lib.hirl_learn_dev(self._h, K, st.data_ptr(), on.data_ptr(), ex.data_ptr(), bc.data_ptr(), out.data_ptr(), stream))
+        launch.keep = (st, on, ex, bc, out)
+        return launch, out
