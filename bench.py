@@ -36,6 +36,8 @@ WORKLOADS = {
     "fixed4096": dict(batch=4096, bcw=0.5, expert_num=1024, flop_per_row=3_511_040, desc="HIRL fixed BC weight, batch 4096"),
     "linear4096": dict(batch=4096, bcw=0.5 - 3 / 5000, expert_num=0, flop_per_row=3_511_040, desc="HIRL linear BC schedule, batch 4096"),
 }
+WORKLOADS["ensemble128"] = dict(batch=256, bcw=100.0, expert_num=64, flop_per_row=3_783_424, replicas=128,
+                                desc="128 independent HIRL-soft agent replicas per GPU (1024 on 8 GPUs), ensemble kernel, batch 256")
 N_ONLINE, N_EXPERT = 30_000, 20_000
 HP = dict(actorLR=1e-3, criticLR=1e-3, tau=0.005, gamma=0.99, bufferSize=10 ** 5)
 
@@ -202,10 +204,92 @@ def env_roofline(device, peaks):
             "note": "10 M synthetic pursuit states, 124 algorithmic B/state (64 in + 60 out), 1.24 GB per pass >> L2, includes torch output allocation"}
 
 
+def run_ensemble(args):
+    """BASELINE config 4: R replicas per GPU in one ensemble launch; a step = every replica makes one learn() call."""
+    rank, local, world = dist_env()
+    from hirl4ucav_b200 import _lib, synth, parallel
+    from hirl4ucav_b200.ensemble import AgentEnsemble
+    from hirl4ucav_b200.environments import harfang_math as hm
+    wl = WORKLOADS[args.workload]
+    R = args.replicas or wl["replicas"]
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = min(args.steps, 60), min(max(args.warmup, 3), 12)
+    K -= K % 6 if K >= 6 else 0
+    peaks, peak_src = measured_peaks()
+    es, ea = synth.expert_table(N_EXPERT)
+    erows, _ = hm.expert_scan(es, ea, local)
+    seeds = parallel.replica_seeds(0, R * world, world, rank)          # replica i has seed i wherever it runs
+    ens = AgentEnsemble(seeds, HP["actorLR"], HP["criticLR"], HP["tau"], HP["gamma"], N_ONLINE, wl["batch"], es, ea,
+                        device=local, max_fused_steps=max(K, W))
+    rng = np.random.default_rng(77 + rank)
+    for r in range(R):
+        s, a, s2 = synth.env_states(rng, N_ONLINE), synth.env_actions(rng, N_ONLINE), synth.env_states(rng, N_ONLINE)
+        rew, succ, done = hm.offline_reward(s, a, s2, local)
+        rows = np.empty((N_ONLINE, 32), np.float32)
+        rows[:, 0:13], rows[:, 13:17], rows[:, 17:30], rows[:, 30], rows[:, 31] = s, a, s2, rew, done
+        ens.store_rows(r, rows)
+        ens.store_rows(r, erows, expert=True)
+    ens.reseed(1)
+    calls = [(wl["bcw"], wl["expert_num"], 0)]
+    sampler = ClockSampler(local)
+    with sampler:
+        ens.draw(calls * W)
+        warm, _ = ens.device_streams(W)
+        warm(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ens.draw(calls * K)
+        draw_s = time.perf_counter() - t0
+        timed, out_d = ens.device_streams(K)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+        e0.record(); timed(); e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+        ms_total = e0.elapsed_time(e1)
+        assert torch.isfinite(out_d[:, -1, :4]).all()
+        # e2e: the public call with host buffers (host RNG pre-draw + H2D + launch + D2H)
+        t0 = time.perf_counter()
+        ens.learn_many(calls * K)
+        e2e_s = time.perf_counter() - t0
+    ms_total = parallel.max_over_ranks(ms_total, dev)
+    e2e_s = parallel.max_over_ranks(e2e_s, dev)
+    if rank == 0:
+        B = wl["batch"]
+        value = world * R * K / (ms_total * 1e-3)
+        fp32 = C.c_double(0)
+        _lib.check(_lib.load().hirl_measure_fp32_peak(local, C.byref(fp32)))
+        achieved = wl["flop_per_row"] * B * R * K / (ms_total * 1e-3) / 1e12
+        hbm = 11.1e6 * R * K / (ms_total * 1e-3) / 1e9
+        line = {"metric": "agent updates/sec", "value": value, "unit": "replica-updates/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": dict(config_of(args, wl), replicas_per_gpu=R, replicas_total=R * world,
+                                                      parallelism=f"{R} replicas/GPU x {world} GPUs, teams of CTAs, no collective"),
+                "clocks": sampler.summary(),
+                "e2e": {"value": world * R * K / e2e_s, "unit": "replica-updates/s", "h2d_bytes_per_step": R * (3 * B * 4 + 64),
+                        "d2h_bytes_per_step": R * 32, "api": "AgentEnsemble.learn_many (host RNG streams of every replica + H2D + launch + D2H)",
+                        "host_draw_seconds": draw_s},
+                "gpu_launches": 1,
+                "roofline": {"kernel": "hirl_ensemble_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32.value, "unit": "TFLOP/s",
+                             "frac": achieved / fp32.value, "traffic": None, "hbm_stream_gbs_if_weights_streamed": hbm,
+                             "note": "weights + Adam state of 128 replicas = 1.1 GB > L2: 11.1 MB algorithmic HBM bytes per replica-update"}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     rank, local, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    if "replicas" in WORKLOADS[args.workload]:
+        return run_ensemble(args)
     from hirl4ucav_b200 import _lib
     lib = _lib.load()
     wl = WORKLOADS[args.workload]
@@ -308,6 +392,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=60)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="soft256", choices=sorted(WORKLOADS))
+    ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU for the ensemble workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
