@@ -101,6 +101,8 @@ struct Scratch {
     float *PART_A;   // [MAX_CTAS][ActorL::SMALL]
     float *LP;       // [MAX_CTAS][LP_WORDS]
     float *GW2B;     // [H2][H1] actor dW2 of the expert-state branch
+    float *H1T;      // [4][H1][BT]  transposed h1 of C1, C2, A, AB   (tensor-core dW operands, K-major)
+    float *DZ2T;     // [4][H2][BT]  transposed dz2 of the same passes
 };
 
 // Everything one replica's update needs.  Passed to the kernel by value (per-replica array in
@@ -110,6 +112,7 @@ struct AgentCtx {
     float *actor, *tactor, *critic, *tcritic, *bc;
     float *g_actor, *g_critic;
     float *m_actor, *v_actor, *m_critic, *v_critic;
+    float *w2t_actor, *w2t_critic;   // transposed copies of W2 ([H1][H2], per tower): K-major operand of the tensor-core dX GEMMs
     // replay tables
     const float *online;   // [online_capacity][32]
     const float *expert;   // [expert_capacity][32]
@@ -124,6 +127,8 @@ struct AgentCtx {
     int zsplit;            // allocated split-K slots per Z2 / DH1 buffer (max of ns[])
     int ns[NS_COUNT];      // split-K factor per GEMM group
     int activation;
+    int use_tc;            // 1: 256<->512 contractions on tcgen05 (3xTF32), 0: FP32-FMA tiles
+    int BT;                // batch rounded up to 32: leading dimension of the transposed buffers
     float gamma, tau, noise_clamp, loss_lambda;
 };
 

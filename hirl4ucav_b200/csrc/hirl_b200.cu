@@ -29,10 +29,26 @@ __global__ void __launch_bounds__(THREADS, 1) hirl_update_kernel(const __grid_co
         for (int i = threadIdx.x; i < (int)(sizeof(AgentCtx) / sizeof(int)); i += THREADS) dst[i] = src[i];
     }
     __syncthreads();
+    __shared__ tc::Barriers tc_bars;
+    __shared__ uint32_t tmem_slot;
+    if (ctx.use_tc) {
+        if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot);
+        if (threadIdx.x == 32) tc::barriers_init(&tc_bars);
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+    }
     Team tm;
     tm.rank = blockIdx.x; tm.size = gridDim.x; tm.flags = L.bar_flags; tm.gen = 0u;
+    tm.tmem_base = ctx.use_tc ? tmem_slot : 0u;
+    tm.tc_smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+    tm.tc_bars = &tc_bars;
     for (int step = 0; step < L.k_steps; ++step)
-        if (learn_step(ctx, step, tm, smem, step == 0 ? L.stop_after : 0, L.prof)) return;
+        if (learn_step(ctx, step, tm, smem, step == 0 ? L.stop_after : 0, L.prof)) break;
+    if (ctx.use_tc) {
+        __syncthreads();
+        if (threadIdx.x < 32) tc::tmem_dealloc(tm.tmem_base);
+    }
 }
 
 // Ensemble form (BASELINE config 4): the grid is cut into teams of team_size CTAs; every team runs
@@ -44,9 +60,22 @@ __global__ void __launch_bounds__(THREADS, 1) hirl_ensemble_kernel(const __grid_
     __shared__ AgentCtx ctx;
     const int team = blockIdx.x / L.team_size;
     if (team >= L.n_teams) return;
+    __shared__ tc::Barriers tc_bars;
+    __shared__ uint32_t tmem_slot;
+    const bool use_tc = L.agents[0].use_tc != 0;
+    if (use_tc) {
+        if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot);
+        if (threadIdx.x == 32) tc::barriers_init(&tc_bars);
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+    }
     Team tm;
     tm.rank = blockIdx.x % L.team_size; tm.size = L.team_size;
     tm.flags = L.bar_flags + (size_t)team * L.team_size * FLAG_STRIDE; tm.gen = 0u;
+    tm.tmem_base = use_tc ? tmem_slot : 0u;
+    tm.tc_smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+    tm.tc_bars = &tc_bars;
     for (int r = team; r < L.replicas; r += L.n_teams) {
         __syncthreads();
         const int *src = reinterpret_cast<const int *>(L.agents + r);
@@ -54,6 +83,10 @@ __global__ void __launch_bounds__(THREADS, 1) hirl_ensemble_kernel(const __grid_
         for (int i = threadIdx.x; i < (int)(sizeof(AgentCtx) / sizeof(int)); i += THREADS) dst[i] = src[i];
         __syncthreads();
         for (int step = 0; step < L.k_steps; ++step) learn_step(ctx, step, tm, smem, 0, nullptr);
+    }
+    if (use_tc) {
+        __syncthreads();
+        if (threadIdx.x < 32) tc::tmem_dealloc(tm.tmem_base);
     }
 }
 
@@ -244,6 +277,15 @@ static int flat_import(hirl_agent *h, int replica, int net, int kind, const floa
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy(d, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+    if (kind == 0 && (net == HIRL_NET_ACTOR || net == HIRL_NET_CRITIC)) {   // W2^T copies of the trainable nets
+        const int towers = cr ? 2 : 1;
+        const int w2off = cr ? CriticL::W2 : ActorL::W2, tsize = cr ? CriticL::SIZE : ActorL::SIZE;
+        std::vector<float> t((size_t)towers * H1 * H2);
+        for (int tw = 0; tw < towers; ++tw)
+            for (int n = 0; n < H2; ++n)
+                for (int k = 0; k < H1; ++k) t[(size_t)tw * H1 * H2 + (size_t)k * H2 + n] = tmp[(size_t)tw * tsize + w2off + (size_t)n * H1 + k];
+        CU(cudaMemcpy(cr ? h->ctxs[replica].w2t_critic : h->ctxs[replica].w2t_actor, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 static int flat_export(hirl_agent *h, int replica, int net, int kind, float *dst, size_t n) {
@@ -340,6 +382,14 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     proto.ns[NS_G5] = pick_split({fwd, fwd}, team_ctas, forced);
     proto.ns[NS_G6] = pick_split({dx}, team_ctas, forced);
     proto.ns[NS_G7DX] = pick_split({{32, kb, false}, {32, kb, false}, dx, dx}, team_ctas, forced);
+    // tensor-core path (tcgen05, 3xTF32, 128x64 tiles).  Measured: at batch 256 a single agent has at most one
+    // tile per SM per stage and the FP32 64x64 tiles (twice as many, split-K) finish sooner; once a CTA has several
+    // tiles per stage (large batch, or a team of 8 CTAs per replica in ensembles) the tensor-core tiles win 2.5-3.5x.
+    proto.use_tc = (cfg->batch >= 512 || (R > 1 && cfg->batch >= 128)) ? 1 : 0;
+    if (const char *e = getenv("HIRL_TC")) proto.use_tc = atoi(e) != 0;
+    proto.BT = (cfg->batch + 31) & ~31;
+    if (proto.use_tc)
+        for (int i = 0; i < NS_COUNT; ++i) proto.ns[i] = 1;
     proto.zsplit = 1;
     for (int i = 0; i < NS_COUNT; ++i) proto.zsplit = std::max(proto.zsplit, proto.ns[i]);
 
@@ -362,6 +412,8 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
 #undef SCR
         const int slots = R > 1 ? h->team_size : MAX_CTAS;
         if ((rc = dev_alloc(h, &s.GW2B, (size_t)H2 * H1))) return rc;
+        if ((rc = dev_alloc(h, &s.H1T, (size_t)4 * H1 * proto.BT))) return rc;
+        if ((rc = dev_alloc(h, &s.DZ2T, (size_t)4 * H2 * proto.BT))) return rc;
         if ((rc = dev_alloc(h, &s.PART_C, (size_t)slots * 2 * CriticL::SMALL))) return rc;
         if ((rc = dev_alloc(h, &s.PART_A, (size_t)slots * ActorL::SMALL))) return rc;
     }
@@ -384,6 +436,8 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
         c.online = h->online[r]; c.expert = h->expert[r]; c.bctab = h->bctab;
         c.sc = team_sc[r % h->n_teams];
         if ((rc = dev_alloc(h, &c.carry, 8))) return rc;
+        if ((rc = dev_alloc(h, &c.w2t_actor, (size_t)H1 * H2))) return rc;
+        if ((rc = dev_alloc(h, &c.w2t_critic, (size_t)2 * H1 * H2))) return rc;
     }
     const size_t K = (size_t)cfg->max_steps * R;
     if ((rc = dev_alloc(h, &h->d_steps, K))) return rc;

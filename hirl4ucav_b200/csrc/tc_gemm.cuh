@@ -21,6 +21,7 @@
 #endif
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 namespace hirl {
 namespace tc {
@@ -57,14 +58,29 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t tmem_base) {
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must fail loudly (trap -> CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int tag = 0) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    bool reported = false;
+    while (!mbar_try(bar, parity)) {
+        const long long dt = clock64() - t0;
+        if (dt > 4000000000LL && !reported) {   // ~2 s: report, keep waiting a little so every stuck warp reports, then trap
+            reported = true;
+            if ((threadIdx.x & 31) == 0)
+                printf("hirl tc_gemm: mbarrier wait timed out (block %d warp %d tag %d parity %u)\n", blockIdx.x, threadIdx.x >> 5, tag, parity);
+        }
+        if (dt > 6000000000LL) __trap();
+    }
 }
 
 // ---- descriptors -----------------------------------------------------------------------------
@@ -157,10 +173,23 @@ constexpr int KCHUNK = 512;
 constexpr int COL_MAIN = 0, COL_CORR = BN, COL_CORR2 = 2 * BN, COL_A = 3 * BN;
 constexpr int ISSUERS = 3;          // warps 0,1,2 each issue one of the three products (a single thread issuing all
                                     // twelve MMAs of a block costs ~70 cycles per MMA and was the critical path)
+// Initialised ONCE per kernel (barriers_init); phases are tracked across tiles with the two running
+// counters, the mbarrier objects are never re-initialised while the kernel runs.
 struct Barriers {
     uint64_t full[NSTAGE], empty[NSTAGE], chunk;
+    uint32_t blocks_done;   // K blocks staged so far by this CTA (all tiles)
+    uint32_t chunks_done;   // chunk completions so far
 };
 
+// once per kernel, by one thread, followed by __syncthreads()
+__device__ __forceinline__ void barriers_init(Barriers *bars) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bars->full + s, THREADS_PER_TILE / 32); mbar_init(bars->empty + s, ISSUERS); }
+    mbar_init(&bars->chunk, ISSUERS);
+    bars->blocks_done = 0u;
+    bars->chunks_done = 0u;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -182,9 +211,9 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         : "memory");
 }
 
-__device__ __noinline__ void gemm_tile(const float *__restrict__ A, int lda, int M, const float *__restrict__ Bm, int ldb, int N, int K,
-                                       int m0, int n0, int k_begin, int k_end, float *__restrict__ C, int ldc,
-                                       const float *__restrict__ bias, uint32_t tmem_base, char *smem, Barriers *bars) {
+__device__ __noinline__ void gemm_tile(const float *A, int lda, int M, const float *Bm, int ldb, int N, int K,
+                                       int m0, int n0, int k_begin, int k_end, float *C, int ldc,
+                                       const float *bias, uint32_t tmem_base, char *smem, Barriers *bars) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = (k_end - k_begin + BK - 1) / BK;
     constexpr int KB_PER_CHUNK = KCHUNK / BK;
@@ -194,14 +223,8 @@ __device__ __noinline__ void gemm_tile(const float *__restrict__ A, int lda, int
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int bc = tid & 7, br = tid >> 3;                // B staging: 16-byte chunk and row (0..31, +32)
 
-    __syncthreads();                         // previous users of smem / TMEM / barriers are done
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bars->full + s, THREADS_PER_TILE / 32); mbar_init(bars->empty + s, ISSUERS); }
-        mbar_init(&bars->chunk, ISSUERS);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
+    __syncthreads();                         // previous users of smem / TMEM are done; counters are stable
+    const uint32_t g0 = bars->blocks_done, c0 = bars->chunks_done;   // running block / chunk indices of this CTA
 
     float acc[BN / 2];
 #pragma unroll
@@ -225,8 +248,9 @@ __device__ __noinline__ void gemm_tile(const float *__restrict__ A, int lda, int
         }
     };
     auto issue = [&](int kb, int kb0, bool last) {      // warps 0..2: this warp's product of block kb
-        const int s = kb % NSTAGE;
-        mbar_wait(bars->full + s, (uint32_t)((kb / NSTAGE) & 1));
+        const uint32_t g = g0 + (uint32_t)kb;
+        const int s = (int)(g % NSTAGE);
+        mbar_wait(bars->full + s, (g / NSTAGE) & 1u, 100 + kb);
         tc_fence_after();
         if (lane == 0) {
             const uint64_t bhi = bdesc0 + (uint64_t)((s * (2 * B_BYTES)) >> 4), blo = bhi + (uint64_t)(B_BYTES >> 4);
@@ -247,7 +271,8 @@ __device__ __noinline__ void gemm_tile(const float *__restrict__ A, int lda, int
         const int kb0 = ch * KB_PER_CHUNK, kb1 = min(nkb, kb0 + KB_PER_CHUNK);
         fetch(kb0);
         for (int kb = kb0; kb < kb1; ++kb) {
-            const int s = kb % NSTAGE;
+            const uint32_t g = g0 + (uint32_t)kb;
+            const int s = (int)(g % NSTAGE);
             float4 ca[4], cb[2];
             TC_T0
 #pragma unroll
@@ -259,7 +284,7 @@ __device__ __noinline__ void gemm_tile(const float *__restrict__ A, int lda, int
 #endif
             TC_T(warp) TC_TR
             if (kb + 1 < kb1) fetch(kb + 1);                                              // in flight while this block is staged
-            if (kb >= NSTAGE) mbar_wait(bars->empty + s, (uint32_t)((kb / NSTAGE - 1) & 1));  // MMAs that read this stage are done
+            if (g >= NSTAGE) mbar_wait(bars->empty + s, (g / NSTAGE - 1u) & 1u, 200 + kb);  // MMAs that read this stage are done
             tc_fence_after();
             TC_T(8 + warp) TC_TR
             // A: my row's 16 elements -> hi / lo -> my TMEM lane
@@ -297,7 +322,7 @@ __device__ __noinline__ void gemm_tile(const float *__restrict__ A, int lda, int
         if (warp < ISSUERS) issue(kb1 - 1, kb0, true);
         // ---------------- chunk epilogue: TMEM -> registers (all warps) ----------------
         TC_T0
-        mbar_wait(&bars->chunk, (uint32_t)(ch & 1));
+        mbar_wait(&bars->chunk, (c0 + (uint32_t)ch) & 1u, 300 + ch);
         tc_fence_after();
         TC_T(40 + warp) TC_TR
 #pragma unroll
@@ -314,6 +339,7 @@ __device__ __noinline__ void gemm_tile(const float *__restrict__ A, int lda, int
         __syncthreads();                     // TMEM may be overwritten by the next chunk / tile after this
         TC_T(48 + warp)
     }
+    if (tid == 0) { bars->blocks_done = g0 + (uint32_t)nkb; bars->chunks_done = c0 + (uint32_t)nchunks; }   // read after the next entry sync
     const int col0 = n0 + half * (BN / 2);
     if (arow < M && col0 < N) {
         float *dst = C + (size_t)arow * ldc + col0;

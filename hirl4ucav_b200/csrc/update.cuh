@@ -12,6 +12,7 @@
 // the ensemble kernel (team = one thread-block cluster per replica).
 #pragma once
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace hirl {
 
@@ -22,7 +23,7 @@ constexpr int GEMM_SMEM_FLOATS = 4 * 16 * TS;  // A,B double buffered
 constexpr int TILE_ROWS = WARPS;             // rows per row-stage chunk
 constexpr int ROWSTAGE_SMEM_FLOATS = 4 * TILE_ROWS * H2 + 64 + TILE_ROWS * 32;
 constexpr int SMEM_FLOATS = ROWSTAGE_SMEM_FLOATS > GEMM_SMEM_FLOATS ? ROWSTAGE_SMEM_FLOATS : GEMM_SMEM_FLOATS;
-constexpr size_t SMEM_BYTES = SMEM_FLOATS * sizeof(float);
+constexpr size_t SMEM_BYTES = SMEM_FLOATS * sizeof(float) > (size_t)tc::SMEM_BYTES ? SMEM_FLOATS * sizeof(float) : (size_t)tc::SMEM_BYTES;
 
 // ---------------------------------------------------------------------------------------------
 // small helpers
@@ -71,6 +72,10 @@ struct Team {
     int rank, size;
     unsigned *flags;  // [size][FLAG_STRIDE], zeroed by the host before every launch
     unsigned gen;
+    // tensor-core tile context of this CTA (TMEM allocated once per kernel)
+    uint32_t tmem_base;
+    char *tc_smem;        // 1024-byte aligned view of the dynamic shared memory
+    tc::Barriers *tc_bars;
 };
 
 // All-to-all flag barrier: every CTA publishes its generation with one release store (no
@@ -108,7 +113,7 @@ __device__ __forceinline__ void team_sync(Team &t) {
 // lane owns outputs n = lane + 32 j.
 template <class L>
 __device__ __forceinline__ void l1_row(const float *tw, const float (&x)[L::k0], float slope, int lane,
-                                       float *h1_out, float *xh_out, float *rs_out) {
+                                       float *h1_out, float *xh_out, float *rs_out, float *h1_tile = nullptr) {
     float z[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) z[j] = tw[L::B1 + lane + 32 * j];
@@ -132,7 +137,9 @@ __device__ __forceinline__ void l1_row(const float *tw, const float (&x)[L::k0],
     for (int j = 0; j < 8; ++j) {
         const int n = lane + 32 * j;
         const float xh = (z[j] - mean) * rstd;
-        h1_out[n] = act_f(fmaf(xh, tw[L::G1 + n], tw[L::BE1 + n]), slope);
+        const float hv = act_f(fmaf(xh, tw[L::G1 + n], tw[L::BE1 + n]), slope);
+        h1_out[n] = hv;
+        if (h1_tile) h1_tile[n] = hv;
         if (xh_out) xh_out[n] = xh;
     }
     if (rs_out && lane == 0) *rs_out = rstd;
@@ -256,7 +263,7 @@ __device__ __forceinline__ void ln1_backward(const float *tw, const float (&dh)[
 // ---------------------------------------------------------------------------------------------
 // FP32 tile GEMM: C[64x64] (+split) = sum_k A . B, three operand arrangements
 // ---------------------------------------------------------------------------------------------
-enum { GEMM_NT = 0, GEMM_NN = 1, GEMM_TN = 2 };
+enum { GEMM_NT = 0, GEMM_NN = 1, GEMM_TN = 2, GEMM_TC = 3 };   // GEMM_TC: tcgen05 tile, both operands K-major
 struct GemmJob {
     const float *A, *B, *bias;
     float *C;
@@ -289,8 +296,8 @@ __device__ __forceinline__ void store_rmajor(float *T, float4 v, int tid) { st4(
 // function with scalar arguments: inlined into the big stage functions the register allocator
 // spilled the prefetch registers, which exposed a full L2 round trip per k-tile.
 template <int MODE>
-__device__ __noinline__ void gemm_tile(const float *__restrict__ Ap, int lda, const float *__restrict__ Bp, int ldb, float *__restrict__ C,
-                                       int ldc, const float *__restrict__ bias, int M, int N, int K, int m0, int n0, int kt_begin,
+__device__ __noinline__ void gemm_tile(const float *Ap, int lda, const float *Bp, int ldb, float *C,
+                                       int ldc, const float *bias, int M, int N, int K, int m0, int n0, int kt_begin,
                                        int kt_end, float *smem) {
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     float *As = smem, *Bs = smem + 2 * 16 * TS;
@@ -369,13 +376,21 @@ __device__ __forceinline__ void run_gemm_jobs(const GemmJob *jobs, int njobs, co
     int total = 0;
     for (int j = 0; j < njobs; ++j) {
         start[j] = total;
-        total += ((jobs[j].M + 63) >> 6) * ((jobs[j].N + 63) >> 6) * jobs[j].nsplit;
+        if (jobs[j].mode == GEMM_TC) total += ((jobs[j].M + tc::BM - 1) / tc::BM) * (jobs[j].N / tc::BN);
+        else total += ((jobs[j].M + 63) >> 6) * ((jobs[j].N + 63) >> 6) * jobs[j].nsplit;
     }
     start[njobs] = total;
     for (int t = tm.rank; t < total; t += tm.size) {
         int j = 0;
         while (t >= start[j + 1]) ++j;
         const GemmJob &J = jobs[j];
+        if (J.mode == GEMM_TC) {
+            const int ntn = J.N / tc::BN;
+            const int local = t - start[j];
+            tc::gemm_tile(J.A, J.lda, J.M, J.B, J.ldb, J.N, J.K, (local / ntn) * tc::BM, (local % ntn) * tc::BN, 0, J.K, J.C, J.ldc, J.bias,
+                          tm.tmem_base, tm.tc_smem, tm.tc_bars);
+            continue;
+        }
         const int ntn = (J.N + 63) >> 6, ntm = (J.M + 63) >> 6;
         int local = t - start[j];
         const int split = local / (ntm * ntn);
@@ -416,11 +431,18 @@ __device__ __forceinline__ float lp_sum(const AgentCtx &c, const Team &tm, int w
     return warp_sum(s);
 }
 
+// eight consecutive batch entries of one column of a [TILE_ROWS][ld] shared tile -> 32 contiguous bytes of a
+// transposed global buffer (full sectors instead of eight scattered 4-byte writes)
+__device__ __forceinline__ void store_col8(float *dst, const float *tile_col, int ld) {
+    st4(dst, make_float4(tile_col[0], tile_col[ld], tile_col[2 * ld], tile_col[3 * ld]));
+    st4(dst + 4, make_float4(tile_col[4 * ld], tile_col[5 * ld], tile_col[6 * ld], tile_col[7 * ld]));
+}
+
 // ---------------------------------------------------------------------------------------------
 // R0: gather + first layers
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void stage_r0(const AgentCtx &c, const hirl_step_t &st, int step, const Team &tm) {
-    const int B = c.B, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ __noinline__ void stage_r0(const AgentCtx &c, const hirl_step_t &st, int step, const Team &tm, float *smem) {
+    const int B = c.B, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
     const float slope = slope_of(c);
     int passes[6];
@@ -432,36 +454,47 @@ __device__ __noinline__ void stage_r0(const AgentCtx &c, const hirl_step_t &st, 
     }
     const int32_t *ion = c.idx_online + (size_t)step * B, *iex = c.idx_expert + (size_t)step * B, *ibc = c.idx_bc + (size_t)step * B;
     for (int task = tm.rank; task < nchunks * np; task += tm.size) {
-        const int pass = passes[task / nchunks];
-        const int b = (task % nchunks) * TILE_ROWS + warp;
-        if (b >= B) continue;
-        float w;
-        if (pass == P_AB) {
-            const float *src = c.bctab + (size_t)__ldg(ibc + b) * BCW;
-            w = lane < BCW ? __ldg(src + lane) : 0.f;
-            if (lane < BCW) c.sc.XB[(size_t)b * BCW + lane] = w;
-        } else {
-            const float *src = b < st.n_online ? c.online + (size_t)__ldg(ion + b) * ROW
-                                               : c.expert + (size_t)__ldg(iex + (b - st.n_online)) * ROW;
-            w = __ldg(src + lane);
-            if (pass == P_C1) c.sc.X[(size_t)b * ROW + lane] = w;
+        const int pass = passes[task / nchunks], chunk = task % nchunks;
+        const int b = chunk * TILE_ROWS + warp;
+        const int slot = bwd_slot(pass);
+        // tensor-core path: back-propagated passes also keep h1 transposed ([k][b]) for the dW GEMM
+        const bool transposed = c.use_tc && slot >= 0 && slot < 4;
+        float *tile = transposed ? smem + warp * H1 : nullptr;
+        if (b < B) {
+            float w;
+            if (pass == P_AB) {
+                const float *src = c.bctab + (size_t)__ldg(ibc + b) * BCW;
+                w = lane < BCW ? __ldg(src + lane) : 0.f;
+                if (lane < BCW) c.sc.XB[(size_t)b * BCW + lane] = w;
+            } else {
+                const float *src = b < st.n_online ? c.online + (size_t)__ldg(ion + b) * ROW
+                                                   : c.expert + (size_t)__ldg(iex + (b - st.n_online)) * ROW;
+                w = __ldg(src + lane);
+                if (pass == P_C1) c.sc.X[(size_t)b * ROW + lane] = w;
+            }
+            if (pass == P_C1 || pass == P_C2) {
+                float x[SA];
+#pragma unroll
+                for (int k = 0; k < SA; ++k) x[k] = __shfl_sync(0xffffffffu, w, k);
+                l1_row<CriticL>(c.critic + (pass == P_C2 ? CriticL::SIZE : 0), x, slope, lane, H1p(c, pass) + (size_t)b * H1,
+                                XH1p(c, slot) + (size_t)b * H1, RS1p(c, slot) + b, tile);
+            } else {
+                float x[S];
+                const int off = pass == P_TA ? SA : 0;  // target actor reads next_state
+#pragma unroll
+                for (int k = 0; k < S; ++k) x[k] = __shfl_sync(0xffffffffu, w, off + k);
+                const float *net = pass == P_TA ? c.tactor : pass == P_BC ? c.bc : c.actor;
+                l1_row<ActorL>(net, x, slope, lane, H1p(c, pass) + (size_t)b * H1,
+                               slot >= 0 ? XH1p(c, slot) + (size_t)b * H1 : nullptr, slot >= 0 ? RS1p(c, slot) + b : nullptr, tile);
+            }
+        } else if (transposed) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tile[lane + 32 * j] = 0.f;
         }
-        if (pass == P_C1 || pass == P_C2) {
-            float x[SA];
-#pragma unroll
-            for (int k = 0; k < SA; ++k) x[k] = __shfl_sync(0xffffffffu, w, k);
-            const int slot = bwd_slot(pass);
-            l1_row<CriticL>(c.critic + (pass == P_C2 ? CriticL::SIZE : 0), x, slope, lane, H1p(c, pass) + (size_t)b * H1,
-                            XH1p(c, slot) + (size_t)b * H1, RS1p(c, slot) + b);
-        } else {
-            float x[S];
-            const int off = pass == P_TA ? SA : 0;  // target actor reads next_state
-#pragma unroll
-            for (int k = 0; k < S; ++k) x[k] = __shfl_sync(0xffffffffu, w, off + k);
-            const float *net = pass == P_TA ? c.tactor : pass == P_BC ? c.bc : c.actor;
-            const int slot = bwd_slot(pass);
-            l1_row<ActorL>(net, x, slope, lane, H1p(c, pass) + (size_t)b * H1,
-                           slot >= 0 ? XH1p(c, slot) + (size_t)b * H1 : nullptr, slot >= 0 ? RS1p(c, slot) + b : nullptr);
+        if (transposed) {
+            __syncthreads();
+            if (tid < H1) store_col8(c.sc.H1T + ((size_t)slot * H1 + tid) * c.BT + chunk * TILE_ROWS, smem + tid, H1);
+            __syncthreads();
         }
     }
 }
@@ -475,19 +508,20 @@ __device__ __forceinline__ GemmJob fwd_job(const AgentCtx &c, int pass, const fl
     J.bias = tw + L::B2;
     J.C = Z2p(c, pass); J.ldc = H2;
     J.M = c.B; J.N = H2; J.K = H1;
-    J.mode = GEMM_NT; J.nsplit = nsplit; J.csplit = z2_split_stride(c);
+    J.mode = c.use_tc ? GEMM_TC : GEMM_NT; J.nsplit = c.use_tc ? 1 : nsplit; J.csplit = z2_split_stride(c);
     return J;
 }
 // dH1[slot] = dZ2[pass] . W2
 template <class L>
-__device__ __forceinline__ GemmJob dx_job(const AgentCtx &c, int pass, const float *tw, int nsplit) {
+__device__ __forceinline__ GemmJob dx_job(const AgentCtx &c, int pass, const float *tw, int nsplit, const float *w2t = nullptr) {
     GemmJob J;
     J.A = Z2p(c, pass); J.lda = H2;
     J.B = tw + L::W2; J.ldb = H1;
+    if (c.use_tc) { J.B = w2t; J.ldb = H2; }     // W2^T [H1][H2]: reduction index contiguous
     J.bias = nullptr;
     J.C = DH1p(c, bwd_slot(pass)); J.ldc = H1;
     J.M = c.B; J.N = H1; J.K = H2;
-    J.mode = GEMM_NN; J.nsplit = nsplit; J.csplit = dh1_split_stride(c);
+    J.mode = c.use_tc ? GEMM_TC : GEMM_NN; J.nsplit = c.use_tc ? 1 : nsplit; J.csplit = dh1_split_stride(c);
     return J;
 }
 // dW2 = dZ2[pass]^T . H1[pass]  (+ second branch)
@@ -501,6 +535,13 @@ __device__ __forceinline__ GemmJob dw_job(const AgentCtx &c, int pass, float *ds
     J.C = dst; J.ldc = H1;
     J.M = H2; J.N = H1;
     J.mode = GEMM_TN; J.nsplit = 1; J.csplit = 0;
+    if (c.use_tc) {   // dW2[n][k] = sum_b dz2T[n][b] h1T[k][b]
+        const int slot = bwd_slot(pass);
+        J.A = c.sc.DZ2T + (size_t)slot * H2 * c.BT; J.lda = c.BT;
+        J.B = c.sc.H1T + (size_t)slot * H1 * c.BT; J.ldb = c.BT;
+        J.K = c.BT;
+        J.mode = GEMM_TC;
+    }
     return J;
 }
 
@@ -647,6 +688,7 @@ __device__ __noinline__ void stage_r2(const AgentCtx &c, const hirl_step_t &st, 
                     a_dbe2[u] += sm.t2[w * H2 + col];
                     a_dw3[u] += sm.t3[w * H2 + col];
                 }
+                if (c.use_tc) store_col8(c.sc.DZ2T + ((size_t)tower * H2 + col) * c.BT + chunk * TILE_ROWS, sm.t0 + col, H2);
             }
             if (tid == 0)
                 for (int w = 0; w < TILE_ROWS; ++w) a_db3 += sm.aux[w * 32];
@@ -681,8 +723,8 @@ __device__ __noinline__ void stage_g3(const AgentCtx &c, const Team &tm, float *
     GemmJob jobs[MAX_JOBS];
     jobs[0] = dw_job<CriticL>(c, P_C1, c.g_critic + CriticL::W2);
     jobs[1] = dw_job<CriticL>(c, P_C2, c.g_critic + CriticL::SIZE + CriticL::W2);
-    jobs[2] = dx_job<CriticL>(c, P_C1, c.critic, c.ns[NS_G3DX]);
-    jobs[3] = dx_job<CriticL>(c, P_C2, c.critic + CriticL::SIZE, c.ns[NS_G3DX]);
+    jobs[2] = dx_job<CriticL>(c, P_C1, c.critic, c.ns[NS_G3DX], c.w2t_critic);
+    jobs[3] = dx_job<CriticL>(c, P_C2, c.critic + CriticL::SIZE, c.ns[NS_G3DX], c.w2t_critic + (size_t)H1 * H2);
     run_gemm_jobs(jobs, 4, tm, smem);
 }
 
@@ -803,12 +845,13 @@ __device__ __forceinline__ float polyak_elem(float t, float p, float tau, float 
 template <class L>
 __device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w, float *gw, const float *gw2b, float *m, float *v, const float *part,
                                            int part_towers, int nslots, float neg_step, float bc2_sqrt, float *target, bool polyak,
-                                           float tau, float one_minus_tau) {
+                                           float tau, float one_minus_tau, float *w2t) {
     const int total = ntowers * L::SIZE;
     for (int e = tm.rank * THREADS + threadIdx.x; e < total; e += tm.size * THREADS) {
         const int tower = e / L::SIZE, off = e - tower * L::SIZE;
         float g;
-        if (off >= L::W2 && off < L::B2) {
+        const bool in_w2 = off >= L::W2 && off < L::B2;
+        if (in_w2) {
             g = __ldcg(gw + e);
             if (gw2b) { g += __ldcg(gw2b + (off - L::W2)); gw[e] = g; }
         } else {
@@ -820,6 +863,10 @@ __device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w
         float wv = w[e], mv = m[e], vv = v[e];
         adam_elem(g, wv, mv, vv, neg_step, bc2_sqrt);
         w[e] = wv; m[e] = mv; v[e] = vv;
+        if (w2t && in_w2) {   // keep W2^T current for the tensor-core dX GEMMs
+            const int i = off - L::W2, n = i / H1, k = i - n * H1;
+            w2t[(size_t)tower * H1 * H2 + (size_t)k * H2 + n] = wv;
+        }
         if (polyak) target[e] = polyak_elem(target[e], wv, tau, one_minus_tau);
     }
 }
@@ -834,7 +881,7 @@ __device__ __noinline__ void stage_g4(const AgentCtx &c, const hirl_step_t &st, 
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
     const int P = gsize < nchunks ? gsize : nchunks;
     adam_arena<CriticL>(tm, 2, c.critic, c.g_critic, nullptr, c.m_critic, c.v_critic, c.sc.PART_C, 2, P, st.critic_neg_step,
-                        st.critic_bc2_sqrt, nullptr, false, 0.f, 0.f);
+                        st.critic_bc2_sqrt, nullptr, false, 0.f, 0.f, c.use_tc ? c.w2t_critic : nullptr);
     if (tm.rank == tm.size - 1 && threadIdx.x < 32) {
         // critic_loss = mse(Q1,y) + mse(Q2,y): even ranks hold tower 0, odd ranks tower 1
         const float s0 = lp_sum(c, tm, 0, 0), s1 = lp_sum(c, tm, 0, 1);
@@ -922,7 +969,7 @@ __device__ __noinline__ void stage_r5(const AgentCtx &c, const hirl_step_t &st, 
 }
 __device__ __noinline__ void stage_g6(const AgentCtx &c, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
-    jobs[0] = dx_job<CriticL>(c, P_QP, c.critic, c.ns[NS_G6]);
+    jobs[0] = dx_job<CriticL>(c, P_QP, c.critic, c.ns[NS_G6], c.w2t_critic);
     run_gemm_jobs(jobs, 1, tm, smem);
 }
 
@@ -1023,6 +1070,7 @@ __device__ __noinline__ void stage_r6(const AgentCtx &c, const hirl_step_t &st, 
 #pragma unroll
                     for (int j = 0; j < A; ++j) a_dw3[j][u] = fmaf(sm.aux[w * 32 + j], hh, a_dw3[j][u]);
                 }
+                if (c.use_tc) store_col8(c.sc.DZ2T + ((size_t)(2 + branch) * H2 + col) * c.BT + chunk * TILE_ROWS, sm.t0 + col, H2);
             }
             if (tid < A)
                 for (int w = 0; w < TILE_ROWS; ++w) a_db3 += sm.aux[w * 32 + tid];
@@ -1059,8 +1107,8 @@ __device__ __noinline__ void stage_g7(const AgentCtx &c, const hirl_step_t &st, 
     // the two branches' dW2 go to separate buffers (twice the tiles in flight); Adam adds them
     jobs[n++] = dw_job<ActorL>(c, P_A, c.g_actor + ActorL::W2);
     if (st.mode == 0) jobs[n++] = dw_job<ActorL>(c, P_AB, c.sc.GW2B);
-    jobs[n++] = dx_job<ActorL>(c, P_A, c.actor, c.ns[NS_G7DX]);
-    if (st.mode == 0) jobs[n++] = dx_job<ActorL>(c, P_AB, c.actor, c.ns[NS_G7DX]);
+    jobs[n++] = dx_job<ActorL>(c, P_A, c.actor, c.ns[NS_G7DX], c.w2t_actor);
+    if (st.mode == 0) jobs[n++] = dx_job<ActorL>(c, P_AB, c.actor, c.ns[NS_G7DX], c.w2t_actor);
     run_gemm_jobs(jobs, n, tm, smem);
 }
 __device__ __noinline__ void stage_r7(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
@@ -1080,7 +1128,7 @@ __device__ __noinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, 
     const int nslots = st.mode == 0 ? 2 * P : P;
     const float tau = c.tau, omt = (float)(1.0 - (double)c.tau);
     adam_arena<ActorL>(tm, 1, c.actor, c.g_actor, st.mode == 0 ? c.sc.GW2B : nullptr, c.m_actor, c.v_actor, c.sc.PART_A, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
-                       c.tactor, st.do_polyak != 0, tau, omt);
+                       c.tactor, st.do_polyak != 0, tau, omt, c.use_tc ? c.w2t_actor : nullptr);
     if (st.do_polyak) polyak_arena<CriticL>(tm, 2, c.critic, c.tcritic, tau, omt);
     if (tm.rank == tm.size - 1 && threadIdx.x < 32) {
         const BcWeight bw = bc_weight_of(c, st, tm);
@@ -1118,7 +1166,7 @@ __device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm
     team_sync(tm);                                                                      \
     if (prof && threadIdx.x == 0) prof[(size_t)(id) * MAX_CTAS * 2 + 1] = clock64();    \
     if (stop_after == (id)) return true;
-    HIRL_STAGE(ST_R0, stage_r0(c, st, step, tm))
+    HIRL_STAGE(ST_R0, stage_r0(c, st, step, tm, smem))
     HIRL_STAGE(ST_G1, stage_g1(c, st, tm, smem))
     HIRL_STAGE(ST_R1, stage_r1(c, st, tm))
     HIRL_STAGE(ST_G2, stage_g2(c, tm, smem))

@@ -13,14 +13,24 @@ __global__ void __launch_bounds__(256, 1) k_test(const float *A, int lda, int M,
     __shared__ uint32_t tmem_slot;
     char *smem = (char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot);
+    if (threadIdx.x == 0) tc::barriers_init(&bars);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     const int ntn = N / tc::BN, ntm = (M + tc::BM - 1) / tc::BM;
-    for (int rep = 0; rep < reps; ++rep)
+    for (int rep = 0; rep < reps; ++rep) {
         for (int t = blockIdx.x; t < ntm * ntn; t += gridDim.x)
             tc::gemm_tile(A, lda, M, B, ldb, N, K, (t / ntn) * tc::BM, (t % ntn) * tc::BN, 0, K, C, ldc, bias, tmem_base, smem, &bars);
+#ifdef TEST_FENCE_BETWEEN
+        // what the persistent kernel does between two GEMM stages: row-stage smem traffic + a gpu-scope fence
+        __syncthreads();
+        for (int i = threadIdx.x; i < 16000; i += blockDim.x) reinterpret_cast<float *>(smem_raw)[i] = (float)i;
+        __syncthreads();
+        if (threadIdx.x < 32) __threadfence();
+        __syncthreads();
+#endif
+    }
     __syncthreads();
     if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base);
 }
