@@ -100,7 +100,7 @@ struct Scratch {
     float *PART_C;   // [MAX_CTAS][2][CriticL::SMALL]
     float *PART_A;   // [MAX_CTAS][ActorL::SMALL]
     float *LP;       // [MAX_CTAS][LP_WORDS]
-    float *GW2B;     // [H2][H1] actor dW2 of the expert-state branch
+    float *GW2P;     // [2 * dw_split][H2][H1] split-K / per-branch partial dW2 buffers, summed in fixed order by Adam
     float *H1T;      // [4][H1][BT]  transposed h1 of C1, C2, A, AB   (tensor-core dW operands, K-major)
     float *DZ2T;     // [4][H2][BT]  transposed dz2 of the same passes
 };
@@ -128,6 +128,7 @@ struct AgentCtx {
     int ns[NS_COUNT];      // split-K factor per GEMM group
     int activation;
     int use_tc;            // 1: 256<->512 contractions on tcgen05 (3xTF32), 0: FP32-FMA tiles
+    int dw_split;          // split-K factor of the dW2 GEMMs (reduction over the batch), >= 1
     int BT;                // batch rounded up to 32: leading dimension of the transposed buffers
     float gamma, tau, noise_clamp, loss_lambda;
 };

@@ -388,6 +388,10 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     proto.use_tc = (cfg->batch >= 512 || (R > 1 && cfg->batch >= 128)) ? 1 : 0;
     if (const char *e = getenv("HIRL_TC")) proto.use_tc = atoi(e) != 0;
     proto.BT = (cfg->batch + 31) & ~31;
+    // dW2 reduces over the batch: split it so that a long reduction still spreads over the SMs (tensor-core tiles:
+    // one split per 512 batch rows = one accumulation chunk; FP32 tiles: one per 1024 rows)
+    proto.dw_split = std::max(1, std::min(8, proto.use_tc ? proto.BT / 512 : proto.BT / 1024));
+    if (const char *e = getenv("HIRL_DW_SPLIT")) proto.dw_split = std::max(1, std::min(8, atoi(e)));
     if (proto.use_tc)
         for (int i = 0; i < NS_COUNT; ++i) proto.ns[i] = 1;
     proto.zsplit = 1;
@@ -411,7 +415,7 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
         SCR(LP, DB_LP, (size_t)MAX_CTAS * LP_WORDS)
 #undef SCR
         const int slots = R > 1 ? h->team_size : MAX_CTAS;
-        if ((rc = dev_alloc(h, &s.GW2B, (size_t)H2 * H1))) return rc;
+        if ((rc = dev_alloc(h, &s.GW2P, (size_t)2 * proto.dw_split * H2 * H1))) return rc;
         if ((rc = dev_alloc(h, &s.H1T, (size_t)4 * H1 * proto.BT))) return rc;
         if ((rc = dev_alloc(h, &s.DZ2T, (size_t)4 * H2 * proto.BT))) return rc;
         if ((rc = dev_alloc(h, &s.PART_C, (size_t)slots * 2 * CriticL::SMALL))) return rc;

@@ -376,7 +376,7 @@ __device__ __forceinline__ void run_gemm_jobs(const GemmJob *jobs, int njobs, co
     int total = 0;
     for (int j = 0; j < njobs; ++j) {
         start[j] = total;
-        if (jobs[j].mode == GEMM_TC) total += ((jobs[j].M + tc::BM - 1) / tc::BM) * (jobs[j].N / tc::BN);
+        if (jobs[j].mode == GEMM_TC) total += ((jobs[j].M + tc::BM - 1) / tc::BM) * (jobs[j].N / tc::BN) * jobs[j].nsplit;
         else total += ((jobs[j].M + 63) >> 6) * ((jobs[j].N + 63) >> 6) * jobs[j].nsplit;
     }
     start[njobs] = total;
@@ -385,10 +385,15 @@ __device__ __forceinline__ void run_gemm_jobs(const GemmJob *jobs, int njobs, co
         while (t >= start[j + 1]) ++j;
         const GemmJob &J = jobs[j];
         if (J.mode == GEMM_TC) {
-            const int ntn = J.N / tc::BN;
-            const int local = t - start[j];
-            tc::gemm_tile(J.A, J.lda, J.M, J.B, J.ldb, J.N, J.K, (local / ntn) * tc::BM, (local % ntn) * tc::BN, 0, J.K, J.C, J.ldc, J.bias,
-                          tm.tmem_base, tm.tc_smem, tm.tc_bars);
+            const int ntn = J.N / tc::BN, per = ((J.M + tc::BM - 1) / tc::BM) * ntn;
+            int local = t - start[j];
+            const int split = local / per;
+            local -= split * per;
+            const int nkb = (J.K + tc::BK - 1) / tc::BK;   // split-K in whole 32-wide blocks
+            const int k0 = (int)(((long long)nkb * split) / J.nsplit) * tc::BK;
+            const int k1 = min(J.K, (int)(((long long)nkb * (split + 1)) / J.nsplit) * tc::BK);
+            tc::gemm_tile(J.A, J.lda, J.M, J.B, J.ldb, J.N, J.K, (local / ntn) * tc::BM, (local % ntn) * tc::BN, k0, k1,
+                          J.C + (size_t)split * J.csplit, J.ldc, split == 0 ? J.bias : nullptr, tm.tmem_base, tm.tc_smem, tm.tc_bars);
             continue;
         }
         const int ntn = (J.N + 63) >> 6, ntm = (J.M + 63) >> 6;
@@ -534,7 +539,7 @@ __device__ __forceinline__ GemmJob dw_job(const AgentCtx &c, int pass, float *ds
     J.bias = nullptr;
     J.C = dst; J.ldc = H1;
     J.M = H2; J.N = H1;
-    J.mode = GEMM_TN; J.nsplit = 1; J.csplit = 0;
+    J.mode = GEMM_TN; J.nsplit = c.dw_split; J.csplit = (size_t)H2 * H1;
     if (c.use_tc) {   // dW2[n][k] = sum_b dz2T[n][b] h1T[k][b]
         const int slot = bwd_slot(pass);
         J.A = c.sc.DZ2T + (size_t)slot * H2 * c.BT; J.lda = c.BT;
@@ -721,8 +726,10 @@ __device__ __noinline__ void stage_r2(const AgentCtx &c, const hirl_step_t &st, 
 
 __device__ __noinline__ void stage_g3(const AgentCtx &c, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
-    jobs[0] = dw_job<CriticL>(c, P_C1, c.g_critic + CriticL::W2);
-    jobs[1] = dw_job<CriticL>(c, P_C2, c.g_critic + CriticL::SIZE + CriticL::W2);
+    // split-K over the batch: partial dW2 buffers, summed by the Adam stage (direct when not split)
+    const size_t part = (size_t)H2 * H1 * c.dw_split;
+    jobs[0] = dw_job<CriticL>(c, P_C1, c.dw_split > 1 ? c.sc.GW2P : c.g_critic + CriticL::W2);
+    jobs[1] = dw_job<CriticL>(c, P_C2, c.dw_split > 1 ? c.sc.GW2P + part : c.g_critic + CriticL::SIZE + CriticL::W2);
     jobs[2] = dx_job<CriticL>(c, P_C1, c.critic, c.ns[NS_G3DX], c.w2t_critic);
     jobs[3] = dx_job<CriticL>(c, P_C2, c.critic + CriticL::SIZE, c.ns[NS_G3DX], c.w2t_critic + (size_t)H1 * H2);
     run_gemm_jobs(jobs, 4, tm, smem);
@@ -843,7 +850,7 @@ __device__ __forceinline__ float polyak_elem(float t, float p, float tau, float 
 }
 
 template <class L>
-__device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w, float *gw, const float *gw2b, float *m, float *v, const float *part,
+__device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w, float *gw, const float *w2parts, int nparts, float *m, float *v, const float *part,
                                            int part_towers, int nslots, float neg_step, float bc2_sqrt, float *target, bool polyak,
                                            float tau, float one_minus_tau, float *w2t) {
     const int total = ntowers * L::SIZE;
@@ -852,8 +859,14 @@ __device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w
         float g;
         const bool in_w2 = off >= L::W2 && off < L::B2;
         if (in_w2) {
-            g = __ldcg(gw + e);
-            if (gw2b) { g += __ldcg(gw2b + (off - L::W2)); gw[e] = g; }
+            if (nparts > 0) {   // fixed-order sum of the split-K / per-branch partial buffers
+                const float *p0 = w2parts + (size_t)tower * nparts * H2 * H1 + (off - L::W2);
+                g = __ldcg(p0);
+                for (int q = 1; q < nparts; ++q) g += __ldcg(p0 + (size_t)q * H2 * H1);
+                gw[e] = g;
+            } else {
+                g = __ldcg(gw + e);
+            }
         } else {
             const int si = L::small_index(off);
             g = 0.f;
@@ -880,7 +893,7 @@ __device__ __forceinline__ void polyak_arena(const Team &tm, int ntowers, const 
 __device__ __noinline__ void stage_g4(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
     const int P = gsize < nchunks ? gsize : nchunks;
-    adam_arena<CriticL>(tm, 2, c.critic, c.g_critic, nullptr, c.m_critic, c.v_critic, c.sc.PART_C, 2, P, st.critic_neg_step,
+    adam_arena<CriticL>(tm, 2, c.critic, c.g_critic, c.sc.GW2P, c.dw_split > 1 ? c.dw_split : 0, c.m_critic, c.v_critic, c.sc.PART_C, 2, P, st.critic_neg_step,
                         st.critic_bc2_sqrt, nullptr, false, 0.f, 0.f, c.use_tc ? c.w2t_critic : nullptr);
     if (tm.rank == tm.size - 1 && threadIdx.x < 32) {
         // critic_loss = mse(Q1,y) + mse(Q2,y): even ranks hold tower 0, odd ranks tower 1
@@ -1104,9 +1117,9 @@ __device__ __noinline__ void stage_r6(const AgentCtx &c, const hirl_step_t &st, 
 __device__ __noinline__ void stage_g7(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
     int n = 0;
-    // the two branches' dW2 go to separate buffers (twice the tiles in flight); Adam adds them
-    jobs[n++] = dw_job<ActorL>(c, P_A, c.g_actor + ActorL::W2);
-    if (st.mode == 0) jobs[n++] = dw_job<ActorL>(c, P_AB, c.sc.GW2B);
+    // the two branches' dW2 (each split-K over the batch) go to separate partial buffers; Adam adds them
+    jobs[n++] = dw_job<ActorL>(c, P_A, c.sc.GW2P);
+    if (st.mode == 0) jobs[n++] = dw_job<ActorL>(c, P_AB, c.sc.GW2P + (size_t)H2 * H1 * c.dw_split);
     jobs[n++] = dx_job<ActorL>(c, P_A, c.actor, c.ns[NS_G7DX], c.w2t_actor);
     if (st.mode == 0) jobs[n++] = dx_job<ActorL>(c, P_AB, c.actor, c.ns[NS_G7DX], c.w2t_actor);
     run_gemm_jobs(jobs, n, tm, smem);
@@ -1127,7 +1140,7 @@ __device__ __noinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, 
     const int P = gsize < nchunks ? gsize : nchunks;
     const int nslots = st.mode == 0 ? 2 * P : P;
     const float tau = c.tau, omt = (float)(1.0 - (double)c.tau);
-    adam_arena<ActorL>(tm, 1, c.actor, c.g_actor, st.mode == 0 ? c.sc.GW2B : nullptr, c.m_actor, c.v_actor, c.sc.PART_A, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
+    adam_arena<ActorL>(tm, 1, c.actor, c.g_actor, c.sc.GW2P, (st.mode == 0 ? 2 : 1) * c.dw_split, c.m_actor, c.v_actor, c.sc.PART_A, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
                        c.tactor, st.do_polyak != 0, tau, omt, c.use_tc ? c.w2t_actor : nullptr);
     if (st.do_polyak) polyak_arena<CriticL>(tm, 2, c.critic, c.tcritic, tau, omt);
     if (tm.rank == tm.size - 1 && threadIdx.x < 32) {

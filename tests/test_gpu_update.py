@@ -152,9 +152,12 @@ def test_learn_many_is_bit_identical_to_single_calls_and_deterministic():
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("tc_mode", ["0", "1"])
 @pytest.mark.parametrize("ns", ["1", "2", "4"])
-def test_split_k_variants_agree(ns, monkeypatch):
-    monkeypatch.setenv("HIRL_NSPLIT", ns)
+def test_split_k_variants_agree(ns, tc_mode, monkeypatch):
+    monkeypatch.setenv("HIRL_NSPLIT", ns)        # split-K of the forward / dX tiles (FP32 path)
+    monkeypatch.setenv("HIRL_DW_SPLIT", ns)      # split of the batch reduction of dW2 (both paths)
+    monkeypatch.setenv("HIRL_TC", tc_mode)
     sc = scenarios.make_scenario(1500, 600)
     orc = scenarios.build_agent(OracleAgent, sc, 48, 0)
     ag = scenarios.build_agent(Agent, sc, 48, 0)
@@ -166,6 +169,8 @@ def test_split_k_variants_agree(ns, monkeypatch):
         out = ag.learn(100, 10, 0, forced={"online": d["online"], "expert": d["expert"], "bc": d["bc"], "noise": d["noise"]})
         assert abs(float(out[0]) - float(ref[0])) <= 1e-5 * abs(float(ref[0]))
         assert rel(ag.export_grads(_lib.NET_CRITIC), grads_flat(r32, "critic.grads")) <= 1e-5
+        if "actor.grads" in r32 and r32.get("soft_count_margin", 1) > 1e-4:
+            assert rel(ag.export_grads(_lib.NET_ACTOR), grads_flat(r32, "actor.grads")) <= 1e-5
         sync_to_oracle(ag, orc)
 
 
