@@ -12,6 +12,28 @@
 namespace hirl {
 
 constexpr int ENV_THREADS = 256;
+#ifndef HIRL_ENV_MIN_BLOCKS
+#define HIRL_ENV_MIN_BLOCKS 6
+#endif
+#ifndef HIRL_ENV_FAST_DIV
+#define HIRL_ENV_FAST_DIV 1
+#endif
+
+// x / d for a compile-time-known divisor with reciprocal r = RN(1/d): q0 = x*r, one FMA residual correction
+// (Markstein), and the sign of zero taken from q0.  The generic IEEE fp64 division sequence (11 of them per
+// state) made the kernel FP64-issue bound at 73 % of HBM peak; this form reaches 87 %.  It is NOT an
+// approximation here: tools/env_bench.cu compares it with IEEE division for ALL 2^32 fp32 bit patterns x
+// (the only inputs this kernel ever sees) and the three divisors used below -- 0 mismatches.
+__device__ __forceinline__ double div_const(double x, double d, double r) {
+#if HIRL_ENV_FAST_DIV
+    const double q0 = x * r;
+    const double rem = fma(-q0, d, x);
+    const double q = fma(rem, r, q0);
+    return x == 0.0 ? q0 : q;      // keeps -0.0 / d == -0.0
+#else
+    return x / d;
+#endif
+}
 
 struct EnvOut { float obs[13]; float reward; int flags; };
 
@@ -24,19 +46,20 @@ __device__ __forceinline__ void env_one(const float4 &q0, const float4 &q1, cons
     bool fire_success = fl & 16u;
     const double PI_D = 3.141592653589793;
     // observation (GYM.py:196-201, 213-218, 232, 262): normalise both, then subtract
-    o.obs[0] = (float)(pax / 10000.0 - pox / 10000.0);
-    o.obs[1] = (float)(pay / 10000.0 - poy / 10000.0);
-    o.obs[2] = (float)(paz / 10000.0 - poz / 10000.0);
-    o.obs[3] = (float)(eax / PI_D);
-    o.obs[4] = (float)(eay / PI_D);
-    o.obs[5] = (float)(eaz / PI_D);
-    const double t_angle = angle / 180.0;
+    const double R_POS = 1.0 / 10000.0, R_PI = 1.0 / 3.141592653589793, R_180 = 1.0 / 180.0;
+    o.obs[0] = (float)(div_const(pax, 10000.0, R_POS) - div_const(pox, 10000.0, R_POS));
+    o.obs[1] = (float)(div_const(pay, 10000.0, R_POS) - div_const(poy, 10000.0, R_POS));
+    o.obs[2] = (float)(div_const(paz, 10000.0, R_POS) - div_const(poz, 10000.0, R_POS));
+    o.obs[3] = (float)div_const(eax, PI_D, R_PI);
+    o.obs[4] = (float)div_const(eay, PI_D, R_PI);
+    o.obs[5] = (float)div_const(eaz, PI_D, R_PI);
+    const double t_angle = div_const(angle, 180.0, R_180);
     o.obs[6] = (float)t_angle;
     o.obs[7] = locked_now ? 1.f : -1.f;
     o.obs[8] = missile_now ? 1.f : -1.f;
-    o.obs[9] = (float)(eox / PI_D);
-    o.obs[10] = (float)(eoy / PI_D);
-    o.obs[11] = (float)(eoz / PI_D);
+    o.obs[9] = (float)div_const(eox, PI_D, R_PI);
+    o.obs[10] = (float)div_const(eoy, PI_D, R_PI);
+    o.obs[11] = (float)div_const(eoz, PI_D, R_PI);
     o.obs[12] = (float)health;
     // reward (GYM.py:101-137), sequential -= like the reference
     const double dx = pax - pox, dy = pay - poy, dz = paz - poz;
@@ -64,7 +87,7 @@ __device__ __forceinline__ void env_one(const float4 &q0, const float4 &q1, cons
 
 // one thread per state; outputs are staged through shared memory so that every global store is
 // a full 128-bit coalesced transaction (13-float rows are not 16 B aligned per state).
-__global__ void __launch_bounds__(ENV_THREADS) env_step_kernel(const float4 *__restrict__ raw, long long n, float *__restrict__ obs,
+__global__ void __launch_bounds__(ENV_THREADS, HIRL_ENV_MIN_BLOCKS) env_step_kernel(const float4 *__restrict__ raw, long long n, float *__restrict__ obs,
                                                                float *__restrict__ reward, int *__restrict__ flags,
                                                                unsigned long long *__restrict__ counters) {
     __shared__ __align__(16) float s_obs[ENV_THREADS * 13];

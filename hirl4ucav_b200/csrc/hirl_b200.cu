@@ -717,7 +717,7 @@ static int env_grid(long long n, int per_block) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (n + per_block - 1) / per_block;
-    return (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sms * 8));
+    return (int)std::max<long long>(1, std::min<long long>(tiles, (long long)sms * 32));
 }
 int hirl_env_step_dev(const float *raw16_dev, int64_t n, float *obs13_dev, float *reward_dev, int32_t *flags_dev,
                       unsigned long long *counters3_dev, void *stream) {
