@@ -26,6 +26,21 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# torchrun exports OMP_NUM_THREADS=1; the CPU legs (reference arm, cpu_baseline) run on rank 0 only and
+# are meant to use every host core, so undo that before torch / MKL read the environment.
+if os.environ.get("OMP_NUM_THREADS") == "1":
+    os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
+# stdout carries exactly ONE JSON line: everything else that libraries print (e.g. NCCL's version banner)
+# goes to stderr until the result is ready.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -136,7 +151,7 @@ def run_reference(args):
             "config": config_of(args, wl),
             "cpu_baseline": {"value": val, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_of(args, wl):
@@ -279,7 +294,7 @@ def run_ensemble(args):
                 "roofline": {"kernel": "hirl_ensemble_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32.value, "unit": "TFLOP/s",
                              "frac": achieved / fp32.value, "traffic": None, "hbm_stream_gbs_if_weights_streamed": hbm,
                              "note": "weights + Adam state of 128 replicas = 1.1 GB > L2: 11.1 MB algorithmic HBM bytes per replica-update"}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -380,7 +395,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": val, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{calls} learn() calls of the same workload after 6 warm-up calls ({dt:.1f} s); oracle/hirl_oracle.py, "
                                           "bit-identical to the unmodified reference in the build container"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

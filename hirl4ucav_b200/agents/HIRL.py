@@ -70,15 +70,7 @@ class Agent(object):
             print(f"upsample expert data num is {np.size(self.target_indices)}")
 
         # host parameter containers, created in the reference's order (RNG stream!)
-        mk_a = lambda tag: nets.make_actor(stateDim, actionDim, full1Dim, full2Dim, tag + name, self._GAIN)
-        mk_c = lambda tag: nets.make_critic(stateDim, actionDim, full1Dim, full2Dim, tag + name, self._GAIN)
-        self.actor = mk_a("Actor_")
-        self.targetActor = mk_a("TargetActor_")
-        self.targetActor.load_state_dict(self.actor.state_dict())
-        self.critic = mk_c("Critic_")
-        self.targetCritic = mk_c("TargetCritic_")
-        self.targetCritic.load_state_dict(self.critic.state_dict())
-        self.bc_actor = mk_a("") if self._MODE == 0 else None
+        self._make_nets(stateDim, actionDim, full1Dim, full2Dim, name)
         if self._MODE == 0:
             print(f"buffer upsample is {self.buffer_upsample}, expert upsample is {self.expert_upsample}, "
                   f"loss lambda is {self.loss_lambda}")
@@ -117,7 +109,20 @@ class Agent(object):
         self._st_out_t = mk((K, _lib.OUT_SCALARS), torch.float32)
         self._st_out = self._st_out_t.numpy()
         self._ret = (np.float32(0), np.float32(0), np.float32(0), np.float32(0), 0.0, bc_weight)
+        self._noise_mean = torch.zeros(self.actionDim)
+        self._noise_std = torch.ones(self.actionDim) * self.TD3LearningNoise
         self.last_draws = {}
+
+    def _make_nets(self, stateDim, actionDim, full1Dim, full2Dim, name):
+        mk_a = lambda tag: nets.make_actor(stateDim, actionDim, full1Dim, full2Dim, tag + name, self._GAIN)
+        mk_c = lambda tag: nets.make_critic(stateDim, actionDim, full1Dim, full2Dim, tag + name, self._GAIN)
+        self.actor = mk_a("Actor_")
+        self.targetActor = mk_a("TargetActor_")
+        self.targetActor.load_state_dict(self.actor.state_dict())
+        self.critic = mk_c("Critic_")
+        self.targetCritic = mk_c("TargetCritic_")
+        self.targetCritic.load_state_dict(self.critic.state_dict())
+        self.bc_actor = mk_a("") if self._MODE == 0 else None
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -235,8 +240,7 @@ class Agent(object):
         if "noise" in forced:
             noise = np.asarray(forced["noise"], np.float32)
         else:
-            noise = torch.normal(mean=torch.zeros(self.actionDim),
-                                 std=torch.ones(self.actionDim) * self.TD3LearningNoise).numpy()
+            noise = torch.normal(mean=self._noise_mean, std=self._noise_std).numpy()   # same stream as HIRL.py:265
         # schedule + Adam scalars
         do_actor = bool(self.actorTrainable)
         self._critic_t += 1

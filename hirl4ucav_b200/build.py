@@ -9,11 +9,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
-LIB_PATH = os.path.join(OUT_DIR, "libhirl_b200.so")
+LIB_PATH = os.environ.get("HIRL_LIB_PATH") or os.path.join(OUT_DIR, "libhirl_b200.so")   # override: A/B builds
 SOURCES = ["hirl_b200.cu"]
-DEPS = ["common.cuh", "update.cuh", "env.cuh", "ensemble.cuh", "../../include/hirl_b200.h"]
+DEPS = ["common.cuh", "update.cuh", "tc_gemm.cuh", "env.cuh", "../../include/hirl_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"] + (os.environ.get("HIRL_NVCC_EXTRA", "").split())
 
 
 def _nvcc() -> str:

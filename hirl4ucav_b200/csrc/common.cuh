@@ -81,7 +81,7 @@ enum Stage {
 
 // debug buffer ids (hirl_debug_export)
 enum DebugBuf { DB_X = 0, DB_XB, DB_H1, DB_XH1, DB_RS1, DB_Z2, DB_DH1, DB_APRIME, DB_PI, DB_PIB, DB_ABC,
-                DB_Y, DB_Q, DB_TQ, DB_RLQ, DB_SOFTQ, DB_GPI, DB_LP };
+                DB_Y, DB_Q, DB_TQ, DB_RLQ, DB_SOFTQ, DB_GPI, DB_LP, DB_GW2P };
 
 struct Scratch {
     float *X;        // [B][32] gathered replay rows

@@ -602,10 +602,10 @@ static int check_steps(hirl_agent *h, int k_steps, const hirl_step_t *steps) {
     if (k_steps < 1 || k_steps > h->cfg.max_steps) return fail(HIRL_E_INVALID, "k_steps outside [1, cfg.max_steps]");
     for (int k = 0; k < k_steps * (int)h->ctxs.size(); ++k) {
         const hirl_step_t &s = steps[k];
-        if (s.n_online < 0 || s.n_expert < 0 || s.n_online + s.n_expert != h->cfg.batch)
+        if (s.mode != 2 && (s.n_online < 0 || s.n_expert < 0 || s.n_online + s.n_expert != h->cfg.batch))
             return fail(HIRL_E_INVALID, "n_online + n_expert must equal the batch size");
-        if (s.mode < 0 || s.mode > 1) return fail(HIRL_E_INVALID, "bad step mode");
-        if (s.mode == 0 && s.do_actor && h->cfg.bc_rows < h->cfg.batch) return fail(HIRL_E_INVALID, "expert table smaller than the batch (np.random.choice without replacement)");
+        if (s.mode < 0 || s.mode > 2) return fail(HIRL_E_INVALID, "bad step mode");
+        if (s.mode != 1 && s.do_actor && h->cfg.bc_rows < h->cfg.batch) return fail(HIRL_E_INVALID, "expert table smaller than the batch (np.random.choice without replacement)");
     }
     return 0;
 }
@@ -700,6 +700,7 @@ int hirl_debug_export(hirl_agent_t *h, int buffer_id, int pass, float *dst, size
         case DB_RLQ: src = s.RLQ; cnt = B; break;
         case DB_SOFTQ: src = s.SOFTQ; cnt = B; break;
         case DB_LP: src = s.LP; cnt = (size_t)MAX_CTAS * LP_WORDS; break;
+        case DB_GW2P: src = s.GW2P; cnt = (size_t)2 * h->ctxs[0].dw_split * H2 * H1; break;
         default: return fail(HIRL_E_INVALID, "bad debug buffer id");
     }
     if (n_out) *n_out = cnt;

@@ -452,10 +452,14 @@ __device__ __noinline__ void stage_r0(const AgentCtx &c, const hirl_step_t &st, 
     const float slope = slope_of(c);
     int passes[6];
     int np = 0;
-    passes[np++] = P_TA; passes[np++] = P_C1; passes[np++] = P_C2;
-    if (st.do_actor) {
-        passes[np++] = P_A;
-        if (st.mode == 0) { passes[np++] = P_AB; passes[np++] = P_BC; }
+    if (st.mode == 2) {            // behaviour cloning (BC.py:160-185): the expert-state actor pass only
+        passes[np++] = P_AB;
+    } else {
+        passes[np++] = P_TA; passes[np++] = P_C1; passes[np++] = P_C2;
+        if (st.do_actor) {
+            passes[np++] = P_A;
+            if (st.mode == 0) { passes[np++] = P_AB; passes[np++] = P_BC; }
+        }
     }
     const int32_t *ion = c.idx_online + (size_t)step * B, *iex = c.idx_expert + (size_t)step * B, *ibc = c.idx_bc + (size_t)step * B;
     for (int task = tm.rank; task < nchunks * np; task += tm.size) {
@@ -554,6 +558,11 @@ __device__ __noinline__ void stage_g1(const AgentCtx &c, const hirl_step_t &st, 
     GemmJob jobs[MAX_JOBS];
     int n = 0;
     const int ns = g1_split(c, st);
+    if (st.mode == 2) {
+        jobs[n++] = fwd_job<ActorL>(c, P_AB, c.actor, ns);
+        run_gemm_jobs(jobs, n, tm, smem);
+        return;
+    }
     jobs[n++] = fwd_job<ActorL>(c, P_TA, c.tactor, ns);
     jobs[n++] = fwd_job<CriticL>(c, P_C1, c.critic, ns);
     jobs[n++] = fwd_job<CriticL>(c, P_C2, c.critic + CriticL::SIZE, ns);
@@ -993,7 +1002,8 @@ __device__ __forceinline__ BcWeight bc_weight_of(const AgentCtx &c, const hirl_s
     BcWeight r;
     r.count = 0.f;
     double w = (double)st.bc_weight_now;
-    if (st.mode != 0) w = 0.0;
+    if (st.mode == 2) w = 1.0;       // BC: the loss IS the cloning term
+    else if (st.mode != 0) w = 0.0;
     else if (st.bc_weight_now == 100.f) {
         r.count = lp_sum(c, tm, 1);
         const float mean = st.force_soft_weight >= 0.f ? st.force_soft_weight : r.count / (float)c.B;  // .float().mean()
@@ -1021,7 +1031,8 @@ __device__ __noinline__ void stage_r6(const AgentCtx &c, const hirl_step_t &st, 
     BcWeight bw;
     bw.w = sm.red[32]; bw.one_minus_w = sm.red[33]; bw.count = 0.f;
     float bc_sq = 0.f, fire_sq = 0.f;
-    const bool active = grank < gsize && (branch == 0 || st.mode == 0);
+    const bool active = grank < gsize && (branch == 0 ? st.mode != 2 : st.mode != 1);
+    const float bc_scale = st.mode == 2 ? 1.f : bw.w * c.loss_lambda;   // BC.py:179 has no loss_lambda
     if (active) {
         // ---- step 1 (branch 0): LayerNorm1 backward of Q1(s,pi) -> unit gradient w.r.t. pi
         if (branch == 0) {
@@ -1052,7 +1063,7 @@ __device__ __noinline__ void stage_r6(const AgentCtx &c, const hirl_step_t &st, 
                             bc_sq = fmaf(diff, diff, bc_sq);
                             if (j == 3) fire_sq = fmaf(diff, diff, fire_sq);
                         }
-                        dpi = ((2.f / (float)(A * B)) * diff) * (bw.w * c.loss_lambda);
+                        dpi = ((2.f / (float)(A * B)) * diff) * bc_scale;
                     }
                     dpre[j] = dpi * (1.f - pi * pi);   // tanh backward
                 }
@@ -1118,38 +1129,47 @@ __device__ __noinline__ void stage_g7(const AgentCtx &c, const hirl_step_t &st, 
     GemmJob jobs[MAX_JOBS];
     int n = 0;
     // the two branches' dW2 (each split-K over the batch) go to separate partial buffers; Adam adds them
-    jobs[n++] = dw_job<ActorL>(c, P_A, c.sc.GW2P);
-    if (st.mode == 0) jobs[n++] = dw_job<ActorL>(c, P_AB, c.sc.GW2P + (size_t)H2 * H1 * c.dw_split);
-    jobs[n++] = dx_job<ActorL>(c, P_A, c.actor, c.ns[NS_G7DX], c.w2t_actor);
-    if (st.mode == 0) jobs[n++] = dx_job<ActorL>(c, P_AB, c.actor, c.ns[NS_G7DX], c.w2t_actor);
+    if (st.mode != 2) jobs[n++] = dw_job<ActorL>(c, P_A, c.sc.GW2P);
+    if (st.mode != 1) jobs[n++] = dw_job<ActorL>(c, P_AB, c.sc.GW2P + (size_t)H2 * H1 * c.dw_split);
+    if (st.mode != 2) jobs[n++] = dx_job<ActorL>(c, P_A, c.actor, c.ns[NS_G7DX], c.w2t_actor);
+    if (st.mode != 1) jobs[n++] = dx_job<ActorL>(c, P_AB, c.actor, c.ns[NS_G7DX], c.w2t_actor);
     run_gemm_jobs(jobs, n, tm, smem);
 }
 __device__ __noinline__ void stage_r7(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS;
     const int gsize = tm.size >> 1, branch = tm.rank & 1, grank = tm.rank >> 1;
     RowSmem sm = row_smem(smem);
-    if (grank < gsize && (branch == 0 || st.mode == 0)) {
+    if (grank < gsize && (branch == 0 ? st.mode != 2 : st.mode != 1)) {
         Ln1Acc<ActorL> acc;
         ln1_bwd_rows<ActorL>(c, c.actor, branch ? 3 : 2, c.ns[NS_G7DX], branch ? c.sc.XB : c.sc.X, branch ? BCW : ROW, grank, gsize, acc, sm, nullptr);
         const int P = gsize < nchunks ? gsize : nchunks;
         if (grank < P) ln1_write_partial<ActorL>(c.sc.PART_A + ((size_t)branch * P + grank) * ActorL::SMALL, acc);
     }
 }
-__device__ __noinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+// forceinline, unlike the other stages: as a separate function the nvcc 12.9 build of this stage read a wrong
+// dW2-partials base in warps 1-7 (compute-sanitizer: out-of-bounds __ldcg in adam_arena) although the SASS data
+// flow looks right and any probe added to it made the fault disappear; inlined it is exact (tests/test_gpu_update.py).
+__device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
     const int P = gsize < nchunks ? gsize : nchunks;
     const int nslots = st.mode == 0 ? 2 * P : P;
     const float tau = c.tau, omt = (float)(1.0 - (double)c.tau);
-    adam_arena<ActorL>(tm, 1, c.actor, c.g_actor, c.sc.GW2P, (st.mode == 0 ? 2 : 1) * c.dw_split, c.m_actor, c.v_actor, c.sc.PART_A, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
+    // mode 2 (BC) only has the expert-state branch: its partial slots / dW2 parts are the second half
+    const size_t part_off = st.mode == 2 ? (size_t)P * ActorL::SMALL : 0, w2_off = st.mode == 2 ? (size_t)H2 * H1 * c.dw_split : 0;
+    const float *part_a = c.sc.PART_A + part_off;
+    const float *w2parts = c.sc.GW2P + w2_off;
+    adam_arena<ActorL>(tm, 1, c.actor, c.g_actor, w2parts, (st.mode == 0 ? 2 : 1) * c.dw_split, c.m_actor, c.v_actor, part_a, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
                        c.tactor, st.do_polyak != 0, tau, omt, c.use_tc ? c.w2t_actor : nullptr);
     if (st.do_polyak) polyak_arena<CriticL>(tm, 2, c.critic, c.tcritic, tau, omt);
     if (tm.rank == tm.size - 1 && threadIdx.x < 32) {
         const BcWeight bw = bc_weight_of(c, st, tm);
-        const float rl_loss = -(lp_sum(c, tm, 2) / (float)c.B);                           // HIRL.py:297
+        const float rl_loss = st.mode == 2 ? 0.f : -(lp_sum(c, tm, 2) / (float)c.B);      // HIRL.py:297
         float bc_loss = 0.f, fire = 0.f;
         if (st.mode == 0) {
             bc_loss = __fmul_rn(lp_sum(c, tm, 3) / (float)(A * c.B), c.loss_lambda);       // HIRL.py:311
             fire = lp_sum(c, tm, 4) / (float)c.B;                                          // HIRL.py:319 (x lambda on the host, in double)
+        } else if (st.mode == 2) {
+            bc_loss = lp_sum(c, tm, 3) / (float)(A * c.B);                                 // BC.py:179
         }
         if (threadIdx.x == 0) {
         c.carry[1] = __fadd_rn(__fmul_rn(bc_loss, bw.w), __fmul_rn(rl_loss, bw.one_minus_w));  // HIRL.py:321
@@ -1179,19 +1199,28 @@ __device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm
     team_sync(tm);                                                                      \
     if (prof && threadIdx.x == 0) prof[(size_t)(id) * MAX_CTAS * 2 + 1] = clock64();    \
     if (stop_after == (id)) return true;
+    // NOTE: every stage function has exactly ONE call site.  ptxas specialises these non-inlined functions per
+    // kernel and lets them read caller registers directly; with a second call site (a separate BC sequence) the
+    // actor Adam received a corrupted pointer in some threads.  One call site each keeps that analysis trivially
+    // consistent; modes skip stages with conditions instead.
+    const bool bc_only = st.mode == 2;   // behaviour cloning (BC.py:160-185): expert-state actor pass, backward, Adam
     HIRL_STAGE(ST_R0, stage_r0(c, st, step, tm, smem))
     HIRL_STAGE(ST_G1, stage_g1(c, st, tm, smem))
-    HIRL_STAGE(ST_R1, stage_r1(c, st, tm))
-    HIRL_STAGE(ST_G2, stage_g2(c, tm, smem))
-    HIRL_STAGE(ST_R2, stage_r2(c, st, tm, smem))
-    HIRL_STAGE(ST_G3, stage_g3(c, tm, smem))
-    HIRL_STAGE(ST_R3, stage_r3(c, tm, smem))
-    HIRL_STAGE(ST_G4, stage_g4(c, st, tm))
-    if (st.do_actor) {
-        HIRL_STAGE(ST_R4, stage_r4(c, st, tm))
-        HIRL_STAGE(ST_G5, stage_g5(c, st, tm, smem))
-        HIRL_STAGE(ST_R5, stage_r5(c, st, tm, smem))
-        HIRL_STAGE(ST_G6, stage_g6(c, tm, smem))
+    if (!bc_only) {
+        HIRL_STAGE(ST_R1, stage_r1(c, st, tm))
+        HIRL_STAGE(ST_G2, stage_g2(c, tm, smem))
+        HIRL_STAGE(ST_R2, stage_r2(c, st, tm, smem))
+        HIRL_STAGE(ST_G3, stage_g3(c, tm, smem))
+        HIRL_STAGE(ST_R3, stage_r3(c, tm, smem))
+        HIRL_STAGE(ST_G4, stage_g4(c, st, tm))
+    }
+    if (bc_only || st.do_actor) {
+        if (!bc_only) {
+            HIRL_STAGE(ST_R4, stage_r4(c, st, tm))
+            HIRL_STAGE(ST_G5, stage_g5(c, st, tm, smem))
+            HIRL_STAGE(ST_R5, stage_r5(c, st, tm, smem))
+            HIRL_STAGE(ST_G6, stage_g6(c, tm, smem))
+        }
         HIRL_STAGE(ST_R6, stage_r6(c, st, tm, smem))
         HIRL_STAGE(ST_G7, stage_g7(c, st, tm, smem))
         HIRL_STAGE(ST_R7, stage_r7(c, st, tm, smem))

@@ -92,7 +92,8 @@ typedef struct hirl_step {
     float critic_bc2_sqrt;   /* sqrt(1-beta2^t)                                              */
     float actor_neg_step;
     float actor_bc2_sqrt;
-    int32_t mode;            /* 0 HIRL (HIRL.py), 1 TD3 (TD3.py:201-260: no BC terms)        */
+    int32_t mode;            /* 0 HIRL (HIRL.py), 1 TD3 (TD3.py:201-260: no BC terms),
+                                2 BC (BC.py:160-185: MSE on an expert batch, actor Adam only)  */
 } hirl_step_t;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

@@ -295,6 +295,37 @@ def test_td3_mode_matches_oracle():
         sync_to_oracle(ag, orc)
 
 
+def test_bc_mode_matches_oracle_and_reference_fixture(golden_dir):
+    from hirl4ucav_b200.agents.BC import Agent as BCAgent
+    from oracle.hirl_oracle import OracleBC
+    fx = np.load(os.path.join(golden_dir, "agent_td3_bc.npz"))
+    sc = scenarios.make_scenario(2000, 800)
+    scenarios.seed_all(0)
+    obc = OracleBC(1e-3, 13, 4, 256, 512, True, "Harfang_GYM", 64, sc["expert_states"], sc["expert_actions"])
+    scenarios.seed_all(0)
+    ag = BCAgent(1e-3, 13, 4, 256, 512, True, "Harfang_GYM", 64, sc["expert_states"], sc["expert_actions"])
+    want0 = np.concatenate([p.detach().double().reshape(-1).numpy() for p in obc.actor.parameters()])
+    assert np.array_equal(ag.export_flat(0).astype(np.float64), want0)           # same seeded init as the reference's single Actor
+    scenarios.seed_all(1)
+    for t in range(6):
+        ref = float(obc.train_actor())
+        got = float(ag.train_actor(forced_bc=obc.last_bc))
+        assert ref == float(fx["bc.losses"][t])                                    # oracle == unmodified reference (frozen)
+        assert abs(got - ref) <= 1e-5 * abs(ref) + 1e-7, (t, got, ref)
+        ag.actor.load_state_dict(obc.actor.state_dict()); ag.push_parameters()    # teacher forcing
+        st = obc.actor.optimizer.state
+        m = np.concatenate([st[p]["exp_avg"].reshape(-1).numpy() for p in obc.actor.parameters()])
+        v = np.concatenate([st[p]["exp_avg_sq"].reshape(-1).numpy() for p in obc.actor.parameters()])
+        ag.import_adam(_lib.NET_ACTOR, m, v, ag._actor_t)
+    # free-running from the same seed: the drop-in draws the same np.random.choice stream as the reference
+    scenarios.seed_all(0)
+    ag2 = BCAgent(1e-3, 13, 4, 256, 512, True, "Harfang_GYM", 64, sc["expert_states"], sc["expert_actions"])
+    scenarios.seed_all(1)
+    losses = [float(ag2.train_actor()) for _ in range(6)]
+    assert np.allclose(losses, fx["bc.losses"], rtol=2e-4)
+    assert rel(ag2.export_flat(0)[np.sort(np.random.default_rng(99).choice(138756, 1024, replace=False))], fx["bc.actor.probe"]) < 2e-4
+
+
 def test_error_behaviour_matches_reference():
     sc = scenarios.make_scenario(100, 80)
     ag = scenarios.build_agent(Agent, sc, 32, 0)
