@@ -59,6 +59,9 @@ SYMBOLS = {
     "hirl_learn_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hirl_last_launch_count": (_i, [_vp]),
     "hirl_act": (_i, [_vp, _i, _i, _vp, _i, _vp]),
+    "hirl_act_dev": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
+    "hirl_store_transitions_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hirl_agent_stream": (_i, [_vp, C.POINTER(_vp)]),
     "hirl_debug_stop_after": (_i, [_vp, _i]),
     "hirl_debug_profile": (_i, [_vp, _i, _vp, _sz]),
     "hirl_debug_export": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_sz)]),

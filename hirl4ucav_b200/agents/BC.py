@@ -41,7 +41,11 @@ class Agent(_HIRLAgent):
         st = self._st_steps[k]
         idx = forced_bc if forced_bc is not None else np.random.choice(len(self.expert_states), B, replace=False)   # BC.py:167
         self._st_bc[k, :] = idx
-        self.last_draws = {"bc": np.asarray(idx)}
+        if self.expert_upsample and forced_bc is None:   # BC.py:171-176
+            print(f"upsample num is {len(self.target_indices)}")
+            selected = np.random.choice(self.target_indices)
+            self._st_bc[k, np.random.randint(B)] = selected
+        self.last_draws = {"bc": self._st_bc[k, :].copy()}
         self._actor_t += 1
         a_neg, a_bs = _adam_scalars(self.actorLR, self._actor_t)
         st["n_online"], st["n_expert"], st["do_actor"], st["do_polyak"] = 0, 0, 1, 0

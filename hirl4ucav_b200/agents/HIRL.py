@@ -34,10 +34,14 @@ class Agent(object):
     _MODE = 0            # 0 HIRL, 1 TD3 (see agents/TD3.py)
     _GAIN = "relu"
     _ACT = _lib.ACT_RELU
+    # HIRL.py:184-185 hard-codes both switches to False inside the constructor; a maintainer who flips those
+    # source lines flips these class attributes instead (or passes the keyword arguments).
+    BUFFER_UPSAMPLE = False   # online ring: weighted draw with replacement (buffer.py:21-29, 39-43)
+    EXPERT_UPSAMPLE = False   # cloning batch: one row replaced by a firing expert row (HIRL.py:253-257)
 
     def __init__(self, actorLR, criticLR, stateDim, actionDim, full1Dim, full2Dim, tau, gamma, bufferSize, batchSize,
                  layerNorm, name, expert_states, expert_actions, bc_weight, expert_warm_up, device=None,
-                 max_fused_steps=64):
+                 max_fused_steps=64, buffer_upsample=None, expert_upsample=None):
         if (stateDim, actionDim, full1Dim, full2Dim) != (13, 4, 256, 512):
             raise NotImplementedError("the fused kernel is specialised for the reference driver's geometry "
                                       "13/4/256/512 (hirl/train_all.py:200-203)")
@@ -59,8 +63,8 @@ class Agent(object):
         self.update_count = 0
         self.loss_lambda = 10000
         self.target_update_freq = 3
-        self.buffer_upsample = False
-        self.expert_upsample = False
+        self.buffer_upsample = bool(self.BUFFER_UPSAMPLE if buffer_upsample is None else buffer_upsample)
+        self.expert_upsample = bool(self.EXPERT_UPSAMPLE if expert_upsample is None else expert_upsample)
         self._critic_t = 0      # Adam step counters (torch keeps them in optimizer.state)
         self._actor_t = 0
         self._max_steps = int(max_fused_steps)
@@ -202,6 +206,35 @@ class Agent(object):
         ids = {"actor": _lib.NET_ACTOR, "targetActor": _lib.NET_TARGET_ACTOR, "bc_actor": _lib.NET_BC_ACTOR}
         return self._actor_forward(states, ids[net])
 
+    def act_batch_dev(self, states, noise=None, net="actor"):
+        """Device-resident batched acting: states (n,13) f32 CUDA tensor -> actions (n,4) f32 CUDA
+        tensor on the caller's current stream, no host round trip.  ``noise``: None, a (4,) tensor shared by all rows
+        (the reference's per-call draw, HIRL.py:196) or an (n,4) tensor; actions = clamp(pi(s) + noise, -1, 1)."""
+        ids = {"actor": _lib.NET_ACTOR, "targetActor": _lib.NET_TARGET_ACTOR, "bc_actor": _lib.NET_BC_ACTOR}
+        if not states.is_cuda or states.dtype != torch.float32 or not states.is_contiguous() or states.shape[-1] != 13:
+            raise ValueError("act_batch_dev takes a contiguous (n,13) float32 CUDA tensor")
+        n = states.numel() // 13
+        out = torch.empty((n, 4), dtype=torch.float32, device=states.device)
+        nz, nrows = None, 0
+        if noise is not None:
+            noise = noise.to(device=states.device, dtype=torch.float32).contiguous()
+            nrows = noise.numel() // 4
+            nz = noise.data_ptr()
+        _lib.check(self._lib.hirl_act_dev(self._h, 0, ids[net], states.data_ptr(), n, out.data_ptr(), nz, nrows,
+                                          torch.cuda.current_stream(states.device).cuda_stream))
+        return out
+
+    def store_batch_dev(self, states, actions, next_states, rewards, flags):
+        """Device-resident store of n transitions (see UniformMemory.store_batch_dev)."""
+        self.buffer.store_batch_dev(states, actions, next_states, rewards, flags)
+
+    def _update_stream(self):
+        if getattr(self, "_ext_stream", None) is None:
+            p = C.c_void_p()
+            _lib.check(self._lib.hirl_agent_stream(self._h, C.byref(p)))
+            self._ext_stream = torch.cuda.ExternalStream(p.value, device=self.device)
+        return self._ext_stream
+
     def store(self, *args):
         self.buffer.store(*args)
 
@@ -235,6 +268,10 @@ class Agent(object):
             n_bc = len(self.expert_states)
             idx_bc = forced["bc"] if "bc" in forced else np.random.choice(n_bc, B, replace=False)
             self._st_bc[k, :] = idx_bc
+            if self.expert_upsample and "bc" not in forced:
+                # HIRL.py:253-257: one random row of the cloning batch is replaced by a firing expert row
+                selected = np.random.choice(self.target_indices)
+                self._st_bc[k, np.random.randint(B)] = selected
         else:
             idx_bc = None
         if "noise" in forced:
@@ -259,7 +296,8 @@ class Agent(object):
         st["noise"] = noise
         st["critic_neg_step"], st["critic_bc2_sqrt"], st["actor_neg_step"], st["actor_bc2_sqrt"] = c_neg, c_bs, a_neg, a_bs
         st["mode"] = self._MODE
-        self.last_draws = {"online": list(idx_on), "expert": list(idx_ex), "bc": idx_bc, "noise": noise.copy()}
+        self.last_draws = {"online": list(idx_on), "expert": list(idx_ex), "bc": None if idx_bc is None else self._st_bc[k].copy(),
+                           "noise": noise.copy()}
         return do_actor
 
     def _finish(self, k, do_actor, bc_weight_now, bc_warm_up_weight):
@@ -287,6 +325,8 @@ class Agent(object):
     def _launch(self, k_steps):
         self.buffer.flush()
         self.expert_buffer.flush()
+        if getattr(self.buffer, "_dev_event", None) is not None:   # device-side appends run on the caller's stream
+            self.buffer.wait_device_appends(self._update_stream())
         _lib.check(self._lib.hirl_learn(self._h, k_steps, self._st_steps.ctypes.data_as(C.c_void_p), _lib.ptr(self._st_on),
                                         _lib.ptr(self._st_ex), _lib.ptr(self._st_bc), _lib.ptr(self._st_out)))
         self._host_stale = True

@@ -111,7 +111,7 @@ __global__ void gather_bc_kernel(const float *__restrict__ tab, const int32_t *_
 
 // HIRL.py:192-212: actor forward for n rows, one CTA per row (latency path; no noise here)
 __global__ void __launch_bounds__(THREADS) act_kernel(const float *net, const float *__restrict__ states, int n, float *__restrict__ actions,
-                                                       float slope) {
+                                                       float slope, const float *__restrict__ noise = nullptr, int noise_stride = 0) {
     __shared__ __align__(16) float h1[H1];
     __shared__ __align__(16) float z2[H2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -146,9 +146,29 @@ __global__ void __launch_bounds__(THREADS) act_kernel(const float *net, const fl
                 z[4 * j] = t.x; z[4 * j + 1] = t.y; z[4 * j + 2] = t.z; z[4 * j + 3] = t.w;
             }
             head_forward<ActorL>(net, z, slope, lane, xh, h, rstd, out);
-            if (lane < A) actions[(size_t)b * A + lane] = tanhf(out[lane]);
+            if (lane < A) {
+                float a = tanhf(out[lane]);
+                if (noise) a = fminf(fmaxf(a + noise[(size_t)b * noise_stride + lane], -1.f), 1.f);   // HIRL.py:196-198
+                actions[(size_t)b * A + lane] = a;
+            }
         }
         __syncthreads();
+    }
+}
+
+// buffer.py:20-36 for n transitions at once: one warp packs one 128-byte replay row
+__global__ void store_transitions_kernel(float *__restrict__ ring, int capacity, int first_slot, int n, const float *__restrict__ s,
+                                         const float *__restrict__ a, const float *__restrict__ s2, const float *__restrict__ reward,
+                                         const int32_t *__restrict__ flags) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+        float v;
+        if (lane < S) v = s[(size_t)i * S + lane];
+        else if (lane < SA) v = a[(size_t)i * A + lane - S];
+        else if (lane < SA + S) v = s2[(size_t)i * S + lane - SA];
+        else if (lane == 30) v = reward[i];
+        else v = (flags[i] & 1) ? 1.f : 0.f;
+        ring[(size_t)((first_slot + i) % capacity) * ROW + lane] = v;
     }
 }
 
@@ -652,6 +672,45 @@ int hirl_act(hirl_agent_t *h, int replica, int net, const float *states13, int n
     CU(cudaMemcpyAsync(actions4, d_a, (size_t)n * A * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(d_s); cudaFree(d_a);
+    return 0;
+}
+
+int hirl_act_dev(hirl_agent_t *h, int replica, int net, const float *states13_dev, int n, float *actions4_dev,
+                 const float *noise4_dev, int noise_rows, void *stream) {
+    if (!h || !states13_dev || !actions4_dev || n < 0) return fail(HIRL_E_INVALID, "bad argument");
+    if (is_critic(net)) return fail(HIRL_E_INVALID, "hirl_act_dev needs an actor network");
+    if (noise4_dev && noise_rows != 1 && noise_rows != n) return fail(HIRL_E_INVALID, "noise_rows must be 1 or n");
+    if (n == 0) return 0;
+    float *w;
+    if (int rc = net_ptr(h, replica, net, 0, &w)) return rc;
+    CU(cudaSetDevice(h->cfg.device));
+    act_kernel<<<std::min(n, 8 * h->sm_count), THREADS, 0, (cudaStream_t)stream>>>(
+        w, states13_dev, n, actions4_dev, h->cfg.activation == HIRL_ACT_LEAKY_RELU ? 0.01f : 0.f, noise4_dev,
+        noise4_dev ? (noise_rows == 1 ? 0 : A) : 0);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int hirl_store_transitions_dev(hirl_agent_t *h, int replica, int buffer, int first_slot, int n, const float *s13_dev,
+                               const float *a4_dev, const float *s2_13_dev, const float *reward_dev,
+                               const int32_t *flags_dev, void *stream) {
+    if (!h || replica < 0 || replica >= (int)h->ctxs.size()) return fail(HIRL_E_INVALID, "bad handle/replica");
+    if (!s13_dev || !a4_dev || !s2_13_dev || !reward_dev || !flags_dev) return fail(HIRL_E_INVALID, "null argument");
+    const int cap = buffer == HIRL_BUF_ONLINE ? h->cfg.online_capacity : buffer == HIRL_BUF_EXPERT ? h->cfg.expert_capacity : -1;
+    if (cap < 0) return fail(HIRL_E_INVALID, "bad buffer selector");
+    if (n < 0 || n > cap || first_slot < 0 || first_slot >= cap) return fail(HIRL_E_INVALID, "row range outside the ring");
+    if (n == 0) return 0;
+    float *base = buffer == HIRL_BUF_ONLINE ? h->online[replica] : h->expert[replica];
+    CU(cudaSetDevice(h->cfg.device));
+    store_transitions_kernel<<<std::min((n + 7) / 8, 8 * h->sm_count), 256, 0, (cudaStream_t)stream>>>(
+        base, cap, first_slot, n, s13_dev, a4_dev, s2_13_dev, reward_dev, flags_dev);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int hirl_agent_stream(hirl_agent_t *h, void **stream_out) {
+    if (!h || !stream_out) return fail(HIRL_E_INVALID, "null argument");
+    *stream_out = (void *)h->stream;
     return 0;
 }
 

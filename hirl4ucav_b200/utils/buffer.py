@@ -43,6 +43,8 @@ class _MemoryView:
             i += r._size
         if not 0 <= i < r._size:
             raise IndexError("list index out of range")
+        if r._dev_ranges:
+            r.sync_host()
         row = r._rows[i]
         return Transition(row[0:S].copy(), row[S:S + A].copy(), row[S + A:S + A + S].copy(), float(row[30]),
                           bool(row[31] != 0), int(r._success[i]))
@@ -53,13 +55,11 @@ class _MemoryView:
 
 class UniformMemory(object):
     def __init__(self, capacity, upsample=False):
-        if upsample:
-            # disabled in the reference (HIRL.py:184: buffer_upsample = False)
-            raise NotImplementedError("prioritised up-sampling is outside the fused path")
         self.capacity = int(capacity)
         self.position = 0
         self.upsample = upsample
-        self.priorities_memory = None
+        # buffer.py:18: per-slot sampling weight, only with up-sampling (off in the reference's constructor, HIRL.py:184)
+        self.priorities_memory = np.zeros(self.capacity) if upsample else None
         self._size = 0
         self._rows_t = _pinned((self.capacity, ROW), torch.float32)
         self._rows = self._rows_t.numpy()
@@ -67,6 +67,7 @@ class UniformMemory(object):
         self._dirty_from = None   # first dirty slot (ring order) and count
         self._dirty_n = 0
         self._backend = None      # (handle, buffer id) once attached to an agent
+        self._dev_ranges = []     # [(first_slot, n, flags tensor)] appended on the device, not mirrored on the host yet
         self.memory = _MemoryView(self)
 
     # ---- device attachment -------------------------------------------------------------
@@ -92,6 +93,70 @@ class UniformMemory(object):
         self._dirty_from, self._dirty_n = None, 0
         return n
 
+    # ---- device-resident append -------------------------------------------------
+    def store_batch_dev(self, states, actions, next_states, rewards, flags):
+        """buffer.py:20-36 for n transitions that already live on the GPU (CUDA tensors: (n,13) f32, (n,4) f32,
+        (n,13) f32, (n,) f32 and the (n,) int32 flag words hirl_env_step_dev writes: bit 0 done, byte 1
+        step_success).  One kernel on the caller's current stream packs the 128-byte rows straight into the ring:
+        no H2D/D2H.  The host mirror (``memory[i]``) is refreshed lazily by sync_host()."""
+        if self._backend is None:
+            raise _lib.HirlError("store_batch_dev needs a ring attached to an agent")
+        handle, which = self._backend
+        ts = [states, actions, next_states, rewards, flags]
+        want = [torch.float32] * 4 + [torch.int32]
+        if any((not t.is_cuda) or t.dtype != d or not t.is_contiguous() for t, d in zip(ts, want)):
+            raise ValueError("store_batch_dev takes contiguous CUDA tensors: f32 states/actions/next_states/rewards, int32 flags")
+        n = int(states.shape[0])
+        if n > self.capacity or tuple(states.shape) != (n, S) or tuple(actions.shape) != (n, A) or \
+                tuple(next_states.shape) != (n, S) or rewards.numel() != n or flags.numel() != n:
+            raise ValueError("store_batch_dev: inconsistent shapes")
+        self.flush()   # rows stored on the host before this call are older: they must land first
+        lib = _lib.load()
+        stream = torch.cuda.current_stream(states.device)
+        _lib.check(lib.hirl_store_transitions_dev(handle, 0, which, self.position, n, states.data_ptr(), actions.data_ptr(),
+                                                  next_states.data_ptr(), rewards.data_ptr(), flags.data_ptr(),
+                                                  stream.cuda_stream))
+        self._dev_ranges.append((self.position, n, flags))
+        self._dev_event = torch.cuda.Event()
+        self._dev_event.record(stream)
+        if self.upsample:   # the weighted draw needs step_success on the host (buffer.py:21-29)
+            self.sync_host(rows=False)
+        self._size = min(self.capacity, self._size + n)
+        self.position = (self.position + n) % self.capacity
+
+    def wait_device_appends(self, handle_stream):
+        """Orders the agent's update stream after the pending device-side appends."""
+        ev = getattr(self, "_dev_event", None)
+        if ev is not None:
+            handle_stream.wait_event(ev)
+            self._dev_event = None
+
+    def sync_host(self, rows=True):
+        """Brings step_success (and with rows=True the row contents) of device-appended transitions to the host."""
+        if not self._dev_ranges:
+            return
+        handle, which = self._backend
+        lib = _lib.load()
+        keep = []
+        for first, n, flags in self._dev_ranges:
+            idx = (first + np.arange(n)) % self.capacity
+            if flags is not None:
+                succ = ((flags.cpu().numpy().astype(np.int32) >> 8) & 0xFF).astype(np.uint8).view(np.int8)
+                self._success[idx] = succ
+                if self.upsample:
+                    self.priorities_memory[idx] = np.where(succ == 1, 1.0, 0.1)
+            if rows:
+                torch.cuda.synchronize()
+                idx32 = _lib.i32c(idx)
+                out = np.empty((n, ROW), np.float32)
+                on, ex = (idx32, None) if which == _lib.BUF_ONLINE else (None, idx32)
+                _lib.check(lib.hirl_gather(handle, 0, None if on is None else _lib.ptr(on), 0 if on is None else n,
+                                           None if ex is None else _lib.ptr(ex), 0 if ex is None else n, _lib.ptr(out)))
+                self._rows[idx] = out
+            else:
+                keep.append((first, n, None))
+        self._dev_ranges = keep
+
     # ---- reference surface ---------------------------------------------------------------
     def store(self, state, action, next_state, reward, done, step_success):
         row = self._rows[self.position]
@@ -101,6 +166,8 @@ class UniformMemory(object):
         row[30] = reward
         row[31] = 1.0 if done else 0.0
         self._success[self.position] = step_success
+        if self.upsample:   # buffer.py:21-29
+            self.priorities_memory[self.position] = 1.0 if step_success == 1 else 0.1
         if self._dirty_n == 0:
             self._dirty_from = self.position
         self._dirty_n += 1
@@ -115,6 +182,8 @@ class UniformMemory(object):
             p = self.position
             self._rows[p] = rows32[i]
             self._success[p] = 0 if success is None else success[i]
+            if self.upsample:
+                self.priorities_memory[p] = 1.0 if self._success[p] == 1 else 0.1
             if self._dirty_n == 0:
                 self._dirty_from = p
             self._dirty_n += 1
@@ -123,7 +192,11 @@ class UniformMemory(object):
             self.position = (p + 1) % self.capacity
 
     def sample_indices(self, batchSize):
-        """The positions ``random.sample(self.memory, batchSize)`` would pick (buffer.py:45)."""
+        """The positions ``random.sample(self.memory, batchSize)`` would pick (buffer.py:45); with up-sampling the
+        weighted numpy draw WITH replacement of buffer.py:39-43.  Same RNG stream consumption as the reference."""
+        if self.upsample:
+            pr = self.priorities_memory[:self._size]
+            return [int(i) for i in np.random.choice(self._size, batchSize, p=pr / np.sum(pr))]
         return random.sample(range(self._size), batchSize)
 
     def sample(self, batchSize):

@@ -141,6 +141,23 @@ int hirl_last_launch_count(hirl_agent_t *h);
 /* ---- acting (HIRL.py:192-212): actions = net(states), n rows, no noise (host adds it) -- */
 int hirl_act(hirl_agent_t *h, int replica, int net, const float *states13, int n, float *actions4);
 
+/* ---- device-resident collection (batched acting + on-device store) ----------
+ * A vectorised rollout keeps observations, actions and rewards on the GPU: hirl_env_step_dev
+ * produces obs/reward/flags, hirl_act_dev the next actions, hirl_store_transitions_dev appends
+ * the transitions to the replay ring -- no per-step H2D/D2H (reference: one chooseAction +
+ * one store per env step, HIRL.py:192-215, train_all.py:343-351).
+ * noise4_dev (may be NULL): noise_rows==1 -> one 4-vector for all rows, noise_rows==n -> one per
+ * row; actions = clamp(tanh(...) + noise, -1, 1) exactly as HIRL.py:196-198. */
+int hirl_act_dev(hirl_agent_t *h, int replica, int net, const float *states13_dev, int n, float *actions4_dev,
+                 const float *noise4_dev, int noise_rows, void *stream);
+/* ring append of n transitions at first_slot (wraps at capacity): row = s[13] a[4] s2[13] r done,
+ * done = flags bit 0 (the layout hirl_env_step_dev writes); buffer.py:20-36 for n rows at once. */
+int hirl_store_transitions_dev(hirl_agent_t *h, int replica, int buffer, int first_slot, int n, const float *s13_dev,
+                               const float *a4_dev, const float *s2_13_dev, const float *reward_dev,
+                               const int32_t *flags_dev, void *stream);
+/* the handle's own cudaStream_t (updates run on it): lets a caller order its streams against it */
+int hirl_agent_stream(hirl_agent_t *h, void **stream_out);
+
 /* ---- test hooks ------------------------------------------------------------------------ */
 /* stop the next hirl_learn after this many stages of its first step (0 = run everything) */
 int hirl_debug_stop_after(hirl_agent_t *h, int stage);

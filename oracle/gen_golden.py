@@ -193,6 +193,50 @@ def td3_bc_case():
     print("    ok: TD3 and BC reference == oracle bit-for-bit")
 
 
+def upsample_case(batch=32, steps=8, expert_num=8):
+    """Both up-sampling switches ON (buffer.py:21-29,39-43; HIRL.py:253-257).  The reference hard-codes them to
+    False in its constructor (HIRL.py:184-185), so the unmodified class is constructed first and then switched the
+    way a user editing those two lines would: expert_upsample attribute + a UniformMemory(capacity, True)."""
+    print(f"[agent] upsample32: B={batch} steps={steps} with buffer_upsample and expert_upsample on")
+    sc = scenarios.make_scenario(300, 1500)   # small ring: the weighted draw WITH replacement repeats rows
+    Ref = ref_harness.hirl_agent_cls()
+    RefMem = ref_harness.ref_memory_cls()
+
+    def make(cls, mem_cls):
+        scenarios.seed_all(0)
+        hp = scenarios.HP
+        ag = cls(hp["actorLR"], hp["criticLR"], 13, 4, 256, 512, hp["tau"], hp["gamma"], hp["bufferSize"], batch, True,
+                 hp["name"], sc["expert_states"], sc["expert_actions"], hp["bc_weight"], hp["expert_warm_up"])
+        ag.expert_upsample = True
+        ag.buffer = mem_cls(hp["bufferSize"], True)
+        scenarios.fill_agent(ag, sc)
+        return ag
+    from oracle.hirl_oracle import OracleMemory
+    with ref_harness.quiet():
+        ref = make(Ref, RefMem)
+    orc = make(OracleAgent, OracleMemory)
+    outs, on, ex, bc, noise = [], [], [], [], []
+    scenarios.seed_all(1)
+    for t in range(steps):
+        outs.append([float(x) for x in ref.learn(100, expert_num, 0)])
+    scenarios.seed_all(1)
+    for t in range(steps):
+        assert [float(x) for x in orc.learn(100, expert_num, 0)] == outs[t], f"step {t}"
+        d = orc.last_draws
+        on.append(d["online"]); ex.append(d["expert"]); bc.append(d["bc"]); noise.append(d["noise"])
+    fix = {"outs": np.asarray(outs, np.float64), "batch": batch, "steps": steps, "expert_num_now": expert_num,
+           "idx_online": np.asarray(on, np.int32), "idx_expert": np.asarray(ex, np.int32), "idx_bc": np.asarray(bc, np.int32),
+           "noise": np.asarray(noise, np.float32), "n_online": 300, "n_expert": 1500}
+    assert any(len(set(r)) < len(r) for r in on), "weighted draw with replacement should repeat rows in this scenario"
+    for w in NETS:
+        a, b = ref_flat(ref, w), orc.flat(w)
+        assert np.array_equal(a, b), f"final weights differ: {w}"
+        pi = probe_indices(a.size)
+        fix[f"{w}.probe_idx"], fix[f"{w}.probe"], fix[f"{w}.sum"] = pi, a[pi].astype(np.float32), a.sum()
+    np.savez_compressed(os.path.join(OUT, "agent_upsample32.npz"), **fix)
+    print(f"    ok: reference == oracle bit-for-bit with up-sampling over {steps} steps; last out = {outs[-1]}")
+
+
 def env_case(n_check=120_000, n_keep=4096):
     print(f"[env] online step on {n_check} raw states through the unmodified reference class")
     rng = np.random.default_rng(2024)
@@ -231,11 +275,20 @@ def env_case(n_check=120_000, n_keep=4096):
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # fixtures must not depend on the intra-op thread count
-    env_case()
-    agent_case("soft32", 32, 12, 100, 8)
-    agent_case("fixed32", 32, 12, 0.5, 0)
-    agent_case("soft256", 256, 12, 100, 64, n_online=4000, n_expert=2000)
-    td3_bc_case()
+    only = set(sys.argv[1:])   # e.g. `python -m oracle.gen_golden upsample` regenerates one fixture
+    run = lambda tag: not only or tag in only
+    if run("env"):
+        env_case()
+    if run("soft32"):
+        agent_case("soft32", 32, 12, 100, 8)
+    if run("fixed32"):
+        agent_case("fixed32", 32, 12, 0.5, 0)
+    if run("soft256"):
+        agent_case("soft256", 256, 12, 100, 64, n_online=4000, n_expert=2000)
+    if run("td3_bc"):
+        td3_bc_case()
+    if run("upsample"):
+        upsample_case()
     print("golden fixtures written to", OUT)
 
 

@@ -150,19 +150,21 @@ def clone_into_(target: nn.Module, source: nn.Module) -> None:
 
 
 # --------------------------------------------------------------------------------------
-# replay ring  (hirl/utils/buffer.py:11-54, uniform path only)
+# replay ring  (hirl/utils/buffer.py:11-54; uniform path and the prioritised up-sampling path)
 # --------------------------------------------------------------------------------------
 class OracleMemory:
     def __init__(self, capacity, upsample=False):
-        if upsample:
-            raise NotImplementedError("prioritised up-sampling is disabled in the reference (HIRL.py:184)")
         self.capacity = int(capacity)
         self.memory: list[Row] = []
         self.position = 0
+        self.upsample = upsample
+        self.priorities_memory = np.zeros(self.capacity) if upsample else None   # buffer.py:18
         self.last_indices: list[int] = []
 
     def store(self, *fields):
         row = Row(*fields)
+        if self.upsample:   # buffer.py:21-29: successful shots weigh 1.0, everything else 0.1
+            self.priorities_memory[self.position] = 1.0 if fields[-1] == 1 else 0.1
         if len(self.memory) < self.capacity:
             self.memory.append(row)
         else:
@@ -172,7 +174,13 @@ class OracleMemory:
     def sample(self, k, forced=None):
         # random.sample(list, k) and random.sample(range(len(list)), k) consume the
         # Mersenne stream identically and pick the same positions (buffer.py:45).
-        idx = list(forced) if forced is not None else random.sample(range(len(self.memory)), k)
+        if forced is not None:
+            idx = list(forced)
+        elif self.upsample:   # buffer.py:39-43: numpy stream, WITH replacement
+            pr = self.priorities_memory[:len(self.memory)]
+            idx = [int(i) for i in np.random.choice(len(self.memory), k, p=pr / np.sum(pr))]
+        else:
+            idx = random.sample(range(len(self.memory)), k)
         self.last_indices = idx
         picked = [self.memory[i] for i in idx]
         cols = Row(*zip(*picked))
@@ -215,6 +223,10 @@ class OracleAgent:
         self.update_count = 0
         self.loss_lambda = 10000
         self.target_update_freq = 3
+        self.buffer_upsample = False   # HIRL.py:184-185 (both off in the reference's constructor)
+        self.expert_upsample = False
+        if mode == "HIRL" and expert_actions is not None:
+            self.target_indices = np.where(np.asarray(expert_actions)[:, 3] == 1)[0]   # HIRL.py:168, 217-219
         act = F.relu if mode == "HIRL" else _leaky
 
         # construction order fixes the init RNG stream (HIRL.py:172-180)
@@ -294,7 +306,10 @@ class OracleAgent:
             bc_s_all = torch.tensor(np.array(self.expert_states), dtype=torch.float).to(self.dtype)
             bc_a_all = torch.tensor(np.array(self.expert_actions), dtype=torch.float).to(self.dtype)
             idx_bc = forced["bc"] if "bc" in forced else np.random.choice(bc_s_all.shape[0], B, replace=False)
-            idx_bc = np.asarray(idx_bc)
+            idx_bc = np.array(idx_bc)
+            if self.expert_upsample and "bc" not in forced:   # HIRL.py:253-257: one row becomes a firing expert row
+                selected = np.random.choice(self.target_indices)
+                idx_bc[np.random.randint(self.batchSize)] = selected
             Sb, Ab = bc_s_all[idx_bc], bc_a_all[idx_bc]
 
         # -- TD target (HIRL.py:264-274) ----------------------------------------------------
@@ -395,12 +410,17 @@ class OracleBC:
         self.actor = OracleActor(lr, stateDim, actionDim, full1Dim, full2Dim, layerNorm, name, _leaky)
         self.batchsize = batchSize
         self.expert_states, self.expert_actions = expert_states, expert_actions
+        self.target_indices = np.where(np.asarray(expert_actions)[:, 3] == 1)[0]   # BC.py:152, 156-158
+        self.expert_upsample = False                                               # BC.py:154
         self.bc_loss = torch.zeros(())
 
     def train_actor(self, forced_bc=None):
         s_all = torch.tensor(np.array(self.expert_states), dtype=torch.float)
         a_all = torch.tensor(np.array(self.expert_actions), dtype=torch.float)
-        idx = np.asarray(forced_bc) if forced_bc is not None else np.random.choice(s_all.shape[0], self.batchsize, replace=False)
+        idx = np.array(forced_bc) if forced_bc is not None else np.random.choice(s_all.shape[0], self.batchsize, replace=False)
+        if self.expert_upsample and forced_bc is None:   # BC.py:171-176
+            selected = np.random.choice(self.target_indices)
+            idx[np.random.randint(self.batchsize)] = selected
         self.last_bc = idx
         pred = self.actor(s_all[idx])
         self.bc_loss = F.mse_loss(pred, a_all[idx])

@@ -46,6 +46,12 @@ def hirl_agent_cls():
     return Agent
 
 
+def ref_memory_cls():
+    _ensure_path()
+    from hirl.utils.buffer import UniformMemory
+    return UniformMemory
+
+
 def td3_agent_cls():
     _ensure_path()
     sub = os.path.join(REF_ROOT, "hirl")   # TD3.py:7 uses the script-relative "utils.buffer"

@@ -135,6 +135,28 @@ def test_free_run_matches_reference_fixture(golden_dir, name):
         assert rel(got, fx[f"{w}.probe"]) <= 2e-4, w
 
 
+def test_upsampling_free_run_matches_reference_fixture(golden_dir):
+    """prioritised up-sampling of the online ring (weighted draw WITH replacement, buffer.py:39-43) and the
+    firing-row replacement of the cloning batch (HIRL.py:253-257).  Index streams bit-exact, scalars to fp32 tolerance."""
+    fx = np.load(os.path.join(golden_dir, "agent_upsample32.npz"))
+    B, steps, en = int(fx["batch"]), int(fx["steps"]), int(fx["expert_num_now"])
+    sc = scenarios.make_scenario(int(fx["n_online"]), int(fx["n_expert"]))
+    ag = scenarios.build_agent(Agent, sc, B, 0, buffer_upsample=True, expert_upsample=True)
+    assert ag.buffer.upsample and ag.buffer.priorities_memory[:len(ag.buffer)].max() == 1.0
+    scenarios.seed_all(1)
+    for t in range(steps):
+        out = ag.learn(100, en, 0)
+        ref = fx["outs"][t]
+        d = ag.last_draws
+        assert np.array_equal(d["online"], fx["idx_online"][t]) and np.array_equal(d["expert"], fx["idx_expert"][t])
+        assert np.array_equal(d["bc"], fx["idx_bc"][t]) and np.array_equal(d["noise"], fx["noise"][t])
+        for j in range(4):
+            assert abs(float(out[j]) - ref[j]) <= 2e-4 * abs(ref[j]) + 1e-5, f"step {t} out[{j}]: {float(out[j])} vs {ref[j]}"
+        assert abs(out[5] - ref[5]) <= 1.0 / B + 1e-12
+    for w, nid in NETS:
+        assert rel(ag.export_flat(nid)[fx[f"{w}.probe_idx"]], fx[f"{w}.probe"]) <= 2e-4, w
+
+
 def test_learn_many_is_bit_identical_to_single_calls_and_deterministic():
     sc = scenarios.make_scenario(2000, 600)
     runs = []

@@ -38,6 +38,37 @@ def test_agent_oracle_matches_reference_fixture(golden_dir, name):
         assert a.sum() == fx[f"{w}.sum"] and (a * a).sum() == fx[f"{w}.sumsq"]
 
 
+def _upsample_agent(cls, mem_cls, sc, B, **kw):
+    hp = scenarios.HP
+    scenarios.seed_all(0)
+    ag = cls(hp["actorLR"], hp["criticLR"], 13, 4, 256, 512, hp["tau"], hp["gamma"], hp["bufferSize"], B, True,
+             hp["name"], sc["expert_states"], sc["expert_actions"], hp["bc_weight"], hp["expert_warm_up"], **kw)
+    if mem_cls is not None:   # the oracle mirrors the reference: switched after construction (see gen_golden.upsample_case)
+        ag.expert_upsample = True
+        ag.buffer = mem_cls(hp["bufferSize"], True)
+    scenarios.fill_agent(ag, sc)
+    return ag
+
+
+def test_upsampling_oracle_matches_reference_fixture(golden_dir):
+    """buffer.py:21-29,39-43 + HIRL.py:253-257 switched on: weighted numpy draws with replacement."""
+    from oracle.hirl_oracle import OracleMemory
+    torch.set_num_threads(1)
+    fx = np.load(os.path.join(golden_dir, "agent_upsample32.npz"))
+    B, steps, en = int(fx["batch"]), int(fx["steps"]), int(fx["expert_num_now"])
+    sc = scenarios.make_scenario(int(fx["n_online"]), int(fx["n_expert"]))
+    orc = _upsample_agent(OracleAgent, OracleMemory, sc, B)
+    scenarios.seed_all(1)
+    for t in range(steps):
+        assert [float(x) for x in orc.learn(100, en, 0)] == list(fx["outs"][t]), f"step {t}"
+        d = orc.last_draws
+        assert np.array_equal(d["online"], fx["idx_online"][t]) and np.array_equal(d["expert"], fx["idx_expert"][t])
+        assert np.array_equal(d["bc"], fx["idx_bc"][t]) and np.array_equal(d["noise"], fx["noise"][t])
+    assert any(len(set(r)) < len(r) for r in fx["idx_online"]), "fixture should contain repeated rows"
+    for w in NETS:
+        assert orc.flat(w).sum() == fx[f"{w}.sum"]
+
+
 def test_td3_and_bc_oracles_match_reference_fixture(golden_dir):
     torch.set_num_threads(1)
     fx = np.load(os.path.join(golden_dir, "agent_td3_bc.npz"))
