@@ -56,12 +56,16 @@ SYMBOLS = {
     "hirl_gather": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp]),
     "hirl_gather_bc": (_i, [_vp, _vp, _i, _vp, _vp]),
     "hirl_learn": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hirl_learn_async": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hirl_learn_wait": (_i, [_vp]),
     "hirl_learn_dev": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hirl_last_launch_count": (_i, [_vp]),
     "hirl_act": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "hirl_act_dev": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "hirl_store_transitions_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hirl_agent_stream": (_i, [_vp, C.POINTER(_vp)]),
+    "hirl_host_sample_indices": (_i, [_vp, _i, _i, _vp]),
+    "hirl_host_choice_noreplace": (_i, [_vp, _i, _i, _vp]),
     "hirl_debug_stop_after": (_i, [_vp, _i]),
     "hirl_debug_profile": (_i, [_vp, _i, _vp, _sz]),
     "hirl_debug_export": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_sz)]),

@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..utils import fast_rng
 from .HIRL import Agent as _HIRLAgent, _adam_scalars
 
 
@@ -39,7 +40,11 @@ class Agent(_HIRLAgent):
         k = 0
         B = self.batchSize
         st = self._st_steps[k]
-        idx = forced_bc if forced_bc is not None else np.random.choice(len(self.expert_states), B, replace=False)   # BC.py:167
+        if forced_bc is not None:
+            idx = forced_bc
+        else:   # BC.py:167: np.random.choice(samples_num, batchsize, replace=False), pre-drawn during the last launch when possible
+            pre = self._pre_np.take([(len(self.expert_states), B)])
+            idx = pre[0] if pre is not None else fast_rng.choice_noreplace(len(self.expert_states), B)
         self._st_bc[k, :] = idx
         if self.expert_upsample and forced_bc is None:   # BC.py:171-176
             print(f"upsample num is {len(self.target_indices)}")
@@ -53,7 +58,7 @@ class Agent(_HIRLAgent):
         st["noise"] = 0.0
         st["critic_neg_step"], st["critic_bc2_sqrt"], st["actor_neg_step"], st["actor_bc2_sqrt"] = 0.0, 1.0, a_neg, a_bs
         st["mode"] = 2
-        self._launch(1)
+        self._launch(1, predraw_for=None if forced_bc is not None else 0)
         self.bc_loss = np.float32(self._st_out[k][2])
         return self.bc_loss
 

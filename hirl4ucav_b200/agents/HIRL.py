@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from .. import _lib, nets
+from ..utils import fast_rng
 from ..utils.buffer import UniformMemory
 
 SOFT_SENTINEL = 100
@@ -38,6 +39,7 @@ class Agent(object):
     # source lines flips these class attributes instead (or passes the keyword arguments).
     BUFFER_UPSAMPLE = False   # online ring: weighted draw with replacement (buffer.py:21-29, 39-43)
     EXPERT_UPSAMPLE = False   # cloning batch: one row replaced by a firing expert row (HIRL.py:253-257)
+    PREDRAW = True            # overlap the next call's host index draws with the GPU (exact: utils/fast_rng.Predraw)
 
     def __init__(self, actorLR, criticLR, stateDim, actionDim, full1Dim, full2Dim, tau, gamma, bufferSize, batchSize,
                  layerNorm, name, expert_states, expert_actions, bc_weight, expert_warm_up, device=None,
@@ -65,6 +67,8 @@ class Agent(object):
         self.target_update_freq = 3
         self.buffer_upsample = bool(self.BUFFER_UPSAMPLE if buffer_upsample is None else buffer_upsample)
         self.expert_upsample = bool(self.EXPERT_UPSAMPLE if expert_upsample is None else expert_upsample)
+        self._pre_py, self._pre_np = fast_rng.Predraw("py"), fast_rng.Predraw("np")
+        self._n_online_prev = 0
         self._critic_t = 0      # Adam step counters (torch keeps them in optimizer.state)
         self._actor_t = 0
         self._max_steps = int(max_fused_steps)
@@ -247,12 +251,17 @@ class Agent(object):
         B = self.batchSize
         st = self._st_steps[k]
         forced = forced or {}
-        if self.expert_warm_up and expert_num_now:
-            n_ex = int(expert_num_now)
+        warm = bool(self.expert_warm_up and expert_num_now)
+        n_ex = int(expert_num_now) if warm else 0
+        pre = None
+        if k == 0 and not forced and not self.buffer.upsample:
+            pre = self._pre_py.take(self._py_requests(len(self.buffer), n_ex))   # pre-drawn while the GPU ran the last call
+        if pre is not None:
+            idx_on, idx_ex = pre[0], (pre[1] if n_ex else [])
+        elif warm:
             idx_on = forced.get("online") if "online" in forced else self.buffer.sample_indices(B - n_ex)
             idx_ex = forced.get("expert") if "expert" in forced else self.expert_buffer.sample_indices(n_ex)
         else:
-            n_ex = 0
             idx_on = forced.get("online") if "online" in forced else self.buffer.sample_indices(B)
             idx_ex = []
         n_on = B - n_ex
@@ -266,7 +275,11 @@ class Agent(object):
             self._st_ex[k, :n_ex] = idx_ex
         if self._MODE == 0:
             n_bc = len(self.expert_states)
-            idx_bc = forced["bc"] if "bc" in forced else np.random.choice(n_bc, B, replace=False)
+            if "bc" in forced:
+                idx_bc = forced["bc"]
+            else:
+                pre = self._pre_np.take([(n_bc, B)]) if k == 0 and not self.buffer.upsample else None
+                idx_bc = pre[0] if pre is not None else fast_rng.choice_noreplace(n_bc, B)   # == np.random.choice(n_bc, B, replace=False)
             self._st_bc[k, :] = idx_bc
             if self.expert_upsample and "bc" not in forced:
                 # HIRL.py:253-257: one random row of the cloning batch is replaced by a firing expert row
@@ -322,18 +335,43 @@ class Agent(object):
             self._ret = (critic_loss,) + self._ret[1:]
         return self._ret
 
-    def _launch(self, k_steps):
+    def _py_requests(self, n_online_rows, n_ex):
+        """The random.sample calls one learn() makes, as (population, k) pairs (HIRL.py:224-233)."""
+        B = self.batchSize
+        return [(n_online_rows, B - n_ex), (len(self.expert_buffer), n_ex)] if n_ex else [(n_online_rows, B)]
+
+    def _predraw_next(self, expert_num_now):
+        """Runs while the GPU executes the current call: draws the NEXT call's index streams on copies of the
+        generator states (fast_rng.Predraw).  Prediction: same expert_num_now, online ring grown by as many rows as
+        between the last two calls.  A wrong guess or any foreign use of the generators just discards the copy."""
+        if not self.PREDRAW:
+            return
+        n_now = len(self.buffer)
+        n_next = min(self.buffer.capacity, n_now + max(0, n_now - self._n_online_prev))
+        self._n_online_prev = n_now
+        n_ex = int(expert_num_now) if (self.expert_warm_up and expert_num_now) else 0
+        if not self.buffer.upsample:
+            self._pre_py.prepare(self._py_requests(n_next, n_ex))
+            if self._MODE != 1:
+                self._pre_np.prepare([(len(self.expert_states), self.batchSize)])
+
+    def _launch(self, k_steps, predraw_for=None):
         self.buffer.flush()
         self.expert_buffer.flush()
         if getattr(self.buffer, "_dev_event", None) is not None:   # device-side appends run on the caller's stream
             self.buffer.wait_device_appends(self._update_stream())
-        _lib.check(self._lib.hirl_learn(self._h, k_steps, self._st_steps.ctypes.data_as(C.c_void_p), _lib.ptr(self._st_on),
-                                        _lib.ptr(self._st_ex), _lib.ptr(self._st_bc), _lib.ptr(self._st_out)))
+        _lib.check(self._lib.hirl_learn_async(self._h, k_steps, self._st_steps.ctypes.data_as(C.c_void_p), _lib.ptr(self._st_on),
+                                              _lib.ptr(self._st_ex), _lib.ptr(self._st_bc), _lib.ptr(self._st_out)))
+        try:
+            if predraw_for is not None:
+                self._predraw_next(predraw_for)
+        finally:
+            _lib.check(self._lib.hirl_learn_wait(self._h))
         self._host_stale = True
 
     def learn(self, bc_weight_now, expert_num_now, bc_warm_up_weight=0, forced=None):
         do_actor = self._draw(0, bc_weight_now, expert_num_now, bc_warm_up_weight, forced)
-        self._launch(1)
+        self._launch(1, predraw_for=None if forced else expert_num_now)
         return self._finish(0, do_actor, bc_weight_now, bc_warm_up_weight)
 
     def learn_many(self, calls, forced=None):

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "env.cuh"
 #include "update.cuh"
+#include "host_rng.h"
 
 using namespace hirl;
 
@@ -646,6 +647,27 @@ int hirl_learn(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, const int
     return 0;
 }
 
+int hirl_learn_async(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, const int32_t *idx_online, const int32_t *idx_expert,
+                     const int32_t *idx_bc, float *out_scalars) {
+    if (!h || !steps || !idx_online || !out_scalars) return fail(HIRL_E_INVALID, "null argument");
+    if (int rc = check_steps(h, k_steps, steps)) return rc;
+    const size_t B = h->cfg.batch, K = (size_t)k_steps * h->ctxs.size();
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemcpyAsync(h->d_steps, steps, K * sizeof(hirl_step_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_ion, idx_online, K * B * 4, cudaMemcpyHostToDevice, h->stream));
+    if (idx_expert) CU(cudaMemcpyAsync(h->d_iex, idx_expert, K * B * 4, cudaMemcpyHostToDevice, h->stream));
+    if (idx_bc) CU(cudaMemcpyAsync(h->d_ibc, idx_bc, K * B * 4, cudaMemcpyHostToDevice, h->stream));
+    if (int rc = launch_update(h, k_steps, h->d_steps, h->d_ion, h->d_iex, h->d_ibc, h->d_out, h->stream)) return rc;
+    CU(cudaMemcpyAsync(out_scalars, h->d_out, K * HIRL_OUT_SCALARS * 4, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+int hirl_learn_wait(hirl_agent_t *h) {
+    if (!h) return fail(HIRL_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int hirl_learn_dev(hirl_agent_t *h, int k_steps, const hirl_step_t *steps_dev, const int32_t *idx_online_dev, const int32_t *idx_expert_dev,
                    const int32_t *idx_bc_dev, float *out_scalars_dev, void *stream) {
     if (!h || !steps_dev || !idx_online_dev || !out_scalars_dev) return fail(HIRL_E_INVALID, "null argument");
@@ -711,6 +733,96 @@ int hirl_store_transitions_dev(hirl_agent_t *h, int replica, int buffer, int fir
 int hirl_agent_stream(hirl_agent_t *h, void **stream_out) {
     if (!h || !stream_out) return fail(HIRL_E_INVALID, "null argument");
     *stream_out = (void *)h->stream;
+    return 0;
+}
+
+int hirl_host_choice_noreplace(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t *out) {
+    if (!st || !out || population < 1 || size < 0 || size > population || st->pos < 0 || st->pos > 624)
+        return fail(HIRL_E_INVALID, "bad argument");
+    hirl_host::MT19937 g{st->key, st->pos};
+    static thread_local std::vector<int32_t> perm;
+    perm.resize((size_t)population);
+    int32_t *p = perm.data();
+    for (int32_t i = 0; i < population; ++i) p[i] = i;
+    // mtrand _shuffle_raw: for i = n-1 .. 1: j = random_interval(i) (masked rejection on one 32-bit output per try),
+    // swap(i, j).  Written branch-free: a rejected output swaps p[i] with itself and does not advance i -- the
+    // data-dependent rejection branch was half the run time.  Outputs are tempered a block at a time.
+    uint32_t blk[624];
+    int32_t i = population - 1;
+    uint32_t mask = i >= 1 ? 0xffffffffu >> __builtin_clz((uint32_t)i) : 0u;
+    while (i >= 1) {
+        if (g.pos >= 624) g.regenerate();
+        const int avail = 624 - g.pos;
+        const uint32_t *kp = g.key + g.pos;
+        for (int q = 0; q < avail; ++q) blk[q] = hirl_host::MT19937::temper(kp[q]);
+        int q = 0;
+        for (; q < avail && i >= 1; ++q) {
+            const uint32_t v = blk[q] & mask;
+            const bool ok = v <= (uint32_t)i;
+            const uint32_t j = ok ? v : (uint32_t)i;
+            const int32_t t = p[j];
+            p[j] = p[i];
+            p[i] = t;
+            i -= ok;
+            mask = 0xffffffffu >> __builtin_clz((uint32_t)(i | 1));
+        }
+        g.pos += q;
+    }
+    for (int32_t i = 0; i < size; ++i) out[i] = perm[i];
+    st->pos = g.pos;
+    return 0;
+}
+
+int hirl_host_sample_indices(hirl_mt19937_t *st, int32_t n, int32_t k, int32_t *out) {
+    if (!st || !out || n < 0 || k < 0 || k > n || st->pos < 0 || st->pos > 624) return fail(HIRL_E_INVALID, "bad argument");
+    if (k == 0) return 0;
+    hirl_host::MT19937 g{st->key, st->pos};
+    auto randbelow = [&g](uint32_t m) {   // Random._randbelow_with_getrandbits: getrandbits(m.bit_length()), redrawn while >= m
+        int bits = 0;
+        for (uint32_t t = m; t; t >>= 1) ++bits;
+        uint32_t r;
+        do { r = g.next() >> (32 - bits); } while (r >= m);
+        return r;
+    };
+    // Random.sample: setsize = 21 (+ 4 ** ceil(log(3k, 4)) for k > 5) decides between the pool and the set algorithm
+    long long setsize = 21;
+    if (k > 5) {
+        long long p = 1;
+        while (p < 3LL * k) p *= 4;       // 4 ** ceil(log_4(3k)) for integer 3k
+        setsize += p;
+    }
+    if (n <= setsize) {
+        static thread_local std::vector<int32_t> pool;
+        pool.resize((size_t)n);
+        for (int32_t i = 0; i < n; ++i) pool[i] = i;
+        for (int32_t i = 0; i < k; ++i) {
+            const uint32_t j = randbelow((uint32_t)(n - i));
+            out[i] = pool[j];
+            pool[j] = pool[n - i - 1];
+        }
+    } else {
+        // open-addressing set of the selected positions (capacity >= 2k, power of two)
+        static thread_local std::vector<int32_t> tab;
+        size_t cap = 16;
+        while (cap < (size_t)k * 2) cap <<= 1;
+        tab.assign(cap, -1);
+        for (int32_t i = 0; i < k; ++i) {
+            for (;;) {
+                const int32_t j = (int32_t)randbelow((uint32_t)n);
+                size_t hpos = ((uint32_t)j * 2654435761u) & (cap - 1);
+                bool dup = false;
+                while (tab[hpos] != -1) {
+                    if (tab[hpos] == j) { dup = true; break; }
+                    hpos = (hpos + 1) & (cap - 1);
+                }
+                if (dup) continue;
+                tab[hpos] = j;
+                out[i] = j;
+                break;
+            }
+        }
+    }
+    st->pos = g.pos;
     return 0;
 }
 

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from . import fast_rng
 
 Transition = namedtuple("Transition", ("state", "action", "next_state", "reward", "done", "step_success"))
 S, A, ROW = 13, 4, 32
@@ -197,7 +198,7 @@ class UniformMemory(object):
         if self.upsample:
             pr = self.priorities_memory[:self._size]
             return [int(i) for i in np.random.choice(self._size, batchSize, p=pr / np.sum(pr))]
-        return random.sample(range(self._size), batchSize)
+        return fast_rng.sample_indices(self._size, batchSize)   # == random.sample(range(self._size), batchSize)
 
     def sample(self, batchSize):
         idx = self.sample_indices(batchSize)

@@ -132,6 +132,11 @@ int hirl_gather_bc(hirl_agent_t *h, const int32_t *idx_bc, int n, float *out_sta
  * soft_count, reserved.  With replicas>1 every array has a leading [replicas] dimension. */
 int hirl_learn(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, const int32_t *idx_online,
                const int32_t *idx_expert, const int32_t *idx_bc, float *out_scalars);
+/* hirl_learn split in two: enqueue (H2D of the host streams, launch, D2H of out_scalars into the caller's
+ * pinned buffer) and wait.  The host may draw the NEXT call's indices between the two. */
+int hirl_learn_async(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, const int32_t *idx_online,
+                     const int32_t *idx_expert, const int32_t *idx_bc, float *out_scalars);
+int hirl_learn_wait(hirl_agent_t *h);
 /* same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t) */
 int hirl_learn_dev(hirl_agent_t *h, int k_steps, const hirl_step_t *steps_dev, const int32_t *idx_online_dev,
                    const int32_t *idx_expert_dev, const int32_t *idx_bc_dev, float *out_scalars_dev, void *stream);
@@ -157,6 +162,16 @@ int hirl_store_transitions_dev(hirl_agent_t *h, int replica, int buffer, int fir
                                const int32_t *flags_dev, void *stream);
 /* the handle's own cudaStream_t (updates run on it): lets a caller order its streams against it */
 int hirl_agent_stream(hirl_agent_t *h, void **stream_out);
+
+/* ---- host-side index draws (buffer.py:45; HIRL.py:249, BC.py:167) -----------------------
+ * Exact replicas of random.sample(range(n), k) (CPython Random.sample) and of
+ * np.random.choice(n, k, replace=False) (legacy RandomState: permutation(n)[:k]) on an MT19937
+ * state {key[624], pos}: same indices, same final generator state.  `st` is either numpy's own
+ * live state (bit_generator.ctypes.state_address has this layout) or a caller-owned copy used for
+ * speculative pre-draws.  Pure host code. */
+typedef struct hirl_mt19937 { uint32_t key[624]; int32_t pos; } hirl_mt19937_t;
+int hirl_host_sample_indices(hirl_mt19937_t *st, int32_t n, int32_t k, int32_t *out);
+int hirl_host_choice_noreplace(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t *out);
 
 /* ---- test hooks ------------------------------------------------------------------------ */
 /* stop the next hirl_learn after this many stages of its first step (0 = run everything) */

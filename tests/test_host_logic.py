@@ -2,6 +2,7 @@
 import random
 
 import numpy as np
+import pytest
 import torch
 
 from hirl4ucav_b200 import nets, synth
@@ -59,3 +60,77 @@ def test_expert_csv_round_trip(tmp_path):
     assert s2.shape == (40, 13) and a2.shape == (40, 4)
     assert np.allclose(s2, es, rtol=0, atol=5e-9 * np.abs(es).max() + 1e-8)   # str(np.ndarray) keeps 8 significant digits
     assert list(data_processor.up_sample(ea)) == list(np.where(ea[:, 3] == 1)[0])
+
+
+# ---- exact fast index draws + speculative pre-drawing (utils/fast_rng.py, csrc/host_rng.h) ---------------------------
+def test_fast_draws_equal_the_interpreter_level_originals_and_leave_the_same_state():
+    import random
+    from hirl4ucav_b200.utils import fast_rng as fr
+    assert fr.py_fast() and fr.np_fast(), "generator state access self-check failed on this interpreter / numpy"
+    rng = np.random.default_rng(0)
+    for seed in range(40):
+        n1, n2, nb = int(rng.integers(1, 40000)), int(rng.integers(1, 3000)), int(rng.integers(1, 25000))
+        k1, k2, kb = int(rng.integers(0, min(n1, 4096) + 1)), int(rng.integers(0, min(n2, 300) + 1)), int(rng.integers(0, min(nb, 4096) + 1))
+        random.seed(seed); np.random.seed(seed)
+        want = (random.sample(range(n1), k1), random.sample(range(n2), k2), np.random.choice(nb, kb, replace=False),
+                random.random(), random.getrandbits(17), np.random.rand(), np.random.randn(), np.random.randint(1 << 20))
+        random.seed(seed); np.random.seed(seed)
+        got = (fr.sample_indices(n1, k1), fr.sample_indices(n2, k2), fr.choice_noreplace(nb, kb),
+               random.random(), random.getrandbits(17), np.random.rand(), np.random.randn(), np.random.randint(1 << 20))
+        assert want[0] == got[0] and want[1] == got[1] and np.array_equal(want[2], got[2]), (seed, n1, k1, n2, k2, nb, kb)
+        assert want[3:] == got[3:], "generator state after the draws differs"
+    # both branches of Random.sample around the set/pool threshold (k=192: setsize 21 + 4**5 = 1045)
+    for n in (192, 193, 1044, 1045, 1046, 5000):
+        random.seed(n); a = random.sample(range(n), 192); random.seed(n); b = fr.sample_indices(n, 192)
+        assert a == b
+    with pytest.raises(ValueError):
+        fr.sample_indices(10, 11)
+    with pytest.raises(ValueError):
+        fr.choice_noreplace(10, 11)
+
+
+def test_predraw_is_exact_under_reseeding_foreign_draws_and_wrong_guesses():
+    import random
+    from hirl4ucav_b200.utils import fast_rng as fr
+
+    def reference(script):
+        out = []
+        for op in script:
+            if op[0] == "seed":
+                random.seed(op[1]); np.random.seed(op[1])
+            elif op[0] == "foreign":
+                out.append((random.randint(-100, 100), float(np.random.rand())))     # e.g. env reset (GYM.py:74)
+            else:
+                _, n, k, nb, kb = op
+                out.append((random.sample(range(n), k), np.random.choice(nb, kb, replace=False).tolist()))
+        return out
+
+    def with_predraw(script):
+        py, npd = fr.Predraw("py"), fr.Predraw("np")
+        out = []
+        last = None
+        for op in script:
+            if op[0] == "seed":
+                random.seed(op[1]); np.random.seed(op[1])
+            elif op[0] == "foreign":
+                out.append((random.randint(-100, 100), float(np.random.rand())))
+            else:
+                _, n, k, nb, kb = op
+                r = py.take([(n, k)])
+                s = r[0].tolist() if r is not None else fr.sample_indices(n, k)
+                r = npd.take([(nb, kb)])
+                c = r[0].tolist() if r is not None else fr.choice_noreplace(nb, kb).tolist()
+                out.append((s, c))
+                last = op
+                py.prepare([(n + 1, k)])          # guess: the ring grows by one row per call
+                npd.prepare([(nb, kb)])
+        return out, py, npd
+
+    script = [("seed", 1)] + [("learn", 5000 + i, 64, 2000, 32) for i in range(6)]          # guesses right: hits
+    script += [("foreign",), ("learn", 5006, 64, 2000, 32)]                                  # foreign draw: discard
+    script += [("seed", 9), ("learn", 5007, 64, 2000, 32), ("learn", 5007, 64, 2000, 32)]    # reseed, then a wrong size guess
+    script += [("learn", 5008, 48, 2000, 32), ("learn", 5009, 48, 2000, 16)]                 # argument changes
+    want = reference(script)
+    got, py, npd = with_predraw(script)
+    assert want == got
+    assert py.hits >= 5 and py.misses >= 4 and npd.hits >= 6
