@@ -39,6 +39,7 @@ class Agent(object):
     # source lines flips these class attributes instead (or passes the keyword arguments).
     BUFFER_UPSAMPLE = False   # online ring: weighted draw with replacement (buffer.py:21-29, 39-43)
     EXPERT_UPSAMPLE = False   # cloning batch: one row replaced by a firing expert row (HIRL.py:253-257)
+    FUSE_SUB = 8              # learn_many: calls per queued launch (host draws of the next ones overlap the GPU)
     PREDRAW = True            # overlap the next call's host index draws with the GPU (exact: utils/fast_rng.Predraw)
 
     def __init__(self, actorLR, criticLR, stateDim, actionDim, full1Dim, full2Dim, tau, gamma, bufferSize, batchSize,
@@ -116,6 +117,9 @@ class Agent(object):
         self._st_on, self._st_ex, self._st_bc = self._st_on_t.numpy(), self._st_ex_t.numpy(), self._st_bc_t.numpy()
         self._st_out_t = mk((K, _lib.OUT_SCALARS), torch.float32)
         self._st_out = self._st_out_t.numpy()
+        self._st_ptrs = (self._st_steps.ctypes.data_as(C.c_void_p), _lib.ptr(self._st_on), _lib.ptr(self._st_ex),
+                         _lib.ptr(self._st_bc), _lib.ptr(self._st_out))   # the staging arrays never move
+        self._st_addr = tuple(a.ctypes.data for a in (self._st_steps, self._st_on, self._st_ex, self._st_bc, self._st_out))
         self._ret = (np.float32(0), np.float32(0), np.float32(0), np.float32(0), 0.0, bc_weight)
         self._noise_mean = torch.zeros(self.actionDim)
         self._noise_std = torch.ones(self.actionDim) * self.TD3LearningNoise
@@ -303,14 +307,11 @@ class Agent(object):
             self.update_count += 1
             do_polyak = self.update_count % self.target_update_freq == 0
         self.actorTrainable = not self.actorTrainable
-        st["n_online"], st["n_expert"], st["do_actor"], st["do_polyak"] = n_on, n_ex, int(do_actor), int(do_polyak)
-        st["bc_weight_now"], st["bc_warm_up"] = bc_weight_now, bc_warm_up_weight
-        st["force_soft_weight"] = forced.get("soft_weight", -1.0)
-        st["noise"] = noise
-        st["critic_neg_step"], st["critic_bc2_sqrt"], st["actor_neg_step"], st["actor_bc2_sqrt"] = c_neg, c_bs, a_neg, a_bs
-        st["mode"] = self._MODE
-        self.last_draws = {"online": list(idx_on), "expert": list(idx_ex), "bc": None if idx_bc is None else self._st_bc[k].copy(),
-                           "noise": noise.copy()}
+        # one record assignment (field order = hirl_step_t)
+        self._st_steps[k] = (n_on, n_ex, int(do_actor), int(do_polyak), bc_weight_now, bc_warm_up_weight,
+                             forced.get("soft_weight", -1.0), noise, c_neg, c_bs, a_neg, a_bs, self._MODE)
+        self.last_draws = {"online": self._st_on[k, :n_on].copy(), "expert": self._st_ex[k, :n_ex].copy(),
+                           "bc": None if idx_bc is None else self._st_bc[k].copy(), "noise": noise.copy()}
         return do_actor
 
     def _finish(self, k, do_actor, bc_weight_now, bc_warm_up_weight):
@@ -355,13 +356,15 @@ class Agent(object):
             if self._MODE != 1:
                 self._pre_np.prepare([(len(self.expert_states), self.batchSize)])
 
-    def _launch(self, k_steps, predraw_for=None):
+    def _pre_launch(self):
         self.buffer.flush()
         self.expert_buffer.flush()
         if getattr(self.buffer, "_dev_event", None) is not None:   # device-side appends run on the caller's stream
             self.buffer.wait_device_appends(self._update_stream())
-        _lib.check(self._lib.hirl_learn_async(self._h, k_steps, self._st_steps.ctypes.data_as(C.c_void_p), _lib.ptr(self._st_on),
-                                              _lib.ptr(self._st_ex), _lib.ptr(self._st_bc), _lib.ptr(self._st_out)))
+
+    def _launch(self, k_steps, predraw_for=None):
+        self._pre_launch()
+        _lib.check(self._lib.hirl_learn_async(self._h, k_steps, *self._st_ptrs))
         try:
             if predraw_for is not None:
                 self._predraw_next(predraw_for)
@@ -386,11 +389,29 @@ class Agent(object):
         out = []
         for base in range(0, len(calls), self._max_steps):
             chunk = calls[base:base + self._max_steps]
-            flags = [self._draw(k, c[0], c[1], c[2] if len(c) > 2 else 0, forced[base + k] if forced else None)
-                     for k, c in enumerate(chunk)]
-            self._launch(len(chunk))
+            flags = []
+            self._pre_launch()
+            try:
+                # pipelined: while the GPU runs sub-chunk j the host draws sub-chunk j+1 (launches queue on one stream,
+                # so the device still executes the calls back to back, in order)
+                for lo in range(0, len(chunk), self.FUSE_SUB):
+                    hi = min(len(chunk), lo + self.FUSE_SUB)
+                    for k in range(lo, hi):
+                        c = chunk[k]
+                        flags.append(self._draw(k, c[0], c[1], c[2] if len(c) > 2 else 0, forced[base + k] if forced else None))
+                    _lib.check(self._lib.hirl_learn_async(self._h, hi - lo, *self._slot_ptrs(lo)))
+            finally:
+                _lib.check(self._lib.hirl_learn_wait(self._h))
+            self._host_stale = True
             out += [self._finish(k, flags[k], c[0], c[2] if len(c) > 2 else 0) for k, c in enumerate(chunk)]
         return out
+
+    def _slot_ptrs(self, k):
+        """Staging pointers of step slot k (steps, idx_online, idx_expert, idx_bc, out_scalars)."""
+        B = self.batchSize
+        p = self._st_addr
+        return (C.c_void_p(p[0] + k * _lib.STEP_DTYPE.itemsize), C.c_void_p(p[1] + k * B * 4), C.c_void_p(p[2] + k * B * 4),
+                C.c_void_p(p[3] + k * B * 4), C.c_void_p(p[4] + k * _lib.OUT_SCALARS * 4))
 
     # aliases named by the north star
     select_action = chooseAction

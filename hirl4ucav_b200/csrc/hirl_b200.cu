@@ -745,29 +745,41 @@ int hirl_host_choice_noreplace(hirl_mt19937_t *st, int32_t population, int32_t s
     int32_t *p = perm.data();
     for (int32_t i = 0; i < population; ++i) p[i] = i;
     // mtrand _shuffle_raw: for i = n-1 .. 1: j = random_interval(i) (masked rejection on one 32-bit output per try),
-    // swap(i, j).  Written branch-free: a rejected output swaps p[i] with itself and does not advance i -- the
-    // data-dependent rejection branch was half the run time.  Outputs are tempered a block at a time.
+    // swap(i, j).  Written branch-free: a rejected output swaps p[i] with itself and does not advance i (the
+    // data-dependent rejection branch was half the run time); i runs through segments (2^b-1 .. 2^(b-1)] in which
+    // the mask is constant, which keeps the loop-carried chain at and/compare/subtract; outputs are tempered a
+    // block at a time and the unconsumed tail of the last block is handed back to the generator.
     uint32_t blk[624];
     int32_t i = population - 1;
-    uint32_t mask = i >= 1 ? 0xffffffffu >> __builtin_clz((uint32_t)i) : 0u;
+    int q = 0, avail = 0;
     while (i >= 1) {
-        if (g.pos >= 624) g.regenerate();
-        const int avail = 624 - g.pos;
-        const uint32_t *kp = g.key + g.pos;
-        for (int q = 0; q < avail; ++q) blk[q] = hirl_host::MT19937::temper(kp[q]);
-        int q = 0;
-        for (; q < avail && i >= 1; ++q) {
-            const uint32_t v = blk[q] & mask;
-            const bool ok = v <= (uint32_t)i;
-            const uint32_t j = ok ? v : (uint32_t)i;
-            const int32_t t = p[j];
-            p[j] = p[i];
-            p[i] = t;
-            i -= ok;
-            mask = 0xffffffffu >> __builtin_clz((uint32_t)(i | 1));
+        const uint32_t mask = 0xffffffffu >> __builtin_clz((uint32_t)i);
+        const int32_t lo = (int32_t)(mask >> 1);
+        while (i > lo) {
+            if (q == avail) {
+                if (g.pos >= 624) g.regenerate();
+                avail = 624 - g.pos;
+                const uint32_t *kp = g.key + g.pos;
+                for (int t = 0; t < avail; ++t) blk[t] = hirl_host::MT19937::temper(kp[t]);
+                g.pos = 624;
+                q = 0;
+            }
+            int qq = q;
+            int32_t ii = i;
+            for (; qq < avail && ii > lo; ++qq) {
+                const uint32_t v = blk[qq] & mask;
+                const bool ok = v <= (uint32_t)ii;
+                const uint32_t j = ok ? v : (uint32_t)ii;
+                const int32_t t = p[j];
+                p[j] = p[ii];
+                p[ii] = t;
+                ii -= ok;
+            }
+            q = qq;
+            i = ii;
         }
-        g.pos += q;
     }
+    if (avail) g.pos = 624 - (avail - q);   // hand the unconsumed outputs back (no block drawn: position untouched)
     for (int32_t i = 0; i < size; ++i) out[i] = perm[i];
     st->pos = g.pos;
     return 0;

@@ -18,6 +18,7 @@ a = ap.parse_args()
 es, ea = synth.expert_table(20000)
 set_seed(0)
 ag = Agent(1e-3, 1e-3, 13, 4, 256, 512, 0.005, 0.99, 10 ** 5, a.batch, True, "Harfang_GYM", es, ea, 0.5, True, max_fused_steps=64)
+ag.FUSE_SUB = 64   # one launch for all calls (profilers look at a single persistent launch)
 synth.fill_agent(ag, 30000, expert_states=es, expert_actions=ea)
 for _ in range(a.launches):
     out = ag.learn_many([(a.bcw, a.expert, 0)] * a.steps)

@@ -30,6 +30,7 @@ def main():
     es, ea = synth.expert_table(20000)
     set_seed(0)
     ag = Agent(1e-3, 1e-3, 13, 4, 256, 512, 0.005, 0.99, 10 ** 5, a.batch, True, "Harfang_GYM", es, ea, 0.5, True, max_fused_steps=64)
+    ag.FUSE_SUB = 64   # one launch for all calls: the in-kernel stamps cover the first 12 steps of a launch
     synth.fill_agent(ag, 30000, expert_states=es, expert_actions=ea)
     lib = _lib.load()
     calls = [(a.bcw, a.expert, 0)] * 12
