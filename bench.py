@@ -45,6 +45,16 @@ def emit(line: dict) -> None:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures
+# (profiles/r1_ncu_full_*_v8_raw.csv), per unit of work so that it scales to the launch this run times:
+# update kernel, soft256: 9.08 MB read + 67.67 MB written in a 12-call launch -> 6.396 MB per call (the agent state
+# and its replay tables are L2-resident; the writes are scratch buffers draining from L2);
+# env kernel: 640.1 MB read + 557.7 MB written for 10 M states -> 119.8 B per state (algorithmic 124 B).
+NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_full_{update_kernel,env_step_kernel}_v8_raw.csv, scaled to this launch"
+NCU_UPDATE_DRAM_BYTES_PER_STEP = {"soft256": (9.083136e6 + 67.668480e6) / 12}
+NCU_ENV_DRAM_BYTES_PER_STATE = (640.081664e6 + 557.742080e6) / 10_000_000
+
+
 WORKLOADS = {
     # BASELINE.json configs[1] / SURVEY 8(d): soft every call, 64 expert rows per batch
     "soft256": dict(batch=256, bcw=100.0, expert_num=64, flop_per_row=3_783_424, desc="HIRL-soft fused update, batch 256"),
@@ -215,7 +225,7 @@ def env_roofline(device, peaks):
     ms = e0.elapsed_time(e1) / reps
     gbs = n * 124 / (ms * 1e-3) / 1e9
     return {"kernel": "env_step_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            "traffic": None, "states": n, "ms_per_pass": ms, "evals_per_s": n / (ms * 1e-3),
+            "traffic": NCU_ENV_DRAM_BYTES_PER_STATE * n, "traffic_source": NCU_TRAFFIC_SOURCE, "states": n, "ms_per_pass": ms, "evals_per_s": n / (ms * 1e-3),
             "note": "10 M synthetic pursuit states, 124 algorithmic B/state (64 in + 60 out), 1.24 GB per pass >> L2, includes torch output allocation"}
 
 
@@ -382,7 +392,9 @@ def run_ours(args):
         "gpu_launches": 1,
         "gpu_launches_note": "value: ONE persistent hirl_update_kernel launch covers the K timed steps; e2e: K launches",
         "roofline": {"kernel": "hirl_update_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32.value, "unit": "TFLOP/s",
-                     "frac": achieved / fp32.value if fp32.value else None, "traffic": None,
+                     "frac": achieved / fp32.value if fp32.value else None,
+                     "traffic": NCU_UPDATE_DRAM_BYTES_PER_STEP[args.workload] * K if args.workload in NCU_UPDATE_DRAM_BYTES_PER_STEP else None,
+                     "traffic_source": NCU_TRAFFIC_SOURCE,
                      "peak_source": "in-run register-resident FFMA loop (hirl_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                      "flop_per_step": flops_per_step,
                      "frac_of_bf16_tensor_burst": achieved / peaks.get("bf16_tflops", 1660.5), "tensor_peak_source": peak_src},
