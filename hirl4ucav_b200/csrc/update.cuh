@@ -19,7 +19,7 @@ namespace hirl {
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr int TS = 68;                       // padded row stride of a 16x64 operand tile
-constexpr int GEMM_SMEM_FLOATS = 4 * 16 * TS;  // A,B double buffered
+constexpr int GEMM_SMEM_FLOATS = 3 * 2 * 64 * 16;  // three-stage ring of A and B k-tiles (gemm_tile); gemm_tile_regs needs 4*16*TS
 constexpr int TILE_ROWS = WARPS;             // rows per row-stage chunk
 constexpr int ROWSTAGE_SMEM_FLOATS = 4 * TILE_ROWS * H2 + 64 + TILE_ROWS * 32;
 constexpr int SMEM_FLOATS = ROWSTAGE_SMEM_FLOATS > GEMM_SMEM_FLOATS ? ROWSTAGE_SMEM_FLOATS : GEMM_SMEM_FLOATS;
@@ -297,11 +297,12 @@ __device__ __forceinline__ float4 load_rmajor(const float *P, int ld, int c0, in
 }
 __device__ __forceinline__ void store_rmajor(float *T, float4 v, int tid) { st4(T + (tid >> 4) * TS + 4 * (tid & 15), v); }
 
-// One 64x64 output tile over k-tiles [kt_begin, kt_end).  Deliberately a small stand-alone
-// function with scalar arguments: inlined into the big stage functions the register allocator
-// spilled the prefetch registers, which exposed a full L2 round trip per k-tile.
+// Register-staged tile (global -> registers two k-tiles ahead -> transposing stores into [k][64] shared tiles).
+// Kept for the forward GEMMs (GEMM_NT): their units are short (8 k-tiles after split-K) and this version has the
+// smaller fixed cost per unit (tools/fp32_gemm_probe.cu: 9.5k vs 11.3k cycles for 8 k-tiles, 20.7k vs 20.3k for 16);
+// the cp.async tile below wins on the long dW / dX units (stages G3, G6, G7: -1.2, -0.6, -1.4 us).
 template <int MODE>
-__device__ __noinline__ void gemm_tile(const float *Ap, int lda, const float *Bp, int ldb, float *C,
+__device__ __noinline__ void gemm_tile_regs(const float *Ap, int lda, const float *Bp, int ldb, float *C,
                                        int ldc, const float *bias, int M, int N, int K, int m0, int n0, int kt_begin,
                                        int kt_end, float *smem) {
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -375,6 +376,128 @@ __device__ __noinline__ void gemm_tile(const float *Ap, int lda, const float *Bp
     }
 }
 
+// ---- asynchronous global -> shared copies (LDGSTS): no register staging, no transposing stores -------------------
+__device__ __forceinline__ void cp_async16(float *dst, const float *src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int n = valid ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One 64x64 output tile over k-tiles [kt_begin, kt_end).  Deliberately a small stand-alone function with scalar
+// arguments (inlined into the big stage functions the register allocator spilled the pipeline state).
+//
+// Operands are copied with cp.async.cg (L2-coherent, bypasses L1 like the ld.global.cg it replaces) through a
+// 3-stage ring and stay in the orientation they have in global memory:
+//   * "k-major" operand (reduction index contiguous: activations [row][k], weights W[n][k]):
+//     shared layout [64 rows][16 k] with the 16-byte chunk index XOR-swizzled by (row>>1)&3; a thread owns the
+//     strided rows q+16i and reads one float4 = 4 k-steps of a row -> conflict-free LDS.128, no transposition.
+//     (The first version transposed through 4 scalar, 2-way-conflicting STS per operand and k-tile: tools/
+//     fp32_gemm_probe.cu measures 1 440 -> 1 113 cycles per k-tile for the NT tile at lda = 256.)
+//   * "row-major" operand (output index contiguous: [k][out]): shared layout [16 k][64]; a thread owns the
+//     contiguous outputs 4q..4q+3 and reads one float4 per k-step.
+// GEMM_NT: A k-major, B k-major.  GEMM_NN: A k-major, B row-major.  GEMM_TN: A row-major, B row-major.
+constexpr int GEMM_STAGES = 3, GEMM_OPF = 64 * 16;   // floats per operand per stage
+template <int MODE>
+__device__ __noinline__ void gemm_tile(const float *Ap, int lda, const float *Bp, int ldb, float *C,
+                                       int ldc, const float *bias, int M, int N, int K, int m0, int n0, int kt_begin,
+                                       int kt_end, float *smem) {
+    constexpr bool AKM = MODE != GEMM_TN, BKM = MODE == GEMM_NT;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    // copy roles: k-major -> (row tid>>2, chunk tid&3); row-major -> (k tid>>4, 4 outputs at 4*(tid&15))
+    const int kr = tid >> 2, kc = tid & 3, rk = tid >> 4, rc = 4 * (tid & 15);
+    const int a_dst = AKM ? kr * 16 + 4 * (kc ^ ((kr >> 1) & 3)) : rk * 64 + rc;
+    const int b_dst = BKM ? kr * 16 + 4 * (kc ^ ((kr >> 1) & 3)) : rk * 64 + rc;
+    const bool a_in = AKM ? (m0 + kr < M) : (m0 + rc < M);
+    const bool b_in = BKM ? (n0 + kr < N) : (n0 + rc < N);
+    const float *a_src = AKM ? Ap + (size_t)(a_in ? m0 + kr : 0) * lda + 4 * kc : Ap + (a_in ? m0 + rc : 0);
+    const float *b_src = BKM ? Bp + (size_t)(b_in ? n0 + kr : 0) * ldb + 4 * kc : Bp + (b_in ? n0 + rc : 0);
+    auto issue = [&](int kt) {
+        const int st = (kt - kt_begin) % GEMM_STAGES, k0 = kt << 4;
+        float *as = smem + (2 * st) * GEMM_OPF, *bs = as + GEMM_OPF;
+        if (AKM) cp_async16(as + a_dst, a_src + k0, a_in && k0 + 4 * kc < K);
+        else { const bool v = a_in && k0 + rk < K; cp_async16(as + a_dst, a_src + (size_t)(v ? k0 + rk : 0) * lda, v); }
+        if (BKM) cp_async16(bs + b_dst, b_src + k0, b_in && k0 + 4 * kc < K);
+        else { const bool v = b_in && k0 + rk < K; cp_async16(bs + b_dst, b_src + (size_t)(v ? k0 + rk : 0) * ldb, v); }
+    };
+    // fragment offsets of this thread
+    int a_off[4], a_sw[4], b_off[4], b_sw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ra = ty + 16 * i, rb = tx + 16 * i;
+        a_off[i] = ra * 16; a_sw[i] = (ra >> 1) & 3;
+        b_off[i] = rb * 16; b_sw[i] = (rb >> 1) & 3;
+    }
+    __syncthreads();  // previous user of this shared memory is done
+    if (kt_begin < kt_end) issue(kt_begin);
+    cp_async_commit();
+    if (kt_begin + 1 < kt_end) issue(kt_begin + 1);
+    cp_async_commit();
+    for (int kt = kt_begin; kt < kt_end; ++kt) {
+        cp_async_wait<1>();   // k-tile kt has landed (this thread's copies) ...
+        __syncthreads();      // ... and everybody's; also: stage (kt+2)%3 is no longer being read
+        if (kt + 2 < kt_end) issue(kt + 2);
+        cp_async_commit();
+        const int st = (kt - kt_begin) % GEMM_STAGES;
+        const float *as = smem + (2 * st) * GEMM_OPF, *bs = as + GEMM_OPF;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {   // 4 k-steps per chunk
+            float a[4][4], b[4][4];     // [i or j][kk]
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (AKM) {
+                    const float4 t = ld4(as + a_off[i] + 4 * (c ^ a_sw[i]));
+                    a[i][0] = t.x; a[i][1] = t.y; a[i][2] = t.z; a[i][3] = t.w;
+                } else {   // i indexes the k-step here: one float4 = rows 4ty..4ty+3 at k = 4c+i
+                    const float4 t = ld4(as + (4 * c + i) * 64 + 4 * ty);
+                    a[0][i] = t.x; a[1][i] = t.y; a[2][i] = t.z; a[3][i] = t.w;
+                }
+                if (BKM) {
+                    const float4 t = ld4(bs + b_off[i] + 4 * (c ^ b_sw[i]));
+                    b[i][0] = t.x; b[i][1] = t.y; b[i][2] = t.z; b[i][3] = t.w;
+                } else {
+                    const float4 t = ld4(bs + (4 * c + i) * 64 + 4 * tx);
+                    b[0][i] = t.x; b[1][i] = t.y; b[2][i] = t.z; b[3][i] = t.w;
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i][kk], b[j][kk], acc[i][j]);
+        }
+    }
+    // epilogue: rows ty+16i (A k-major) or 4ty+i; columns tx+16j (B k-major) or 4tx+j
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + (AKM ? ty + 16 * i : 4 * ty + i);
+        if (m >= M) continue;
+        if (BKM) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + tx + 16 * j;
+                if (n < N) C[(size_t)m * ldc + n] = acc[i][j] + (bias ? bias[n] : 0.f);
+            }
+        } else {
+            const int n = n0 + 4 * tx;
+            if (n < N) {
+                float4 bv4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias) bv4 = ld4(bias + n);
+                st4(C + (size_t)m * ldc + n, make_float4(acc[i][0] + bv4.x, acc[i][1] + bv4.y, acc[i][2] + bv4.z, acc[i][3] + bv4.w));
+            }
+        }
+    }
+}
+
 constexpr int MAX_JOBS = 8;
 __device__ __forceinline__ void run_gemm_jobs(const GemmJob *jobs, int njobs, const Team &tm, float *smem) {
     int start[MAX_JOBS + 1];
@@ -410,7 +533,7 @@ __device__ __forceinline__ void run_gemm_jobs(const GemmJob *jobs, int njobs, co
         const int kb = (int)(((long long)nk * split) / J.nsplit), ke = (int)(((long long)nk * (split + 1)) / J.nsplit);
         float *Cs = J.C + (size_t)split * J.csplit;
         const float *bias = split == 0 ? J.bias : nullptr;
-        if (J.mode == GEMM_NT) gemm_tile<GEMM_NT>(J.A, J.lda, J.B, J.ldb, Cs, J.ldc, bias, J.M, J.N, J.K, tmi * 64, tni * 64, kb, ke, smem);
+        if (J.mode == GEMM_NT) gemm_tile_regs<GEMM_NT>(J.A, J.lda, J.B, J.ldb, Cs, J.ldc, bias, J.M, J.N, J.K, tmi * 64, tni * 64, kb, ke, smem);
         else if (J.mode == GEMM_NN) gemm_tile<GEMM_NN>(J.A, J.lda, J.B, J.ldb, Cs, J.ldc, bias, J.M, J.N, J.K, tmi * 64, tni * 64, kb, ke, smem);
         else gemm_tile<GEMM_TN>(J.A, J.lda, J.B, J.ldb, Cs, J.ldc, bias, J.M, J.N, J.K, tmi * 64, tni * 64, kb, ke, smem);
     }
