@@ -128,6 +128,7 @@ struct AgentCtx {
     int ns[NS_COUNT];      // split-K factor per GEMM group
     int activation;
     int use_tc;            // 1: 256<->512 contractions on tcgen05 (3xTF32), 0: FP32-FMA tiles
+    int tc_g1;             // 1: only the forward GEMMs of stage G1 on tcgen05 (mid-size batches, see hirl_agent_create)
     int dw_split;          // split-K factor of the dW2 GEMMs (reduction over the batch), >= 1
     int BT;                // batch rounded up to 32: leading dimension of the transposed buffers
     float gamma, tau, noise_clamp, loss_lambda;

@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(THREADS, 1) hirl_update_kernel(const __grid_co
     __syncthreads();
     __shared__ tc::Barriers tc_bars;
     __shared__ uint32_t tmem_slot;
-    if (ctx.use_tc) {
+    const bool any_tc = ctx.use_tc || ctx.tc_g1;
+    if (any_tc) {
         if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot);
         if (threadIdx.x == 32) tc::barriers_init(&tc_bars);
         tc::tc_fence_before();
@@ -41,12 +42,12 @@ __global__ void __launch_bounds__(THREADS, 1) hirl_update_kernel(const __grid_co
     }
     Team tm;
     tm.rank = blockIdx.x; tm.size = gridDim.x; tm.flags = L.bar_flags; tm.gen = L.gen_base;
-    tm.tmem_base = ctx.use_tc ? tmem_slot : 0u;
+    tm.tmem_base = any_tc ? tmem_slot : 0u;
     tm.tc_smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
     tm.tc_bars = &tc_bars;
     for (int step = 0; step < L.k_steps; ++step)
         if (learn_step(ctx, step, tm, smem, step == 0 ? L.stop_after : 0, L.prof)) break;
-    if (ctx.use_tc) {
+    if (any_tc) {
         __syncthreads();
         if (threadIdx.x < 32) tc::tmem_dealloc(tm.tmem_base);
     }
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(THREADS, 1) hirl_ensemble_kernel(const __grid_
     if (team >= L.n_teams) return;
     __shared__ tc::Barriers tc_bars;
     __shared__ uint32_t tmem_slot;
-    const bool use_tc = L.agents[0].use_tc != 0;
+    const bool use_tc = L.agents[0].use_tc != 0 || L.agents[0].tc_g1 != 0;   // any tensor-core tile in this launch
     if (use_tc) {
         if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot);
         if (threadIdx.x == 32) tc::barriers_init(&tc_bars);
@@ -410,7 +411,15 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     // tile per SM per stage and the FP32 64x64 tiles (twice as many, split-K) finish sooner; once a CTA has several
     // tiles per stage (large batch, or a team of 8 CTAs per replica in ensembles) the tensor-core tiles win 2.5-3.5x.
     proto.use_tc = (cfg->batch >= 512 || (R > 1 && cfg->batch >= 128)) ? 1 : 0;
-    if (const char *e = getenv("HIRL_TC")) proto.use_tc = atoi(e) != 0;
+    // Mid-size batches (single agent, 128 <= batch < 512): only stage G1 goes to the tensor cores.  Its 3-6 forward
+    // passes are 16 tiles of 128x64x256 each -> one wave of 48-96 concurrent tcgen05 tiles (10.4 us measured) against
+    // 24 us for the FP32 tiles; the other GEMM stages have too few tiles (G2, G5: 32) or would need the transposed
+    // operand copies (dX, dW), where the FP32 tiles stay faster at this size.
+    proto.tc_g1 = (!proto.use_tc && R == 1 && cfg->batch >= 128) ? 1 : 0;
+    if (const char *e = getenv("HIRL_TC")) {   // 0: FP32 tiles only, 1: every 256<->512 contraction on tcgen05, 2: stage G1 only
+        proto.use_tc = atoi(e) == 1;
+        proto.tc_g1 = atoi(e) == 2;
+    }
     proto.BT = (cfg->batch + 31) & ~31;
     // dW2 reduces over the batch: split it so that a long reduction still spreads over the SMs (tensor-core tiles:
     // one split per 512 batch rows = one accumulation chunk; FP32 tiles: one per 1024 rows)
@@ -418,6 +427,9 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     if (const char *e = getenv("HIRL_DW_SPLIT")) proto.dw_split = std::max(1, std::min(8, atoi(e)));
     if (proto.use_tc)
         for (int i = 0; i < NS_COUNT; ++i) proto.ns[i] = 1;
+    if (proto.tc_g1) proto.ns[NS_G1] = proto.ns[NS_G1_ACTOR] = 1;   // tensor-core tiles take the full K (splitting the
+                                                                    // 48 tiles of a critic-only call in two K halves
+                                                                    // made G1 3 us shorter and the step no faster)
     proto.zsplit = 1;
     for (int i = 0; i < NS_COUNT; ++i) proto.zsplit = std::max(proto.zsplit, proto.ns[i]);
 

@@ -638,14 +638,14 @@ __device__ __noinline__ void stage_r0(const AgentCtx &c, const hirl_step_t &st, 
 
 // second-layer forward GEMM job: Z2[pass] = H1[pass] . W2^T + b2
 template <class L>
-__device__ __forceinline__ GemmJob fwd_job(const AgentCtx &c, int pass, const float *tw, int nsplit) {
+__device__ __forceinline__ GemmJob fwd_job(const AgentCtx &c, int pass, const float *tw, int nsplit, bool tc) {
     GemmJob J;
     J.A = H1p(c, pass); J.lda = H1;
     J.B = tw + L::W2; J.ldb = H1;
     J.bias = tw + L::B2;
     J.C = Z2p(c, pass); J.ldc = H2;
     J.M = c.B; J.N = H2; J.K = H1;
-    J.mode = c.use_tc ? GEMM_TC : GEMM_NT; J.nsplit = c.use_tc ? 1 : nsplit; J.csplit = z2_split_stride(c);
+    J.mode = tc ? GEMM_TC : GEMM_NT; J.nsplit = nsplit; J.csplit = z2_split_stride(c);   // (full tensor-core mode: the host sets every split to 1)
     return J;
 }
 // dH1[slot] = dZ2[pass] . W2
@@ -686,19 +686,20 @@ __device__ __noinline__ void stage_g1(const AgentCtx &c, const hirl_step_t &st, 
     GemmJob jobs[MAX_JOBS];
     int n = 0;
     const int ns = g1_split(c, st);
+    const bool tc = c.use_tc || c.tc_g1;
     if (st.mode == 2) {
-        jobs[n++] = fwd_job<ActorL>(c, P_AB, c.actor, ns);
+        jobs[n++] = fwd_job<ActorL>(c, P_AB, c.actor, ns, tc);
         run_gemm_jobs(jobs, n, tm, smem);
         return;
     }
-    jobs[n++] = fwd_job<ActorL>(c, P_TA, c.tactor, ns);
-    jobs[n++] = fwd_job<CriticL>(c, P_C1, c.critic, ns);
-    jobs[n++] = fwd_job<CriticL>(c, P_C2, c.critic + CriticL::SIZE, ns);
+    jobs[n++] = fwd_job<ActorL>(c, P_TA, c.tactor, ns, tc);
+    jobs[n++] = fwd_job<CriticL>(c, P_C1, c.critic, ns, tc);
+    jobs[n++] = fwd_job<CriticL>(c, P_C2, c.critic + CriticL::SIZE, ns, tc);
     if (st.do_actor) {
-        jobs[n++] = fwd_job<ActorL>(c, P_A, c.actor, ns);
+        jobs[n++] = fwd_job<ActorL>(c, P_A, c.actor, ns, tc);
         if (st.mode == 0) {
-            jobs[n++] = fwd_job<ActorL>(c, P_AB, c.actor, ns);
-            jobs[n++] = fwd_job<ActorL>(c, P_BC, c.bc, ns);
+            jobs[n++] = fwd_job<ActorL>(c, P_AB, c.actor, ns, tc);
+            jobs[n++] = fwd_job<ActorL>(c, P_BC, c.bc, ns, tc);
         }
     }
     run_gemm_jobs(jobs, n, tm, smem);
@@ -748,8 +749,8 @@ __device__ __noinline__ void stage_r1(const AgentCtx &c, const hirl_step_t &st, 
 
 __device__ __noinline__ void stage_g2(const AgentCtx &c, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
-    jobs[0] = fwd_job<CriticL>(c, P_TC1, c.tcritic, c.ns[NS_G2]);
-    jobs[1] = fwd_job<CriticL>(c, P_TC2, c.tcritic + CriticL::SIZE, c.ns[NS_G2]);
+    jobs[0] = fwd_job<CriticL>(c, P_TC1, c.tcritic, c.ns[NS_G2], c.use_tc != 0);
+    jobs[1] = fwd_job<CriticL>(c, P_TC2, c.tcritic + CriticL::SIZE, c.ns[NS_G2], c.use_tc != 0);
     run_gemm_jobs(jobs, 2, tm, smem);
 }
 
@@ -1069,8 +1070,8 @@ __device__ __noinline__ void stage_r4(const AgentCtx &c, const hirl_step_t &st, 
 __device__ __noinline__ void stage_g5(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
     GemmJob jobs[MAX_JOBS];
     int n = 0;
-    jobs[n++] = fwd_job<CriticL>(c, P_QP, c.critic, c.ns[NS_G5]);
-    if (st.mode == 0 && st.bc_weight_now == 100.f) jobs[n++] = fwd_job<CriticL>(c, P_QS, c.critic, c.ns[NS_G5]);
+    jobs[n++] = fwd_job<CriticL>(c, P_QP, c.critic, c.ns[NS_G5], c.use_tc != 0);
+    if (st.mode == 0 && st.bc_weight_now == 100.f) jobs[n++] = fwd_job<CriticL>(c, P_QS, c.critic, c.ns[NS_G5], c.use_tc != 0);
     run_gemm_jobs(jobs, n, tm, smem);
 }
 // R5: Q heads, soft count (HIRL.py:303), rl_loss partial (HIRL.py:297), backward of Q1(s,pi) with

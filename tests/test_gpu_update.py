@@ -7,7 +7,8 @@ Tolerances (stated, fp32 path):
     on ordinary steps.  A step where torch-fp32 itself is more than 3e-6 away from the fp64 twin
     (a ReLU mask / soft-count tie flipped by summation order) is a "tie step": there
     only the envelope  err(cuda, fp64) <= 4 * err(torch32, fp64) + 2e-6  is required.
-  * both GEMM back-ends are exercised: FP32-FMA tiles (HIRL_TC=0) and tcgen05 3xTF32 tiles (HIRL_TC=1)
+  * all GEMM back-end choices are exercised: FP32-FMA tiles (HIRL_TC=0), tcgen05 3xTF32 tiles (HIRL_TC=1) and the
+    mid-size default where only stage G1 runs on the tensor cores (HIRL_TC=2)
   * free-running drift: within 5x the natural fp32-vs-fp64 drift of the reference, same run.
 """
 import os
@@ -68,7 +69,7 @@ def check_step(tag, got, ref32, ref64, tol=1e-5):
     return e_c32
 
 
-@pytest.mark.parametrize("tc_mode", ["0", "1"])
+@pytest.mark.parametrize("tc_mode", ["0", "1", "2"])
 @pytest.mark.parametrize("B,bcw,en,steps", [(32, 100, 8, 12), (32, 0.5, 0, 12), (256, 100, 64, 12), (100, 100, 33, 6), (5, 0.3, 2, 6)])
 def test_teacher_forced_parity(B, bcw, en, steps, tc_mode, monkeypatch):
     monkeypatch.setenv("HIRL_TC", tc_mode)
