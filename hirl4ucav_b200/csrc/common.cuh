@@ -137,7 +137,6 @@ struct AgentCtx {
 struct LaunchCtx {
     AgentCtx agent;        // single-agent launch: the context travels as a kernel parameter
     unsigned *bar_flags;   // [MAX_CTAS][32] barrier flags: generations keep counting up across launches (never reset)
-    unsigned gen_base;     // generation this launch starts from
     int k_steps;
     int stop_after;        // debug: leave after this stage of step 0 (0 = never)
     long long *prof;       // debug: [PROF_STEPS][ST_END][MAX_CTAS][2] SM-clock stamps (work done, barrier released)
@@ -149,7 +148,6 @@ constexpr int PROF_STEPS = 12;
 struct EnsembleLaunch {
     const AgentCtx *agents;  // [replicas] in global memory
     unsigned *bar_flags;     // [n_teams][team_size][32]
-    unsigned gen_base;       // generation this launch starts from (flags are never reset)
     int replicas, n_teams, team_size, k_steps;
 };
 

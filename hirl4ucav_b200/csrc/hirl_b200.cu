@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(THREADS, 1) hirl_update_kernel(const __grid_co
         tc::tc_fence_after();
     }
     Team tm;
-    tm.rank = blockIdx.x; tm.size = gridDim.x; tm.flags = L.bar_flags; tm.gen = L.gen_base;
+    tm.rank = blockIdx.x; tm.size = gridDim.x; tm.flags = L.bar_flags;
+    tm.gen = ld_relaxed_u32(tm.flags + tm.rank * FLAG_STRIDE);   // flags keep counting across launches: resume from the generation this CTA reached
     tm.tmem_base = any_tc ? tmem_slot : 0u;
     tm.tc_smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
     tm.tc_bars = &tc_bars;
@@ -74,7 +75,8 @@ __global__ void __launch_bounds__(THREADS, 1) hirl_ensemble_kernel(const __grid_
     }
     Team tm;
     tm.rank = blockIdx.x % L.team_size; tm.size = L.team_size;
-    tm.flags = L.bar_flags + (size_t)team * L.team_size * FLAG_STRIDE; tm.gen = L.gen_base;
+    tm.flags = L.bar_flags + (size_t)team * L.team_size * FLAG_STRIDE;
+    tm.gen = ld_relaxed_u32(tm.flags + tm.rank * FLAG_STRIDE);
     tm.tmem_base = use_tc ? tmem_slot : 0u;
     tm.tc_smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
     tm.tc_bars = &tc_bars;
@@ -221,7 +223,11 @@ struct hirl_agent {
     long long *d_prof = nullptr;
     bool prof_on = false;
     bool zero_copy = false;      // HIRL_ZERO_COPY=1: kernel reads the pinned host streams over PCIe (measured slower, see below)
-    unsigned gen_base = 0;       // barrier generation the next launch starts from (flags are never reset)
+    // one-call CUDA graph of the per-call sequence (4 H2D copies, cooperative launch, D2H): a single cudaGraphLaunch
+    // instead of six API calls; rebuilt when the caller's staging pointers change, disabled if capture is refused
+    bool use_graph = true;
+    cudaGraphExec_t graph_exec = nullptr;
+    const void *graph_key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_elems[32];
 };
 
@@ -380,6 +386,7 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     if (const char *g = getenv("HIRL_GRID")) h->grid = std::max(2, std::min(h->grid, atoi(g)) & ~1);
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     if (const char *z = getenv("HIRL_ZERO_COPY")) h->zero_copy = atoi(z) != 0;
+    if (const char *z = getenv("HIRL_GRAPH")) h->use_graph = atoi(z) != 0;
 
     const int R = cfg->replicas;
     const size_t B = cfg->batch;
@@ -498,6 +505,7 @@ int hirl_agent_destroy(hirl_agent_t *h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     for (void *p : h->allocs) cudaFree(p);
     delete h;
     return 0;
@@ -605,16 +613,14 @@ static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_de
                          float *out_dev, cudaStream_t stream) {
     const int R = (int)h->ctxs.size();
     const size_t B = h->cfg.batch;
-    // Barrier flags are never reset: every launch starts from a generation above anything the previous one can
-    // have reached (one memset call per launch saved; the comparison in team_sync is wrap-safe).
-    const unsigned gen_base = h->gen_base;
-    h->gen_base += (unsigned)ST_END * (unsigned)k_steps * (unsigned)((R + std::max(1, h->n_teams) - 1) / std::max(1, h->n_teams)) + 1u;
+    // Barrier flags are never reset: every CTA of a team leaves a launch with the same generation in its flag and
+    // resumes from it (no memset per launch, no per-launch kernel argument; the comparison in team_sync is wrap-safe).
     if (R == 1) {
         LaunchCtx L;
         L.agent = h->ctxs[0];
         AgentCtx &c = L.agent;
         c.steps = steps_dev; c.idx_online = ion; c.idx_expert = iex; c.idx_bc = ibc; c.out_scalars = out_dev;
-        L.bar_flags = h->d_bar; L.gen_base = gen_base; L.k_steps = k_steps; L.stop_after = h->stop_after;
+        L.bar_flags = h->d_bar; L.k_steps = k_steps; L.stop_after = h->stop_after;
         L.prof = h->prof_on ? h->d_prof : nullptr;
         void *args[] = {&L};
         CU(cudaLaunchCooperativeKernel((void *)hirl_update_kernel, dim3(h->grid), dim3(THREADS), args, SMEM_BYTES, stream));
@@ -629,7 +635,7 @@ static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_de
         CU(cudaMemcpyAsync(h->d_ctxs, tmp.data(), sizeof(AgentCtx) * R, cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));  // tmp is pageable host memory
         EnsembleLaunch L;
-        L.agents = h->d_ctxs; L.bar_flags = h->d_bar; L.gen_base = gen_base; L.replicas = R; L.n_teams = h->n_teams; L.team_size = h->team_size; L.k_steps = k_steps;
+        L.agents = h->d_ctxs; L.bar_flags = h->d_bar; L.replicas = R; L.n_teams = h->n_teams; L.team_size = h->team_size; L.k_steps = k_steps;
         void *args[] = {&L};
         CU(cudaLaunchCooperativeKernel((void *)hirl_ensemble_kernel, dim3(h->n_teams * h->team_size), dim3(THREADS), args, SMEM_BYTES, stream));
     }
@@ -691,13 +697,42 @@ int hirl_learn_async(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, con
         return launch_update(h, k_steps, (const hirl_step_t *)d_st, (const int32_t *)d_on, d_ex ? (const int32_t *)d_ex : h->d_iex,
                              d_bc ? (const int32_t *)d_bc : h->d_ibc, (float *)d_out, h->stream);
     }
-    CU(cudaMemcpyAsync(h->d_steps, steps, K * sizeof(hirl_step_t), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->d_ion, idx_online, K * B * 4, cudaMemcpyHostToDevice, h->stream));
-    if (idx_expert) CU(cudaMemcpyAsync(h->d_iex, idx_expert, K * B * 4, cudaMemcpyHostToDevice, h->stream));
-    if (idx_bc) CU(cudaMemcpyAsync(h->d_ibc, idx_bc, K * B * 4, cudaMemcpyHostToDevice, h->stream));
-    if (int rc = launch_update(h, k_steps, h->d_steps, h->d_ion, h->d_iex, h->d_ibc, h->d_out, h->stream)) return rc;
-    CU(cudaMemcpyAsync(out_scalars, h->d_out, K * HIRL_OUT_SCALARS * 4, cudaMemcpyDeviceToHost, h->stream));
-    return 0;
+    auto enqueue = [&]() -> int {
+        CU(cudaMemcpyAsync(h->d_steps, steps, K * sizeof(hirl_step_t), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->d_ion, idx_online, K * B * 4, cudaMemcpyHostToDevice, h->stream));
+        if (idx_expert) CU(cudaMemcpyAsync(h->d_iex, idx_expert, K * B * 4, cudaMemcpyHostToDevice, h->stream));
+        if (idx_bc) CU(cudaMemcpyAsync(h->d_ibc, idx_bc, K * B * 4, cudaMemcpyHostToDevice, h->stream));
+        if (int rc = launch_update(h, k_steps, h->d_steps, h->d_ion, h->d_iex, h->d_ibc, h->d_out, h->stream)) return rc;
+        CU(cudaMemcpyAsync(out_scalars, h->d_out, K * HIRL_OUT_SCALARS * 4, cudaMemcpyDeviceToHost, h->stream));
+        return 0;
+    };
+    const bool graphable = h->use_graph && k_steps == 1 && h->ctxs.size() == 1 && !h->prof_on && h->stop_after == 0;
+    if (graphable) {
+        const void *key[5] = {steps, idx_online, idx_expert, idx_bc, out_scalars};
+        if (!h->graph_exec && !h->graph_key[0]) {   // built once, for the first set of staging pointers seen
+            cudaGraph_t g = nullptr;
+            bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                ok = enqueue() == 0;
+                ok = (cudaStreamEndCapture(h->stream, &g) == cudaSuccess) && ok && g;
+            }
+            if (ok) ok = cudaGraphInstantiate(&h->graph_exec, g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            if (!ok) {   // e.g. a driver that refuses cooperative launches inside a capture: plain calls from now on
+                cudaGetLastError();
+                h->graph_exec = nullptr;
+                h->use_graph = false;
+            }
+            std::memcpy(h->graph_key, key, sizeof(key));
+        }
+        if (h->graph_exec && std::memcmp(key, h->graph_key, sizeof(key)) != 0) return enqueue();   // other buffers: plain calls
+        if (h->graph_exec) {
+            CU(cudaGraphLaunch(h->graph_exec, h->stream));
+            h->last_launches = 1;
+            return 0;
+        }
+    }
+    return enqueue();
 }
 int hirl_learn_wait(hirl_agent_t *h) {
     if (!h) return fail(HIRL_E_INVALID, "null handle");
