@@ -70,8 +70,21 @@ def _copy(st: MTState) -> MTState:
     return out
 
 
+_memcmp = C.CDLL(None).memcmp
+_memcmp.restype, _memcmp.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]
+
+
 def _same(a: MTState, b: MTState) -> bool:
-    return a.pos == b.pos and bytes(a.key) == bytes(b.key)
+    return a.pos == b.pos and _memcmp(C.byref(a), C.byref(b), 624 * 4) == 0
+
+
+def _live_equals(kind: str, snap: MTState) -> bool:
+    """Compares the live generator state with a snapshot in place (no copy of the 2.5 KB state)."""
+    if kind == "py":
+        live = _py_live()
+        return live.index == snap.pos and _memcmp(C.byref(live, _PyRandomObject.state.offset), C.byref(snap), 624 * 4) == 0
+    live = _np_live()
+    return live.pos == snap.pos and _memcmp(C.byref(live), C.byref(snap), 624 * 4) == 0
 
 
 # ---- the C draws ---------------------------------------------------------------------------------------------------
@@ -188,7 +201,7 @@ class Predraw:
     def take(self, requests):
         """Returns the pre-drawn index arrays if they are exactly what drawing now would give, else None."""
         snap, self._snap = self._snap, None
-        if snap is None or list(requests) != self._req or not _same(self._live(), snap):
+        if snap is None or list(requests) != self._req or not _live_equals(self.kind, snap):
             self.misses += 1
             return None
         if self.kind == "py":
