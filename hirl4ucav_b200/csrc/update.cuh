@@ -508,7 +508,17 @@ __device__ __forceinline__ void run_gemm_jobs(const GemmJob *jobs, int njobs, co
         else total += ((jobs[j].M + 63) >> 6) * ((jobs[j].N + 63) >> 6) * jobs[j].nsplit;
     }
     start[njobs] = total;
-    for (int t = tm.rank; t < total; t += tm.size) {
+    // Fewer work units than CTAs: spread them over the whole rank range (unit u -> rank ceil(u*size/total)) instead
+    // of packing them on ranks 0..total-1, so that the busy SMs are not concentrated on a few GPCs / L2 ports.
+    const bool sparse = total < tm.size;
+    int t_first = tm.rank, t_step = tm.size;
+    if (sparse) {
+        const int u = (int)(((long long)tm.rank * total) / tm.size);
+        const bool mine = u < total && (int)(((long long)u * tm.size + total - 1) / total) == tm.rank;
+        t_first = mine ? u : total;
+        t_step = total;   // at most one unit per CTA
+    }
+    for (int t = t_first; t < total; t += t_step) {
         int j = 0;
         while (t >= start[j + 1]) ++j;
         const GemmJob &J = jobs[j];
