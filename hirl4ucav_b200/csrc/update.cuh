@@ -1038,11 +1038,22 @@ __device__ __forceinline__ void polyak_arena(const Team &tm, int ntowers, const 
         target[e] = polyak_elem(target[e], w[e], tau, one_minus_tau);
 }
 
+// In the Adam stages the last rank also reduces the loss scalars (a few dependent L2 round trips): with an equal
+// share of the arena it was the stage's straggler by 1.3-1.7 us (tools/stage_profile.py --ranks).  On large teams
+// the arena is therefore dealt to ranks 0..size-2 only and the last rank just does the reductions.
+__device__ __forceinline__ Team arena_team(const Team &tm) {
+    Team t = tm;
+    if (tm.size >= 32) t.size = tm.size - 1;
+    return t;
+}
+
 __device__ __noinline__ void stage_g4(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
     const int P = gsize < nchunks ? gsize : nchunks;
-    adam_arena<CriticL>(tm, 2, c.critic, c.g_critic, c.sc.GW2P, c.dw_split > 1 ? c.dw_split : 0, c.m_critic, c.v_critic, c.sc.PART_C, 2, P, st.critic_neg_step,
-                        st.critic_bc2_sqrt, nullptr, false, 0.f, 0.f, c.use_tc ? c.w2t_critic : nullptr);
+    const Team at = arena_team(tm);
+    if (tm.rank < at.size)
+        adam_arena<CriticL>(at, 2, c.critic, c.g_critic, c.sc.GW2P, c.dw_split > 1 ? c.dw_split : 0, c.m_critic, c.v_critic, c.sc.PART_C, 2, P,
+                            st.critic_neg_step, st.critic_bc2_sqrt, nullptr, false, 0.f, 0.f, c.use_tc ? c.w2t_critic : nullptr);
     if (tm.rank == tm.size - 1 && threadIdx.x < 32) {
         // critic_loss = mse(Q1,y) + mse(Q2,y): even ranks hold tower 0, odd ranks tower 1
         const float s0 = lp_sum(c, tm, 0, 0), s1 = lp_sum(c, tm, 0, 1);
@@ -1297,9 +1308,11 @@ __device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &s
     const size_t part_off = st.mode == 2 ? (size_t)P * ActorL::SMALL : 0, w2_off = st.mode == 2 ? (size_t)H2 * H1 * c.dw_split : 0;
     const float *part_a = c.sc.PART_A + part_off;
     const float *w2parts = c.sc.GW2P + w2_off;
-    adam_arena<ActorL>(tm, 1, c.actor, c.g_actor, w2parts, (st.mode == 0 ? 2 : 1) * c.dw_split, c.m_actor, c.v_actor, part_a, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
+    const Team at = arena_team(tm);
+    if (tm.rank < at.size)
+        adam_arena<ActorL>(at, 1, c.actor, c.g_actor, w2parts, (st.mode == 0 ? 2 : 1) * c.dw_split, c.m_actor, c.v_actor, part_a, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
                        c.tactor, st.do_polyak != 0, tau, omt, c.use_tc ? c.w2t_actor : nullptr);
-    if (st.do_polyak) polyak_arena<CriticL>(tm, 2, c.critic, c.tcritic, tau, omt);
+    if (st.do_polyak && tm.rank < at.size) polyak_arena<CriticL>(at, 2, c.critic, c.tcritic, tau, omt);
     if (tm.rank == tm.size - 1 && threadIdx.x < 32) {
         const BcWeight bw = bc_weight_of(c, st, tm);
         const float rl_loss = st.mode == 2 ? 0.f : -(lp_sum(c, tm, 2) / (float)c.B);      // HIRL.py:297

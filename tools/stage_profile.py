@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--expert", type=int, default=64)
     ap.add_argument("--mhz", type=float, default=1965.0)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--ranks", action="store_true", help="also print the slowest CTA ranks of every stage")
     a = ap.parse_args()
     es, ea = synth.expert_table(20000)
     set_seed(0)
@@ -57,6 +58,10 @@ def main():
             busy = int((work > 0.25 * work.max()).sum())
             lines.append(f"  {NAMES[s]:3s} total {us(stage_total):7.2f} us | work max {us(work.max()):7.2f} mean {us(work.mean()):7.2f} "
                          f"busy CTAs {busy:3d} | barrier min {us(bar.min()):5.2f} us")
+            if a.ranks:   # the slowest CTAs of the stage: which ranks are the stragglers
+                top = np.argsort(-work)[:4]
+                lines.append("        slowest ranks: " + ", ".join(f"{int(r)}: {us(work[r]):.2f}" for r in top)
+                             + f" | median {us(np.median(work)):.2f}")
             tot += us(stage_total)
             prev = p[s, :, 1].copy()
         lines.append(f"  sum of stages: {tot:.1f} us")
