@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib, nets
+from .utils import fast_rng
 from .agents.HIRL import SOFT_SENTINEL, _adam_scalars
 
 
@@ -148,10 +149,11 @@ class AgentEnsemble(object):
                 n_on = B - n_ex
                 if n_on <= 0:
                     raise TypeError("expert_num_now == batchSize leaves no online rows")
-                on[r, k, :n_on] = st.py.sample(range(self.online_len[r]), n_on)
+                # exact C replicas of the reference's draws on this replica's private generators (utils/fast_rng.py)
+                on[r, k, :n_on] = fast_rng.sample_indices_on(st.py, self.online_len[r], n_on)
                 if n_ex:
-                    ex[r, k, :n_ex] = st.py.sample(range(self.expert_len[r]), n_ex)
-                bc[r, k, :] = st.np.choice(self.n_expert, B, replace=False)
+                    ex[r, k, :n_ex] = fast_rng.sample_indices_on(st.py, self.expert_len[r], n_ex)
+                bc[r, k, :] = fast_rng.choice_noreplace_on(st.np, self.n_expert, B)
                 s = steps[r, k]
                 s["n_online"], s["n_expert"] = n_on, n_ex
                 s["do_actor"], s["do_polyak"] = int(sched[k][0]), int(sched[k][1])

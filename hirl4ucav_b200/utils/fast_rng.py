@@ -172,6 +172,25 @@ def choice_noreplace(n: int, k: int) -> np.ndarray:
     return _c_choice(_np_live(), n, k).astype(np.int64)
 
 
+def sample_indices_on(inst, n: int, k: int):
+    """== inst.sample(range(n), k) for a private ``random.Random`` instance (ensemble replicas)."""
+    if not 0 <= k <= n:
+        raise ValueError("Sample larger than population or is negative")
+    if n >= 1 << 31 or not py_fast():
+        return inst.sample(range(n), k)
+    st = _py_read(inst)
+    out = _c_sample(st, n, k)
+    _py_write(st, inst)
+    return out
+
+
+def choice_noreplace_on(rs, n: int, k: int):
+    """== rs.choice(n, k, replace=False) for a private ``np.random.RandomState`` (ensemble replicas)."""
+    if k > n or n < 1 or n >= 1 << 31 or not np_fast():
+        return rs.choice(n, k, replace=False)
+    return _c_choice(_np_live(rs), n, k)
+
+
 class Predraw:
     """Speculative draws for the next call (see the module docstring).  ``kind`` is "py" (random.sample stream:
     a list of (n, k) draws made back to back) or "np" (np.random.choice stream: one (n, k) draw)."""
