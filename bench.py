@@ -46,13 +46,13 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures
-# (profiles/r1_ncu_full_update_kernel_v9_raw.csv, r1_ncu_full_env_step_kernel_v8_raw.csv), per unit of work so that
+# (profiles/r1_ncu_full_update_kernel_v10_raw.csv, r1_ncu_full_env_step_kernel_v8_raw.csv), per unit of work so that
 # it scales to the launch this run times:
-# update kernel, soft256: 9.25 MB read + 54.70 MB written in a 12-call launch -> 5.33 MB per call (the agent state
+# update kernel, soft256: 10.72 MB read + 53.91 MB written in a 12-call launch -> 5.39 MB per call (the agent state
 # and its replay tables are L2-resident; the writes are scratch buffers draining from L2);
 # env kernel: 640.1 MB read + 557.7 MB written for 10 M states -> 119.8 B per state (algorithmic 124 B).
-NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_full_update_kernel_v9_raw.csv / r1_ncu_full_env_step_kernel_v8_raw.csv, scaled to this launch"
-NCU_UPDATE_DRAM_BYTES_PER_STEP = {"soft256": (9.249280e6 + 54.702080e6) / 12}
+NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_full_update_kernel_v10_raw.csv / r1_ncu_full_env_step_kernel_v8_raw.csv, scaled to this launch"
+NCU_UPDATE_DRAM_BYTES_PER_STEP = {"soft256": (10.721024e6 + 53.908480e6) / 12}
 NCU_ENV_DRAM_BYTES_PER_STATE = (640.081664e6 + 557.742080e6) / 10_000_000
 
 
