@@ -225,6 +225,8 @@ struct hirl_agent {
     bool zero_copy = false;      // HIRL_ZERO_COPY=1: kernel reads the pinned host streams over PCIe (measured slower, see below)
     // one-call CUDA graph of the per-call sequence (4 H2D copies, cooperative launch, D2H): a single cudaGraphLaunch
     // instead of six API calls; rebuilt when the caller's staging pointers change, disabled if capture is refused
+    float *d_act_s = nullptr, *d_act_a = nullptr;   // hirl_act staging (states in, actions out), act_cap rows
+    int act_cap = 0;
     bool use_graph = true;
     cudaGraphExec_t graph_exec = nullptr;
     const void *graph_key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -506,6 +508,8 @@ int hirl_agent_destroy(hirl_agent_t *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->d_act_s) cudaFree(h->d_act_s);
+    if (h->d_act_a) cudaFree(h->d_act_a);
     for (void *p : h->allocs) cudaFree(p);
     delete h;
     return 0;
@@ -758,15 +762,21 @@ int hirl_act(hirl_agent_t *h, int replica, int net, const float *states13, int n
     float *w;
     if (int rc = net_ptr(h, replica, net, 0, &w)) return rc;
     CU(cudaSetDevice(h->cfg.device));
-    float *d_s = nullptr, *d_a = nullptr;
-    CU(cudaMalloc(&d_s, (size_t)n * S * 4));
-    CU(cudaMalloc(&d_a, (size_t)n * A * 4));
-    CU(cudaMemcpyAsync(d_s, states13, (size_t)n * S * 4, cudaMemcpyHostToDevice, h->stream));
-    act_kernel<<<std::min(n, 8 * h->sm_count), THREADS, 0, h->stream>>>(w, d_s, n, d_a, h->cfg.activation == HIRL_ACT_LEAKY_RELU ? 0.01f : 0.f);
+    if (n > h->act_cap) {   // staging grows on demand and is kept: chooseAction runs once per env step (no malloc/free per call)
+        const int cap = std::max(n, std::max(64, 2 * h->act_cap));
+        float *ns = nullptr, *na = nullptr;
+        CU(cudaMalloc(&ns, (size_t)cap * S * 4));
+        CU(cudaMalloc(&na, (size_t)cap * A * 4));
+        CU(cudaStreamSynchronize(h->stream));
+        if (h->d_act_s) cudaFree(h->d_act_s);
+        if (h->d_act_a) cudaFree(h->d_act_a);
+        h->d_act_s = ns; h->d_act_a = na; h->act_cap = cap;
+    }
+    CU(cudaMemcpyAsync(h->d_act_s, states13, (size_t)n * S * 4, cudaMemcpyHostToDevice, h->stream));
+    act_kernel<<<std::min(n, 8 * h->sm_count), THREADS, 0, h->stream>>>(w, h->d_act_s, n, h->d_act_a, h->cfg.activation == HIRL_ACT_LEAKY_RELU ? 0.01f : 0.f);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(actions4, d_a, (size_t)n * A * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(actions4, h->d_act_a, (size_t)n * A * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    cudaFree(d_s); cudaFree(d_a);
     return 0;
 }
 
