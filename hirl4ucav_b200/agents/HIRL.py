@@ -31,6 +31,18 @@ def _adam_scalars(lr: float, step: int):
     return -(lr / bc1), bc2 ** 0.5
 
 
+_POOL = None
+
+
+def _draw_pool():
+    """One helper thread for learn_many's np.random draws (created on first use)."""
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=1, thread_name_prefix="hirl-draw")
+    return _POOL
+
+
 class Agent(object):
     _MODE = 0            # 0 HIRL, 1 TD3 (see agents/TD3.py)
     _GAIN = "relu"
@@ -250,8 +262,10 @@ class Agent(object):
         return np.where(BCActions[:, 3] == 1)[0]
 
     # ---- the update ------------------------------------------------------------------------
-    def _draw(self, k, bc_weight_now, expert_num_now, bc_warm_up_weight, forced):
-        """Fills staging slot k with one call's index/noise draws, in the reference's RNG order."""
+    def _draw(self, k, bc_weight_now, expert_num_now, bc_warm_up_weight, forced, defer_bc=False):
+        """Fills staging slot k with one call's index/noise draws, in the reference's RNG order.  ``defer_bc``: the
+        cloning batch of this call is being drawn (from np.random, in call order) by learn_many's helper thread and is
+        written into the slot by the caller."""
         B = self.batchSize
         st = self._st_steps[k]
         forced = forced or {}
@@ -281,6 +295,8 @@ class Agent(object):
             n_bc = len(self.expert_states)
             if "bc" in forced:
                 idx_bc = forced["bc"]
+            elif defer_bc:
+                idx_bc = self._st_bc[k]          # placeholder: the row is overwritten after the helper thread is joined
             else:
                 pre = self._pre_np.take([(n_bc, B)]) if k == 0 and not self.buffer.upsample else None
                 idx_bc = pre[0] if pre is not None else fast_rng.choice_noreplace(n_bc, B)   # == np.random.choice(n_bc, B, replace=False)
@@ -396,9 +412,25 @@ class Agent(object):
                 # so the device still executes the calls back to back, in order)
                 for lo in range(0, len(chunk), self.FUSE_SUB):
                     hi = min(len(chunk), lo + self.FUSE_SUB)
-                    for k in range(lo, hi):
-                        c = chunk[k]
-                        flags.append(self._draw(k, c[0], c[1], c[2] if len(c) > 2 else 0, forced[base + k] if forced else None))
+                    # The np.random stream (one cloning batch per call: the longest draw) is advanced by a helper
+                    # thread while this thread draws the random / torch streams of the same calls.  The three
+                    # generators are independent and each is still consumed in call order; the C draws release the
+                    # GIL.  Not with forced streams or the up-sampling switches (those use np.random elsewhere too).
+                    fut = None
+                    if self._MODE == 0 and not forced and not self.buffer.upsample and not self.expert_upsample:
+                        n_bc, B = len(self.expert_states), self.batchSize
+                        fut = _draw_pool().submit(lambda m=hi - lo: [fast_rng.choice_noreplace(n_bc, B) for _ in range(m)])
+                    try:
+                        for k in range(lo, hi):
+                            c = chunk[k]
+                            flags.append(self._draw(k, c[0], c[1], c[2] if len(c) > 2 else 0, forced[base + k] if forced else None,
+                                                    defer_bc=fut is not None))
+                    finally:
+                        ready = fut.result() if fut is not None else None    # always joined: np.random must be quiescent afterwards
+                    if ready is not None:
+                        for k in range(lo, hi):
+                            self._st_bc[k, :] = ready[k - lo]
+                        self.last_draws["bc"] = self._st_bc[hi - 1].copy()
                     _lib.check(self._lib.hirl_learn_async(self._h, hi - lo, *self._slot_ptrs(lo)))
             finally:
                 _lib.check(self._lib.hirl_learn_wait(self._h))
