@@ -6,10 +6,12 @@
 //             losses and the backward passes through heads / LayerNorms (warp-shuffle
 //             reductions, column sums through shared-memory tiles, per-CTA partial
 //             gradients that are reduced in a fixed order -> run-to-run deterministic)
-//   G stages  the 256<->512 contractions as 64x64 FP32-FMA tiles from shared memory
-//             (forward NT, dX NN, dW TN), optional split-K for small batches
+//   G stages  the 256<->512 contractions: 64x64 FP32-FMA tiles from shared memory (forward NT
+//             register-staged, dX NN / dW TN through a cp.async ring), optional split-K for
+//             small batches; or 128x64 tcgen05 3xTF32 tiles (tc_gemm.cuh) -- every contraction
+//             at batch >= 512 and in ensembles, stage G1 alone at 128 <= batch < 512
 // The same stage functions serve the single-agent grid-wide kernel (team = whole grid) and
-// the ensemble kernel (team = one thread-block cluster per replica).
+// the ensemble kernel (team = 8 CTAs per replica).
 #pragma once
 #include "common.cuh"
 #include "tc_gemm.cuh"
