@@ -73,6 +73,17 @@ def check_step(tag, got, ref32, ref64, tol=1e-5):
 @pytest.mark.parametrize("B,bcw,en,steps", [(32, 100, 8, 12), (32, 0.5, 0, 12), (256, 100, 64, 12), (100, 100, 33, 6), (5, 0.3, 2, 6)])
 def test_teacher_forced_parity(B, bcw, en, steps, tc_mode, monkeypatch):
     monkeypatch.setenv("HIRL_TC", tc_mode)
+    _teacher_forced(B, bcw, en, steps)
+
+
+@pytest.mark.parametrize("bcw,en", [(0.5, 1024), (0.5 - 3 / 5000, 0)])
+def test_teacher_forced_parity_at_baseline_batch_4096(bcw, en):
+    """BASELINE.json configs fixed4096 / linear4096 at their full batch size, default back-end for that size
+    (every contraction on tcgen05, dW2 split over the batch); same bars as the small cases."""
+    _teacher_forced(4096, bcw, en, 4)
+
+
+def _teacher_forced(B, bcw, en, steps):
     sc = scenarios.make_scenario(max(1000, 4 * B), max(600, 3 * B))
     orc = scenarios.build_agent(OracleAgent, sc, B, 0)
     o64 = scenarios.build_agent(OracleAgent, sc, B, 0, dtype=torch.float64)
