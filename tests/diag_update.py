@@ -1,7 +1,7 @@
 """GPU diagnostic: runs the fused update stage by stage and prints, for every intermediate,
-its error against the oracle (fp32) and the fp64 twin.  Not a test; a bug locator.
+its error against the oracle (fp32) and the fp64 twin.  Not a test (pytest does not collect it); a bug locator.  It lives under tests/ because it executes the oracle.
 
-    python tools/diag_update.py [--batch 32] [--steps 4]
+    python tests/diag_update.py [--batch 32] [--steps 4]
 """
 from __future__ import annotations
 
