@@ -81,7 +81,7 @@ enum Stage {
 
 // debug buffer ids (hirl_debug_export)
 enum DebugBuf { DB_X = 0, DB_XB, DB_H1, DB_XH1, DB_RS1, DB_Z2, DB_DH1, DB_APRIME, DB_PI, DB_PIB, DB_ABC,
-                DB_Y, DB_Q, DB_TQ, DB_RLQ, DB_SOFTQ, DB_GPI, DB_LP, DB_GW2P };
+                DB_Y, DB_Q, DB_TQ, DB_RLQ, DB_SOFTQ, DB_GPI, DB_LP, DB_GW2P, DB_XH2, DB_RS2, DB_DZ2S, DB_DZ1, DB_DY1 };
 
 struct Scratch {
     float *X;        // [B][32] gathered replay rows
@@ -103,6 +103,14 @@ struct Scratch {
     float *GW2P;     // [2 * dw_split][H2][H1] split-K / per-branch partial dW2 buffers, summed in fixed order by Adam
     float *H1T;      // [4][H1][BT]  transposed h1 of C1, C2, A, AB   (tensor-core dW operands, K-major)
     float *DZ2T;     // [4][H2][BT]  transposed dz2 of the same passes
+    // cluster-resident kernel (csrc/cluster_update.cuh)
+    float *H1P;      // [N_PASS][Bpad][H1 + 4]  first-layer activations in padded rows: a row block is one contiguous bulk copy
+    float *DZ2S;     // [4][8 slices][Bpad][64] dz2 of C1, C2, A, AB, slice-major: a dW2 tile's operand is one contiguous block
+    float *DZ1, *DY1;  // [4][B][H1]  gradients at the first layer's pre-activation / LayerNorm1 output
+    float *XH2;      // [2][Bpad][H2] xhat2 of passes A, AB (kept from phase A for the actor backward)
+    float *RS2;      // [2][Bpad]
+    float *PART2C;   // [clusters][PC_WORDS] per-cluster column sums of the critic's small second-layer parameters
+    float *PART2A;   // [clusters][PA_WORDS] same for the actor, per branch
 };
 
 // Everything one replica's update needs.  Passed to the kernel by value (per-replica array in
@@ -113,6 +121,8 @@ struct AgentCtx {
     float *g_actor, *g_critic;
     float *m_actor, *v_actor, *m_critic, *v_critic;
     float *w2t_actor, *w2t_critic;   // transposed copies of W2 ([H1][H2], per tower): K-major operand of the tensor-core dX GEMMs
+    // padded images of every W2 ([H2][H1 + 4] per tower): the cluster kernel streams a CTA's 64-row slice with one bulk copy
+    float *w2p_actor, *w2p_tactor, *w2p_bc, *w2p_critic, *w2p_tcritic;
     // replay tables
     const float *online;   // [online_capacity][32]
     const float *expert;   // [expert_capacity][32]
@@ -131,6 +141,8 @@ struct AgentCtx {
     int tc_g1;             // 1: only the forward GEMMs of stage G1 on tcgen05 (mid-size batches, see hirl_agent_create)
     int dw_split;          // split-K factor of the dW2 GEMMs (reduction over the batch), >= 1
     int BT;                // batch rounded up to 32: leading dimension of the transposed buffers
+    int use_cluster;       // 1: cluster-resident kernel (csrc/cluster_update.cuh); rows per block = 2 * cluster_ri
+    int cluster_ri, Bpad;  // Bpad = row blocks * rows per block
     float gamma, tau, noise_clamp, loss_lambda;
 };
 

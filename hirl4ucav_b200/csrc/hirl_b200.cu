@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "env.cuh"
 #include "update.cuh"
+#include "cluster_update.cuh"
 #include "host_rng.h"
 
 using namespace hirl;
@@ -231,6 +232,8 @@ struct hirl_agent {
     cudaGraphExec_t graph_exec = nullptr;
     const void *graph_key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_elems[32];
+    bool coop_ok = true;         // cooperative attribute accepted for cluster launches
+    int ncl = 0;                 // cluster kernel: co-resident clusters of 8 CTAs used per launch
 };
 
 template <class T>
@@ -309,6 +312,18 @@ static int flat_import(hirl_agent *h, int replica, int net, int kind, const floa
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy(d, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+    if (kind == 0 && h->ctxs[replica].use_cluster) {   // padded W2 image ([H2][H1 + 4] per tower) streamed by the cluster kernel
+        const int towers = cr ? 2 : 1;
+        const int w2off = cr ? CriticL::W2 : ActorL::W2, tsize = cr ? CriticL::SIZE : ActorL::SIZE;
+        std::vector<float> img((size_t)towers * H2 * cl::WLD, 0.f);
+        for (int tw = 0; tw < towers; ++tw)
+            for (int n = 0; n < H2; ++n)
+                std::memcpy(&img[((size_t)tw * H2 + n) * cl::WLD], &tmp[(size_t)tw * tsize + w2off + (size_t)n * H1], H1 * 4);
+        AgentCtx &c = h->ctxs[replica];
+        float *dst = net == HIRL_NET_ACTOR ? c.w2p_actor : net == HIRL_NET_TARGET_ACTOR ? c.w2p_tactor : net == HIRL_NET_BC_ACTOR ? c.w2p_bc
+                     : net == HIRL_NET_CRITIC ? c.w2p_critic : c.w2p_tcritic;
+        CU(cudaMemcpy(dst, img.data(), img.size() * 4, cudaMemcpyHostToDevice));
+    }
     if (kind == 0 && (net == HIRL_NET_ACTOR || net == HIRL_NET_CRITIC)) {   // W2^T copies of the trainable nets
         const int towers = cr ? 2 : 1;
         const int w2off = cr ? CriticL::W2 : ActorL::W2, tsize = cr ? CriticL::SIZE : ActorL::SIZE;
@@ -429,6 +444,39 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
         proto.use_tc = atoi(e) == 1;
         proto.tc_g1 = atoi(e) == 2;
     }
+    // Cluster-resident kernel (csrc/cluster_update.cuh): single agent, FP32 path.  HIRL_CLUSTER=0/1 overrides; an explicit
+    // HIRL_TC selects one of the stage-structured back-ends of round 1 instead.
+    proto.use_cluster = (R == 1 && !proto.use_tc && !getenv("HIRL_TC")) ? 1 : 0;
+    if (const char *e = getenv("HIRL_CLUSTER")) proto.use_cluster = (atoi(e) != 0 && R == 1) ? 1 : 0;
+    proto.cluster_ri = 8;
+    proto.Bpad = ((cfg->batch + 15) / 16) * 16;
+    if (proto.use_cluster) {
+        proto.use_tc = proto.tc_g1 = 0;
+        // how many clusters of 8 CTAs are co-resident on this part (B200: 15 or 16, depends on the floor plan of the die)
+        int ncl[2] = {0, 0};
+        for (int v = 0; v < 2; ++v) {
+            const void *fn = v ? (const void *)cl::hirl_cluster_kernel<9> : (const void *)cl::hirl_cluster_kernel<8>;
+            const size_t sm = v ? cl::Ker<9>::SMEM_BYTES : cl::Ker<8>::SMEM_BYTES;
+            CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(cl::MAX_CL * cl::CL); lc.blockDim = dim3(cl::CTHREADS); lc.dynamicSmemBytes = sm;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl::CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            CU(cudaOccupancyMaxActiveClusters(&ncl[v], fn, &lc));
+            ncl[v] = std::min(ncl[v], cl::MAX_CL);
+        }
+        if (const char *e = getenv("HIRL_NCL")) { ncl[0] = std::min(ncl[0], std::max(1, atoi(e))); ncl[1] = std::min(ncl[1], std::max(1, atoi(e))); }
+        if (ncl[0] < 1) return fail(HIRL_E_CUDA, "no co-resident cluster of 8 CTAs for the cluster kernel");
+        // rows per block: 16, or 18 when that saves a whole round of row blocks (e.g. batch 256 on 15 clusters)
+        const int r16 = ((cfg->batch + 15) / 16 + ncl[0] - 1) / ncl[0] * 16;
+        const int r18 = ncl[1] >= 1 ? ((cfg->batch + 17) / 18 + ncl[1] - 1) / ncl[1] * 18 : 1 << 30;
+        proto.cluster_ri = r18 < r16 ? 9 : 8;
+        if (const char *e = getenv("HIRL_RI")) proto.cluster_ri = atoi(e) == 9 ? 9 : 8;
+        h->ncl = proto.cluster_ri == 9 ? ncl[1] : ncl[0];
+        const int rb = 2 * proto.cluster_ri;
+        proto.Bpad = ((cfg->batch + rb - 1) / rb) * rb;
+    }
     proto.BT = (cfg->batch + 31) & ~31;
     // dW2 reduces over the batch: split it so that a long reduction still spreads over the SMs (tensor-core tiles:
     // one split per 512 batch rows = one accumulation chunk; FP32 tiles: one per 1024 rows)
@@ -463,6 +511,14 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
         if ((rc = dev_alloc(h, &s.GW2P, (size_t)2 * proto.dw_split * H2 * H1))) return rc;
         if ((rc = dev_alloc(h, &s.H1T, (size_t)4 * H1 * proto.BT))) return rc;
         if ((rc = dev_alloc(h, &s.DZ2T, (size_t)4 * H2 * proto.BT))) return rc;
+        if ((rc = dev_alloc(h, &s.H1P, (size_t)N_PASS * proto.Bpad * cl::WLD))) return rc;
+        if ((rc = dev_alloc(h, &s.DZ2S, (size_t)4 * cl::CL * proto.Bpad * cl::NS))) return rc;
+        if ((rc = dev_alloc(h, &s.DZ1, (size_t)4 * B * H1))) return rc;
+        if ((rc = dev_alloc(h, &s.DY1, (size_t)4 * B * H1))) return rc;
+        if ((rc = dev_alloc(h, &s.XH2, (size_t)2 * proto.Bpad * H2))) return rc;
+        if ((rc = dev_alloc(h, &s.RS2, (size_t)2 * proto.Bpad))) return rc;
+        if ((rc = dev_alloc(h, &s.PART2C, (size_t)cl::MAX_CL * cl::PC_WORDS))) return rc;
+        if ((rc = dev_alloc(h, &s.PART2A, (size_t)cl::MAX_CL * cl::PA_WORDS))) return rc;
         if ((rc = dev_alloc(h, &s.PART_C, (size_t)slots * 2 * CriticL::SMALL))) return rc;
         if ((rc = dev_alloc(h, &s.PART_A, (size_t)slots * ActorL::SMALL))) return rc;
     }
@@ -487,6 +543,13 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
         if ((rc = dev_alloc(h, &c.carry, 8))) return rc;
         if ((rc = dev_alloc(h, &c.w2t_actor, (size_t)H1 * H2))) return rc;
         if ((rc = dev_alloc(h, &c.w2t_critic, (size_t)2 * H1 * H2))) return rc;
+        if (proto.use_cluster) {
+            if ((rc = dev_alloc(h, &c.w2p_actor, (size_t)H2 * cl::WLD))) return rc;
+            if ((rc = dev_alloc(h, &c.w2p_tactor, (size_t)H2 * cl::WLD))) return rc;
+            if ((rc = dev_alloc(h, &c.w2p_bc, (size_t)H2 * cl::WLD))) return rc;
+            if ((rc = dev_alloc(h, &c.w2p_critic, (size_t)2 * H2 * cl::WLD))) return rc;
+            if ((rc = dev_alloc(h, &c.w2p_tcritic, (size_t)2 * H2 * cl::WLD))) return rc;
+        }
     }
     const size_t K = (size_t)cfg->max_steps * R;
     if ((rc = dev_alloc(h, &h->d_steps, K))) return rc;
@@ -619,7 +682,34 @@ static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_de
     const size_t B = h->cfg.batch;
     // Barrier flags are never reset: every CTA of a team leaves a launch with the same generation in its flag and
     // resumes from it (no memset per launch, no per-launch kernel argument; the comparison in team_sync is wrap-safe).
-    if (R == 1) {
+    if (R == 1 && h->ctxs[0].use_cluster) {
+        cl::ClusterLaunch L;
+        L.agent = h->ctxs[0];
+        AgentCtx &c = L.agent;
+        c.steps = steps_dev; c.idx_online = ion; c.idx_expert = iex; c.idx_bc = ibc; c.out_scalars = out_dev;
+        L.bar_flags = h->d_bar; L.k_steps = k_steps; L.ncl = h->ncl;
+        L.prof = h->prof_on ? h->d_prof : nullptr;
+        const bool r9 = c.cluster_ri == 9;
+        const void *fn = r9 ? (const void *)cl::hirl_cluster_kernel<9> : (const void *)cl::hirl_cluster_kernel<8>;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(h->ncl * cl::CL); lc.blockDim = dim3(cl::CTHREADS);
+        lc.dynamicSmemBytes = r9 ? cl::Ker<9>::SMEM_BYTES : cl::Ker<8>::SMEM_BYTES;
+        lc.stream = stream;
+        // cooperative: the clusters of one launch spin on each other's flags, so they must be co-resident (two agents on
+        // two streams must not interleave half-resident grids); the cluster shape is part of the kernel (__cluster_dims__)
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+        lc.attrs = at; lc.numAttrs = h->coop_ok ? 1 : 0;
+        void *args[] = {&L};
+        cudaError_t e = cudaLaunchKernelExC(&lc, fn, args);
+        if (e != cudaSuccess && h->coop_ok) {   // a driver that refuses cooperative + cluster launches: plain launch (grid <= co-resident clusters)
+            cudaGetLastError();
+            h->coop_ok = false;
+            lc.numAttrs = 0;
+            e = cudaLaunchKernelExC(&lc, fn, args);
+        }
+        if (e != cudaSuccess) return fail(HIRL_E_CUDA, std::string("cluster kernel launch: ") + cudaGetErrorString(e));
+    } else if (R == 1) {
         LaunchCtx L;
         L.agent = h->ctxs[0];
         AgentCtx &c = L.agent;
@@ -967,6 +1057,11 @@ int hirl_debug_export(hirl_agent_t *h, int buffer_id, int pass, float *dst, size
         case DB_SOFTQ: src = s.SOFTQ; cnt = B; break;
         case DB_LP: src = s.LP; cnt = (size_t)MAX_CTAS * LP_WORDS; break;
         case DB_GW2P: src = s.GW2P; cnt = (size_t)2 * h->ctxs[0].dw_split * H2 * H1; break;
+        case DB_XH2: src = s.XH2 + (size_t)pass * h->ctxs[0].Bpad * H2; cnt = (size_t)h->ctxs[0].Bpad * H2; break;
+        case DB_RS2: src = s.RS2 + (size_t)pass * h->ctxs[0].Bpad; cnt = (size_t)h->ctxs[0].Bpad; break;
+        case DB_DZ2S: src = s.DZ2S + (size_t)pass * cl::CL * h->ctxs[0].Bpad * cl::NS; cnt = (size_t)cl::CL * h->ctxs[0].Bpad * cl::NS; break;
+        case DB_DZ1: src = s.DZ1 + (size_t)pass * B * H1; cnt = B * H1; break;
+        case DB_DY1: src = s.DY1 + (size_t)pass * B * H1; cnt = B * H1; break;
         default: return fail(HIRL_E_INVALID, "bad debug buffer id");
     }
     if (n_out) *n_out = cnt;
@@ -974,6 +1069,10 @@ int hirl_debug_export(hirl_agent_t *h, int buffer_id, int pass, float *dst, size
     if (n < cnt) return fail(HIRL_E_INVALID, "destination too small");
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaStreamSynchronize(h->stream));
+    if (h->ctxs[0].use_cluster && buffer_id == DB_H1) {   // padded activation rows of the cluster kernel
+        CU(cudaMemcpy2D(dst, H1 * 4, s.H1P + (size_t)pass * h->ctxs[0].Bpad * cl::WLD, cl::WLD * 4, H1 * 4, B, cudaMemcpyDeviceToHost));
+        return 0;
+    }
     CU(cudaMemcpy(dst, src, cnt * 4, cudaMemcpyDeviceToHost));
     return 0;
 }

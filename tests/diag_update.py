@@ -82,7 +82,7 @@ def main():
         q = buf("Q").reshape(2, B)
         show("Q1", q[0], t2n(rec32["q1"]), t2n(rec64["q1"]))
         show("Q2", q[1], t2n(rec32["q2"]), t2n(rec64["q2"]))
-        if not actor_step:
+        if not actor_step and os.environ.get("HIRL_CLUSTER") == "0":
             # Z2 of critic passes now hold dz2 (grad of z2); target passes still hold z2
             show("Z2[TC1]=z2", nsz(buf("Z2", P["TC1"]), 512), t2n(rec32["tc.q1.z2"]), t2n(rec64["tc.q1.z2"]))
             show("Z2[C1]=dz2 (split0)", buf("Z2", P["C1"]).reshape(-1, B, 512)[0], t2n(rec32["critic.q1.z2"].grad), t2n(rec64["critic.q1.z2"].grad))
@@ -99,10 +99,19 @@ def main():
         if actor_step:
             show("PI", buf("PI").reshape(B, 4), t2n(rec32["pi"]), t2n(rec64["pi"]))
             show("PIB", buf("PIB").reshape(B, 4), t2n(rec32["pi_bc"]), t2n(rec64["pi_bc"]))
+            if "soft_q" in rec32:
+                show("ABC", buf("ABC").reshape(B, 4), t2n(rec32["a_bc"]), t2n(rec64["a_bc"])) if "a_bc" in rec32 else None
             show("RLQ", buf("RLQ"), t2n(rec32["rl_q_all"]), t2n(rec64["rl_q_all"]))
             if "soft_q" in rec32:
                 show("SOFTQ", buf("SOFTQ"), t2n(rec32["soft_q"]), t2n(rec64["soft_q"]))
                 print(f"   soft margin min|softQ-rlQ| = {rec32['soft_count_margin']:.3e}")
+            if os.environ.get("HIRL_CLUSTER") != "0":
+                rs2 = ag.debug_buffer(20, 0); print("   RS2[A] head", rs2[:6], " RS2[AB]", ag.debug_buffer(20, 1)[:6])
+                xh2 = ag.debug_buffer(19, 0).reshape(-1, 512); print("   XH2[A] row0 mean/var", xh2[0].mean(), xh2[0].var(), " row20", xh2[20].mean(), xh2[20].var())
+                xh2b = ag.debug_buffer(19, 1).reshape(-1, 512); print("   XH2[AB] row0 mean/var", xh2b[0].mean(), xh2b[0].var())
+                for sl in (2, 3):
+                    dz = ag.debug_buffer(21, sl); print(f"   DZ2S[{sl}] absmax {np.abs(dz).max():.3e} nonzero {np.count_nonzero(dz)}/{dz.size}")
+                    print(f"   DZ1[{sl}] absmax {np.abs(ag.debug_buffer(22, sl)).max():.3e}  DY1 absmax {np.abs(ag.debug_buffer(23, sl)).max():.3e}")
             ga = ag.export_grads(_lib.NET_ACTOR)
             a32 = np.concatenate([v.double().reshape(-1).numpy() for v in rec32["actor.grads"].values()])
             a64 = np.concatenate([v.double().reshape(-1).numpy() for v in rec64["actor.grads"].values()])
