@@ -77,12 +77,32 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // an LDS.128 costs 4 cycles of the shared-memory pipe when a quarter warp reads 8 distinct addresses (weights) and
 // 2.5 when it reads one (activations, broadcast) whether or not the other quarters repeat them, so tall lane tiles
 // (many activation rows, few weight columns) are the cheap ones: RI + 4 LDS.128 per 16 RI FFMA.
-// The 8 partial tiles are summed through red[4][RB][RLD] in a fixed order (deterministic): after the call the value of
+// The 8 partial tiles are summed through red[4][RB][RL] in a fixed order (deterministic): after the call the value of
 // (m, n) is (red[0]+red[1]) + (red[2]+red[3]) at [m * RLD + n].  All 256 threads; contains __syncthreads.
-constexpr int RLD2 = 80;   // row stride of the reduction buffers (lanes mg = 0 / 1 land 16 banks apart)
+template <int RI>
+struct RedLd { static constexpr int v = RI == 8 ? 80 : 64; };   // row stride of the reduction buffers (80: lanes mg = 0 / 1 land 16 banks apart)
+template <int RI>
+__device__ __forceinline__ void fwd_round(const float *ap, const float *bp, int r, float4 (&a)[RI], float4 (&b)[4]) {
+#pragma unroll
+    for (int i = 0; i < RI; ++i) a[i] = *reinterpret_cast<const float4 *>(ap + 2 * i * WLD + 4 * r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4 *>(bp + 16 * j * WLD + 4 * r);
+}
+template <int RI>
+__device__ __forceinline__ void fwd_fma(const float4 (&a)[RI], const float4 (&b)[4], float (&acc)[RI][4]) {
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+            acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+            acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+            acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+        }
+}
 template <int RI>
 __device__ __forceinline__ void fwd_pass(const float *As, const float *Ws, float *red) {
-    constexpr int RBv = 2 * RI;
+    constexpr int RBv = 2 * RI, RL = RedLd<RI>::v;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, mg = lane >> 4, ng = lane & 15;
     const float *ap = As + mg * WLD + 32 * warp;
     const float *bp = Ws + ng * WLD + 32 * warp;
@@ -91,57 +111,37 @@ __device__ __forceinline__ void fwd_pass(const float *As, const float *Ws, float
     for (int i = 0; i < RI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    float4 a[RI], b[4];
-#pragma unroll
-    for (int i = 0; i < RI; ++i) a[i] = *reinterpret_cast<const float4 *>(ap + 2 * i * WLD);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4 *>(bp + 16 * j * WLD);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        float4 an[RI], bn[4];
-        if (r + 1 < 8) {
-#pragma unroll
-            for (int i = 0; i < RI; ++i) an[i] = *reinterpret_cast<const float4 *>(ap + 2 * i * WLD + 4 * (r + 1));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bn[j] = *reinterpret_cast<const float4 *>(bp + 16 * j * WLD + 4 * (r + 1));
-        }
-#pragma unroll
-        for (int i = 0; i < RI; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
-                acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
-                acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
-                acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
-            }
-        if (r + 1 < 8) {
-#pragma unroll
-            for (int i = 0; i < RI; ++i) a[i] = an[i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = bn[j];
-        }
+    float4 a0[RI], b0[4], a1[RI], b1[4];
+    fwd_round<RI>(ap, bp, 0, a0, b0);
+    // rolled (instruction-cache resident): 4 iterations of two k-rounds with ping-pong fragments
+#pragma unroll 1
+    for (int r = 0; r < 8; r += 2) {
+        fwd_round<RI>(ap, bp, r + 1, a1, b1);
+        fwd_fma<RI>(a0, b0, acc);
+        if (r + 2 < 8) fwd_round<RI>(ap, bp, r + 2, a0, b0);
+        fwd_fma<RI>(a1, b1, acc);
     }
-    float *p = red + (warp & 3) * RBv * RLD2 + mg * RLD2 + ng;
+    float *p = red + (warp & 3) * RBv * RL + mg * RL + ng;
     __syncthreads();   // readers of the previous pass' sums are done
     if (warp >= 4) {
 #pragma unroll
         for (int i = 0; i < RI; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) p[2 * i * RLD2 + 16 * j] = acc[i][j];
+            for (int j = 0; j < 4; ++j) p[2 * i * RL + 16 * j] = acc[i][j];
     }
     __syncthreads();
     if (warp < 4) {
 #pragma unroll
         for (int i = 0; i < RI; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) p[2 * i * RLD2 + 16 * j] += acc[i][j];
+            for (int j = 0; j < 4; ++j) p[2 * i * RL + 16 * j] += acc[i][j];
     }
     __syncthreads();
 }
 template <int RI>
 __device__ __forceinline__ float fwd_value(const float *red, int m, int n) {
-    constexpr int S = 2 * RI * RLD2;
-    const float *q = red + m * RLD2 + n;
+    constexpr int RL = RedLd<RI>::v, S = 2 * RI * RL;
+    const float *q = red + m * RL + n;
     return (q[0] + q[S]) + (q[2 * S] + q[3 * S]);
 }
 
@@ -257,20 +257,22 @@ __device__ __forceinline__ void dw_accumulate(const float *Dz, const float *Hs, 
             for (int k = 0; k < KL; ++k) acc[i][k] = fmaf(a[i], h[k], acc[i][k]);
     }
 }
-// fixed-order sum of the 8 warps' partial tiles through red[4][TK][64] (transposed: n contiguous).  On return thread t
-// holds G[n][k] for n = t & 63, k = KPT * (t >> 6) + j, j < KPT = TK / 4.  Contains barriers.
+// fixed-order sum of the 8 warps' partial tiles through red[4][TK][DLD] (transposed: n contiguous, DLD = 68).  On return
+// thread t holds G[n][k] for k = t % TK, n = t / TK + (256 / TK) j, j < 64 TK / 256: lanes run along k, so the Adam
+// stage's accesses to W2[n][k0 + k] are contiguous.  Contains barriers.
+constexpr int DLD = NS + 4;
 template <int TK>
 __device__ __forceinline__ void dw_reduce(float (&acc)[8][TK / 4], float *red, float (&g)[TK / 4]) {
-    constexpr int KL = TK / 4, KPT = TK / 4;
+    constexpr int KL = TK / 4, NPT = TK / 4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, ng = lane & 7, kg = lane >> 3;
-    float *p = red + (warp & 3) * TK * NS;
+    float *p = red + (warp & 3) * TK * DLD;
     __syncthreads();
     if (warp >= 4) {
 #pragma unroll
         for (int k = 0; k < KL; ++k)
 #pragma unroll
             for (int u = 0; u < 2; ++u)
-                *reinterpret_cast<float4 *>(p + (KL * kg + k) * NS + 32 * u + 4 * ng) = make_float4(acc[4 * u][k], acc[4 * u + 1][k], acc[4 * u + 2][k], acc[4 * u + 3][k]);
+                *reinterpret_cast<float4 *>(p + (KL * kg + k) * DLD + 32 * u + 4 * ng) = make_float4(acc[4 * u][k], acc[4 * u + 1][k], acc[4 * u + 2][k], acc[4 * u + 3][k]);
     }
     __syncthreads();
     if (warp < 4) {
@@ -278,17 +280,17 @@ __device__ __forceinline__ void dw_reduce(float (&acc)[8][TK / 4], float *red, f
         for (int k = 0; k < KL; ++k)
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                float4 *q = reinterpret_cast<float4 *>(p + (KL * kg + k) * NS + 32 * u + 4 * ng);
+                float4 *q = reinterpret_cast<float4 *>(p + (KL * kg + k) * DLD + 32 * u + 4 * ng);
                 const float4 t = *q;
                 *q = make_float4(t.x + acc[4 * u][k], t.y + acc[4 * u + 1][k], t.z + acc[4 * u + 2][k], t.w + acc[4 * u + 3][k]);
             }
     }
     __syncthreads();
-    const int n = tid & 63, kq = tid >> 6;
+    const int kk = tid % TK, nn = tid / TK;
 #pragma unroll
-    for (int j = 0; j < KPT; ++j) {
-        const float *q = red + (KPT * kq + j) * NS + n;
-        g[j] = (q[0] + q[TK * NS]) + (q[2 * TK * NS] + q[3 * TK * NS]);
+    for (int j = 0; j < NPT; ++j) {
+        const float *q = red + kk * DLD + nn + (CTHREADS / TK) * j;
+        g[j] = (q[0] + q[TK * DLD]) + (q[2 * TK * DLD] + q[3 * TK * DLD]);
     }
 }
 

@@ -444,9 +444,11 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
         proto.use_tc = atoi(e) == 1;
         proto.tc_g1 = atoi(e) == 2;
     }
-    // Cluster-resident kernel (csrc/cluster_update.cuh): single agent, FP32 path.  HIRL_CLUSTER=0/1 overrides; an explicit
-    // HIRL_TC selects one of the stage-structured back-ends of round 1 instead.
-    proto.use_cluster = (R == 1 && !proto.use_tc && !getenv("HIRL_TC")) ? 1 : 0;
+    // Cluster-resident kernel (csrc/cluster_update.cuh): single agent, FP32 path, selected with HIRL_CLUSTER=1.  Measured
+    // on B200 (profiles/r2_cluster_timeline.txt) it needs 4 instead of 16 grid barriers per actor call and keeps the
+    // activations on chip, but every one of its sequential sub-steps is latency-bound with 8 warps per SM: 132 us per
+    // batch-256 step against 112 us for the stage-structured kernel, which therefore stays the default.
+    proto.use_cluster = 0;
     if (const char *e = getenv("HIRL_CLUSTER")) proto.use_cluster = (atoi(e) != 0 && R == 1) ? 1 : 0;
     proto.cluster_ri = 8;
     proto.Bpad = ((cfg->batch + 15) / 16) * 16;
