@@ -138,6 +138,90 @@ __device__ __forceinline__ void fwd_pass(const float *As, const float *Ws, float
     }
     __syncthreads();
 }
+// ---- the same pass on the tensor cores: mma.sync m16n8k8 TF32 with the 3-product split (3xTF32) ------------------
+// x = hi + lo, hi = x with the 13 low mantissa bits cleared (what the tensor core reads from an fp32 word), lo = x - hi
+// (exact in fp32); z += lo.hi + hi.lo + hi.hi, accumulated in fp32.  The K range of a warp is only 32, so an accumulation
+// chain is 12 MMAs long and the 8 warps' partial tiles are added in fp32 as before: the result is as close to the fp64
+// product as the FFMA version (tools/cluster_probe4.cu).  Fragments are read straight from the padded [rows][260]
+// operand layouts with conflict-free LDS.32 (bank = 4 row + k), a quarter of the shared-memory traffic of the FFMA tile.
+// Rows 16 .. RB-1 (RB = 18) do not fill a second m16 tile; they are computed with FFMA by all threads.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int RI>
+__device__ __forceinline__ void fwd_pass_mma(const float *As, const float *Ws, float *red) {
+    constexpr int RBv = 2 * RI, RL = RedLd<RI>::v;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    const float *ap = As + g * WLD + 32 * warp + t, *bp = Ws + g * WLD + 32 * warp + t;
+#pragma unroll 1
+    for (int ks = 0; ks < 4; ++ks) {
+        uint32_t ahi[4], alo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float x = ap[(i & 1) * 8 * WLD + (i >> 1) * 4 + 8 * ks];
+            ahi[i] = __float_as_uint(x) & 0xffffe000u;
+            alo[i] = __float_as_uint(x - __uint_as_float(ahi[i]));
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float y0 = bp[nt * 8 * WLD + 8 * ks], y1 = bp[nt * 8 * WLD + 8 * ks + 4];
+            const uint32_t h0 = __float_as_uint(y0) & 0xffffe000u, h1 = __float_as_uint(y1) & 0xffffe000u;
+            const uint32_t l0 = __float_as_uint(y0 - __uint_as_float(h0)), l1 = __float_as_uint(y1 - __uint_as_float(h1));
+            mma_tf32(acc[nt], alo, h0, h1);
+            mma_tf32(acc[nt], ahi, l0, l1);
+            mma_tf32(acc[nt], ahi, h0, h1);
+        }
+    }
+    // rows 16.. (RB = 18): FFMA, thread = (row, column quarter) x k-range of the warp
+    float ex[4] = {0.f, 0.f, 0.f, 0.f};
+    if (RBv > 16) {
+        const int er = lane >> 4, ec = lane & 15;
+        const float *eap = As + (16 + er) * WLD + 32 * warp, *ebp = Ws + ec * WLD + 32 * warp;
+#pragma unroll 2
+        for (int r = 0; r < 8; ++r) {
+            const float4 a = *reinterpret_cast<const float4 *>(eap + 4 * r);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 b = *reinterpret_cast<const float4 *>(ebp + 16 * j * WLD + 4 * r);
+                ex[j] = fmaf(a.x, b.x, ex[j]); ex[j] = fmaf(a.y, b.y, ex[j]); ex[j] = fmaf(a.z, b.z, ex[j]); ex[j] = fmaf(a.w, b.w, ex[j]);
+            }
+        }
+    }
+    float *p = red + (warp & 3) * RBv * RL;
+    __syncthreads();   // readers of the previous pass' sums are done
+    if (warp >= 4) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            *reinterpret_cast<float2 *>(p + g * RL + 8 * nt + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+            *reinterpret_cast<float2 *>(p + (g + 8) * RL + 8 * nt + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+        }
+        if (RBv > 16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p[(16 + (lane >> 4)) * RL + (lane & 15) + 16 * j] = ex[j];
+        }
+    }
+    __syncthreads();
+    if (warp < 4) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            float2 *q0 = reinterpret_cast<float2 *>(p + g * RL + 8 * nt + 2 * t), *q1 = reinterpret_cast<float2 *>(p + (g + 8) * RL + 8 * nt + 2 * t);
+            const float2 u0 = *q0, u1 = *q1;
+            *q0 = make_float2(u0.x + acc[nt][0], u0.y + acc[nt][1]);
+            *q1 = make_float2(u1.x + acc[nt][2], u1.y + acc[nt][3]);
+        }
+        if (RBv > 16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p[(16 + (lane >> 4)) * RL + (lane & 15) + 16 * j] += ex[j];
+        }
+    }
+    __syncthreads();
+}
+
 template <int RI>
 __device__ __forceinline__ float fwd_value(const float *red, int m, int n) {
     constexpr int RL = RedLd<RI>::v, S = 2 * RI * RL;
