@@ -8,8 +8,11 @@ One "step" = one learn() call (reference hirl/agents/HIRL.py:221-334) on one syn
           the K timed steps (CUDA events on the launching stream, max over ranks)
   e2e     updates/s through the public drop-in call Agent.learn(): host RNG draws, H2D of the
           step's indices from pinned memory, the launch, D2H of the step's scalars -- every step
-  --impl reference   the CPU torch restatement of the reference's learn() (oracle/, pinned
-          bit-for-bit to the unmodified reference) on the box's host cores
+  --impl reference   the UNMODIFIED reference hirl.agents.HIRL.Agent.learn (files staged under oracle/_ref by
+          `make -C oracle`) on the box's host cores, CUDA hidden; the oracle port only as a loud fallback
+Every timed figure is the MEDIAN of several repeats of the K-step region (each repeat bracketed by a barrier +
+synchronize on both sides and reduced with MAX over ranks).  The default line also carries sub-records for the other
+BASELINE configs (`configs.fixed4096`, `configs.ensemble128`) and the env pass on this rank's shard (`roofline_env`).
 N>1: independent agent replicas (different seeds), one per GPU, no collective (weak scaling).
 """
 from __future__ import annotations
@@ -145,23 +148,56 @@ def cpu_baseline(wl, calls, warm=6, seed=0):
     return calls / dt, dt
 
 
+def reference_cpu(wl, calls, repeats=3, warm=6):
+    """The unmodified reference's learn() on the host cores (subprocess, CUDA hidden).  Returns (updates/s, info dict) or
+    None when oracle/_ref has not been staged (then the caller falls back to the oracle port, and says so)."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref", "hirl", "agents", "HIRL.py")
+    if not os.path.exists(ref_dir):
+        return None
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS=str(os.cpu_count() or 1), MKL_NUM_THREADS=str(os.cpu_count() or 1))
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--batch", str(wl["batch"]), "--bcw", str(wl["bcw"]),
+           "--expert", str(wl["expert_num"]), "--calls", str(calls), "--repeats", str(repeats), "--warm", str(warm),
+           "--online", str(N_ONLINE), "--experts", str(N_EXPERT)]
+    t0 = time.perf_counter()
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+    if res.returncode != 0:
+        sys.stderr.write("reference arm failed, falling back to the oracle port:\n" + res.stderr[-2000:] + "\n")
+        return None
+    info = json.loads(res.stdout.strip().splitlines()[-1])
+    info["wall_s"] = time.perf_counter() - t0
+    return info["updates_per_s"], info
+
+
+def cpu_arm(wl, calls, repeats=3):
+    """(value, cores, kind, sample) of the CPU baseline: the unmodified reference when staged, else the oracle port."""
+    got = reference_cpu(wl, calls, repeats)
+    if got is not None:
+        val, info = got
+        return val, info["threads"], "reference", (f"unmodified hirl/agents/HIRL.py learn() (oracle/_ref), CUDA hidden, {info['threads']} torch threads on "
+                                                    f"{info['nproc']} host CPUs: median of {repeats} x {calls} consecutive calls (whole 6-call cycles) "
+                                                    f"after 6 warm-up calls; repeats {['%.1f' % r for r in info['all']]} updates/s")
+    sys.stderr.write("WARNING: oracle/_ref is not staged (run `make -C oracle` where /root/reference exists): timing the oracle PORT instead\n")
+    torch.set_num_threads(os.cpu_count() or 1)
+    val, dt = cpu_baseline(wl, calls)
+    return val, torch.get_num_threads(), "port", f"{calls} learn() calls of the oracle port (oracle/hirl_oracle.py) after 6 warm-up calls ({dt:.1f} s)"
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    torch.set_num_threads(os.cpu_count() or 1)
-    per_call_guess = 0.012 if wl["batch"] <= 256 else 0.08
-    calls = max(6, min(args.steps, int(150 / per_call_guess)))      # bounded: <= ~2.5 min of CPU work
-    calls -= calls % 6 if calls >= 12 else 0                           # whole 6-call cycles
-    val, dt = cpu_baseline(wl, calls, warm=max(6, min(args.warmup, 60)))
-    sample = f"{calls} consecutive learn() calls (whole 6-call cycles) of the same workload, {dt:.1f} s of CPU time"
+    # BASELINE.md section 3: >= 300 calls at batch 256 (>= 30 at 4096), whole 6-call cycles, median of 3 repeats;
+    # bounded so that the arm ends within a few minutes whatever --steps says
+    calls = 300 if wl["batch"] <= 256 else 36
+    val, cores, kind, sample = cpu_arm(wl, calls, repeats=3)
     line = {"impl": "reference", "metric": "agent updates/sec", "value": val, "unit": "updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_of(args, wl),
-            "cpu_baseline": {"value": val, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": val, "unit": "updates/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "ONE CPU process on rank 0 whatever --gpus says: at N > 1 compare it with the per-GPU rate of the other arm"}
     emit(line)
 
 
@@ -208,44 +244,166 @@ def device_resident_run(ag, wl, n_steps):
     return launch, out_d
 
 
-def env_roofline(device, peaks):
-    from hirl4ucav_b200 import synth
+def env_roofline(device, peaks, rank, world):
+    """The env pass on this rank's contiguous shard of the 10 M synthetic pursuit states (BASELINE config 5)."""
+    from hirl4ucav_b200 import synth, parallel
     from hirl4ucav_b200.environments import harfang_math as hm
-    n = 10_000_000
+    n_total = 10_000_000
+    a, b = parallel.shard_range(n_total, world, rank)
+    n = b - a
     raw = synth.raw_states(np.random.default_rng(5), 1 << 20)
-    d_raw = torch.from_numpy(np.tile(raw, (10, 1))[:n].copy()).to(device)
+    d_raw = torch.from_numpy(np.tile(raw, (n // (1 << 20) + 1, 1))[:n].copy()).to(device)
     for _ in range(3):
         hm.step_math(d_raw)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 20
-    e0.record()
+    reps, inner = 7, 20
+    times = []
     for _ in range(reps):
-        hm.step_math(d_raw)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all(world)
+        e0.record()
+        for _ in range(inner):
+            hm.step_math(d_raw)
+        e1.record()
+        sync_all(world)
+        times.append(e0.elapsed_time(e1) / inner)
+    ms = median_over_repeats(times, device, world)
     gbs = n * 124 / (ms * 1e-3) / 1e9
     return {"kernel": "env_step_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            "traffic": NCU_ENV_DRAM_BYTES_PER_STATE * n, "traffic_source": NCU_TRAFFIC_SOURCE, "states": n, "ms_per_pass": ms, "evals_per_s": n / (ms * 1e-3),
-            "note": "10 M synthetic pursuit states, 124 algorithmic B/state (64 in + 60 out), 1.24 GB per pass >> L2, includes torch output allocation"}
+            "traffic": NCU_ENV_DRAM_BYTES_PER_STATE * n, "traffic_source": NCU_TRAFFIC_SOURCE, "states_per_gpu": n, "states_total": n_total,
+            "ms_per_pass": ms, "evals_per_s": n_total / (ms * 1e-3), "achieved_is": "per GPU (its shard); evals_per_s is the whole job over all GPUs",
+            "note": f"{n_total} synthetic pursuit states in contiguous shards over {world} GPU(s), no exchange; 124 algorithmic B/state (64 in + 60 out), "
+                    f"{n * 124 / 1e6:.0f} MB per pass per GPU >> L2; median of {reps} x {inner} back-to-back passes, max over ranks; includes torch output allocation"}
 
 
-def run_ensemble(args):
-    """BASELINE config 4: R replicas per GPU in one ensemble launch; a step = every replica makes one learn() call."""
-    rank, local, world = dist_env()
-    from hirl4ucav_b200 import _lib, synth, parallel
-    from hirl4ucav_b200.ensemble import AgentEnsemble
-    from hirl4ucav_b200.environments import harfang_math as hm
-    wl = WORKLOADS[args.workload]
-    R = args.replicas or wl["replicas"]
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+def sync_all(world):
+    torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    K, W = min(args.steps, 60), min(max(args.warmup, 3), 12)
-    K -= K % 6 if K >= 6 else 0
-    peaks, peak_src = measured_peaks()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def median_over_repeats(times, dev, world):
+    """times: this rank's per-repeat figures -> MAX over ranks per repeat, then the median repeat."""
+    t = torch.tensor(times, dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.median().item())
+
+
+def n_repeats(K, per_step_ms):
+    """Enough repeats of the K-step region to make the median robust (>= 0.15 s of timed work), 3..25."""
+    return int(max(3, min(25, np.ceil(150.0 / max(K * per_step_ms, 1e-3)))))
+
+
+def tf32_dense_peak(dev):
+    """Dense TF32 matmul throughput (torch.matmul fp32, allow_tf32, 8192^3), same burst protocol as MEASURED_PEAKS.json's bf16 figure:
+    the denominator of the 3xTF32 tensor-core paths (divide by 3: every fp32-accurate product costs three TF32 MMAs)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn((n, n), device=dev, dtype=torch.float32)
+        b = torch.randn((n, n), device=dev, dtype=torch.float32)
+        for _ in range(3):
+            torch.matmul(a, b)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b)
+        e1.record(); torch.cuda.synchronize()
+        return 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def time_single_agent(name, K, W, local, rank, world, fp32_peak, tf32_peak, peaks, peak_src, with_fused):
+    """Device-resident and end-to-end timing of one single-agent workload; returns the record fields."""
+    wl = WORKLOADS[name]
+    dev = torch.device("cuda", local)
+    ag = build_agent(wl, local, seed=rank, max_steps=max(K, W, 64))
+    B = wl["batch"]
+    guess = 0.12 if B <= 256 else 0.5
+    # ---- value: device-resident streams, one persistent launch for the K timed steps
+    warm, _ = device_resident_run(ag, wl, W)
+    warm(); torch.cuda.synchronize()
+    timed, out_d = device_resident_run(ag, wl, K)
+    reps = n_repeats(K, guess)
+    times = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all(world)
+        e0.record(); timed(); e1.record()
+        sync_all(world)
+        times.append(e0.elapsed_time(e1))
+    ms_total = median_over_repeats(times, dev, world)
+    last = out_d[-1].cpu().numpy()
+    assert np.isfinite(last[:4]).all(), f"non-finite losses {last}"
+    # ---- e2e: the public per-call API, host buffers, copies inside the timed region
+    for _ in range(W):
+        ag.learn(wl["bcw"], wl["expert_num"], 0)
+    ereps = n_repeats(K, guess * 1.6)
+    etimes = []
+    for _ in range(ereps):
+        sync_all(world)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            ag.learn(wl["bcw"], wl["expert_num"], 0)
+        torch.cuda.synchronize()
+        etimes.append(time.perf_counter() - t0)
+        sync_all(world)
+    e2e_s = median_over_repeats(etimes, dev, world)
+    rec = {"value": world * K / (ms_total * 1e-3), "unit": "updates/s", "ms_per_step": ms_total / K, "steps": K, "repeats": reps,
+           "repeat_spread_ms_per_step": [min(times) / K, max(times) / K],
+           "e2e": {"value": world * K / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": 3 * B * 4 + 64, "d2h_bytes_per_step": 32, "repeats": ereps,
+                   "api": "Agent.learn() per call (hirl_learn: pinned host index/noise streams -> H2D, one launch, D2H scalars)"}}
+    if with_fused:
+        # e2e, fused form of the same public API: learn_many in chunks of 60 calls
+        chunk = [(wl["bcw"], wl["expert_num"], 0)] * 60
+        nchunks = max(1, K // 60)
+        ag.learn_many(chunk)
+        ftimes = []
+        for _ in range(max(3, ereps // 2)):
+            sync_all(world)
+            t0 = time.perf_counter()
+            for _ in range(nchunks):
+                ag.learn_many(chunk)
+            torch.cuda.synchronize()
+            ftimes.append(time.perf_counter() - t0)
+            sync_all(world)
+        fused_s = median_over_repeats(ftimes, dev, world)
+        rec["e2e_fused"] = {"value": world * nchunks * 60 / fused_s, "unit": "updates/s", "api": "Agent.learn_many(60 calls) per launch, host buffers"}
+    flops_per_step = wl["flop_per_row"] * B
+    achieved = flops_per_step * K / (ms_total * 1e-3) / 1e12          # per GPU
+    if B >= 512:    # every 256<->512 contraction on tcgen05, 3xTF32 (csrc/tc_gemm.cuh)
+        rec["roofline"] = {"kernel": "hirl_update_kernel (tcgen05 3xTF32 tiles)", "bound": "tensor", "achieved": achieved, "peak": tf32_peak / 3.0,
+                           "unit": "TFLOP/s", "frac": achieved / (tf32_peak / 3.0), "traffic": None, "flop_per_step": flops_per_step,
+                           "peak_source": f"in-run dense TF32 matmul (torch.matmul fp32, allow_tf32, 8192^3: {tf32_peak:.0f} TFLOP/s) / 3 -- an fp32-accurate "
+                                          "product costs three TF32 MMAs; achieved = algorithmic fp32 FLOP/s per GPU",
+                           "frac_of_fp32_fma_peak": achieved / fp32_peak, "frac_of_bf16_tensor_burst": achieved / peaks.get("bf16_tflops", 1660.5)}
+    else:
+        rec["roofline"] = {"kernel": "hirl_update_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                           "frac": achieved / fp32_peak if fp32_peak else None,
+                           "traffic": NCU_UPDATE_DRAM_BYTES_PER_STEP[name] * K if name in NCU_UPDATE_DRAM_BYTES_PER_STEP else None,
+                           "traffic_source": NCU_TRAFFIC_SOURCE,
+                           "peak_source": "in-run register-resident FFMA loop (hirl_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
+                           "flop_per_step": flops_per_step, "frac_of_bf16_tensor_burst": achieved / peaks.get("bf16_tflops", 1660.5),
+                           "tensor_peak_source": peak_src}
+    del ag
+    return rec
+
+
+def time_ensemble(name, K, W, R, local, rank, world, fp32_peak, tf32_peak):
+    """BASELINE config 4: R replicas per GPU in one ensemble launch; a step = every replica makes one learn() call."""
+    from hirl4ucav_b200 import synth, parallel
+    from hirl4ucav_b200.ensemble import AgentEnsemble
+    from hirl4ucav_b200.environments import harfang_math as hm
+    wl = WORKLOADS[name]
+    dev = torch.device("cuda", local)
     es, ea = synth.expert_table(N_EXPERT)
     erows, _ = hm.expert_scan(es, ea, local)
     seeds = parallel.replica_seeds(0, R * world, world, rank)          # replica i has seed i wherever it runs
@@ -261,64 +419,50 @@ def run_ensemble(args):
         ens.store_rows(r, erows, expert=True)
     ens.reseed(1)
     calls = [(wl["bcw"], wl["expert_num"], 0)]
-    sampler = ClockSampler(local)
-    with sampler:
-        ens.draw(calls * W)
-        warm, _ = ens.device_streams(W)
-        warm(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ens.draw(calls * K)
-        draw_s = time.perf_counter() - t0
-        timed, out_d = ens.device_streams(K)
+    ens.draw(calls * W)
+    warm, _ = ens.device_streams(W)
+    warm(); torch.cuda.synchronize()
+    ens.draw(calls * K)
+    timed, out_d = ens.device_streams(K)
+    times = []
+    for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier(); torch.cuda.synchronize()
+        sync_all(world)
         e0.record(); timed(); e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier(); torch.cuda.synchronize()
-        ms_total = e0.elapsed_time(e1)
-        assert torch.isfinite(out_d[:, -1, :4]).all()
-        # e2e: the public call with host buffers (host RNG pre-draw + H2D + launch + D2H)
+        sync_all(world)
+        times.append(e0.elapsed_time(e1))
+    ms_total = median_over_repeats(times, dev, world)
+    assert torch.isfinite(out_d[:, -1, :4]).all()
+    etimes = []
+    for _ in range(3):
+        sync_all(world)
         t0 = time.perf_counter()
         ens.learn_many(calls * K)
-        e2e_s = time.perf_counter() - t0
-    ms_total = parallel.max_over_ranks(ms_total, dev)
-    e2e_s = parallel.max_over_ranks(e2e_s, dev)
-    if rank == 0:
-        B = wl["batch"]
-        value = world * R * K / (ms_total * 1e-3)
-        fp32 = C.c_double(0)
-        _lib.check(_lib.load().hirl_measure_fp32_peak(local, C.byref(fp32)))
-        achieved = wl["flop_per_row"] * B * R * K / (ms_total * 1e-3) / 1e12
-        hbm = 11.1e6 * R * K / (ms_total * 1e-3) / 1e9
-        line = {"metric": "agent updates/sec", "value": value, "unit": "replica-updates/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": dict(config_of(args, wl), replicas_per_gpu=R, replicas_total=R * world,
-                                                      parallelism=f"{R} replicas/GPU x {world} GPUs, teams of CTAs, no collective"),
-                "clocks": sampler.summary(),
-                "e2e": {"value": world * R * K / e2e_s, "unit": "replica-updates/s", "h2d_bytes_per_step": R * (3 * B * 4 + 64),
-                        "d2h_bytes_per_step": R * 32, "api": "AgentEnsemble.learn_many (host RNG streams of every replica + H2D + launch + D2H)",
-                        "host_draw_seconds": draw_s},
-                "gpu_launches": 1,
-                "roofline": {"kernel": "hirl_ensemble_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32.value, "unit": "TFLOP/s",
-                             "frac": achieved / fp32.value, "traffic": None, "hbm_stream_gbs_if_weights_streamed": hbm,
-                             "note": "weights + Adam state of 128 replicas = 1.1 GB > L2: 11.1 MB algorithmic HBM bytes per replica-update"}}
-        emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+        etimes.append(time.perf_counter() - t0)
+        sync_all(world)
+    e2e_s = median_over_repeats(etimes, dev, world)
+    B = wl["batch"]
+    achieved = wl["flop_per_row"] * B * R * K / (ms_total * 1e-3) / 1e12     # per GPU
+    hbm = 11.1e6 * R * K / (ms_total * 1e-3) / 1e9
+    rec = {"value": world * R * K / (ms_total * 1e-3), "unit": "replica-updates/s", "ms_per_step": ms_total / K, "steps": K, "repeats": 3,
+           "replicas_per_gpu": R, "replicas_total": R * world, "parallelism": f"{R} replicas/GPU x {world} GPUs, teams of CTAs, no collective",
+           "e2e": {"value": world * R * K / e2e_s, "unit": "replica-updates/s", "h2d_bytes_per_step": R * (3 * B * 4 + 64), "d2h_bytes_per_step": R * 32,
+                   "api": "AgentEnsemble.learn_many (host RNG streams of every replica + H2D + launch + D2H)"},
+           "roofline": {"kernel": "hirl_ensemble_kernel (tcgen05 3xTF32 tiles)", "bound": "tensor", "achieved": achieved, "peak": tf32_peak / 3.0, "unit": "TFLOP/s",
+                        "frac": achieved / (tf32_peak / 3.0), "traffic": None, "frac_of_fp32_fma_peak": achieved / fp32_peak,
+                        "hbm_stream_gbs_if_weights_streamed": hbm,
+                        "peak_source": f"in-run dense TF32 matmul ({tf32_peak:.0f} TFLOP/s) / 3; achieved = algorithmic fp32 FLOP/s per GPU",
+                        "note": "weights + Adam state of 128 replicas = 1.1 GB > L2: 11.1 MB algorithmic HBM bytes per replica-update"}}
+    del ens
+    return rec
 
 
 def run_ours(args):
     rank, local, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
-    if "replicas" in WORKLOADS[args.workload]:
-        return run_ensemble(args)
     from hirl4ucav_b200 import _lib
     lib = _lib.load()
-    wl = WORKLOADS[args.workload]
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -326,88 +470,49 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
     peaks, peak_src = measured_peaks()
-    ag = build_agent(wl, local, seed=rank, max_steps=max(K, W, 64))
+    fp32 = C.c_double(0)
+    _lib.check(lib.hirl_measure_fp32_peak(local, C.byref(fp32)))
+    tf32 = tf32_dense_peak(dev)
     sampler = ClockSampler(local)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
+    name = args.workload
+    subs = {}
     with sampler:
-        # ---- value: device-resident streams, one persistent launch for the K timed steps
-        warm, _ = device_resident_run(ag, wl, W)
-        warm(); torch.cuda.synchronize()
-        timed, out_d = device_resident_run(ag, wl, K)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record(); timed(); e1.record()
-        barrier()
-        ms_total = e0.elapsed_time(e1)
-        last = out_d[-1].cpu().numpy()
-        assert np.isfinite(last[:4]).all(), f"non-finite losses {last}"
-        # ---- e2e: the public per-call API, host buffers, copies inside the timed region
-        for _ in range(W):
-            ag.learn(wl["bcw"], wl["expert_num"], 0)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            r = ag.learn(wl["bcw"], wl["expert_num"], 0)
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        barrier()
-        # ---- e2e, fused form of the same public API: learn_many in chunks of 60 calls
-        chunk = [(wl["bcw"], wl["expert_num"], 0)] * 60
-        nchunks = max(1, K // 60)
-        ag.learn_many(chunk)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(nchunks):
-            ag.learn_many(chunk)
-        torch.cuda.synchronize()
-        fused_s = time.perf_counter() - t0
-        if rank == 0 and world == 1:
-            roof_env = env_roofline(dev, peaks)
-    t = torch.tensor([ms_total, e2e_s, fused_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s, fused_s = t.tolist()
+        if "replicas" in WORKLOADS[name]:
+            Ke = max(6, min(K, 60) // 6 * 6)
+            head = time_ensemble(name, Ke, 6, args.replicas or WORKLOADS[name]["replicas"], local, rank, world, fp32.value, tf32)
+            K, W = Ke, 6
+        else:
+            head = time_single_agent(name, K, W, local, rank, world, fp32.value, tf32, peaks, peak_src, with_fused=True)
+        if not args.no_subrecords:
+            # the other BASELINE configs ride along in the default line (the driver runs bench.py without --workload)
+            if name != "fixed4096":
+                subs["fixed4096"] = dict(time_single_agent("fixed4096", 12, 6, local, rank, world, fp32.value, tf32, peaks, peak_src, with_fused=False),
+                                         workload=WORKLOADS["fixed4096"]["desc"])
+            if name != "ensemble128":
+                subs["ensemble128"] = dict(time_ensemble("ensemble128", 6, 6, WORKLOADS["ensemble128"]["replicas"], local, rank, world, fp32.value, tf32),
+                                           workload=WORKLOADS["ensemble128"]["desc"])
+        roof_env = env_roofline(dev, peaks, rank, world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    wl = WORKLOADS[name]
+    line = {"metric": "agent updates/sec", "value": head["value"], "unit": head["unit"], "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_of(args, wl), "clocks": sampler.summary(), "e2e": head["e2e"],
+            "gpu_launches": head["repeats"],
+            "gpu_launches_note": "value: every repeat is ONE persistent update-kernel launch covering the K timed steps (median repeat reported); e2e: K launches per repeat",
+            "repeats": head["repeats"], "repeat_spread_ms_per_step": head.get("repeat_spread_ms_per_step"),
+            "roofline": head["roofline"], "roofline_env": roof_env}
+    if "e2e_fused" in head:
+        line["e2e_fused"] = head["e2e_fused"]
+    if subs:
+        line["configs"] = subs
     B = wl["batch"]
-    value = world * K / (ms_total * 1e-3)
-    flops_per_step = wl["flop_per_row"] * B
-    fp32 = C.c_double(0)
-    _lib.check(lib.hirl_measure_fp32_peak(local, C.byref(fp32)))
-    achieved = flops_per_step * K / (ms_total * 1e-3) / 1e12
-    line = {
-        "metric": "agent updates/sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": config_of(args, wl), "clocks": sampler.summary(),
-        "e2e": {"value": world * K / e2e_s, "unit": "updates/s", "h2d_bytes_per_step": 3 * B * 4 + 64, "d2h_bytes_per_step": 32,
-                "api": "Agent.learn() per call (hirl_learn: pinned host index/noise streams -> H2D, one launch, D2H scalars)"},
-        "e2e_fused": {"value": world * nchunks * 60 / fused_s, "unit": "updates/s", "api": "Agent.learn_many(60 calls) per launch, host buffers"},
-        "gpu_launches": 1,
-        "gpu_launches_note": "value: ONE persistent hirl_update_kernel launch covers the K timed steps; e2e: K launches",
-        "roofline": {"kernel": "hirl_update_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32.value, "unit": "TFLOP/s",
-                     "frac": achieved / fp32.value if fp32.value else None,
-                     "traffic": NCU_UPDATE_DRAM_BYTES_PER_STEP[args.workload] * K if args.workload in NCU_UPDATE_DRAM_BYTES_PER_STEP else None,
-                     "traffic_source": NCU_TRAFFIC_SOURCE,
-                     "peak_source": "in-run register-resident FFMA loop (hirl_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
-                     "flop_per_step": flops_per_step,
-                     "frac_of_bf16_tensor_burst": achieved / peaks.get("bf16_tflops", 1660.5), "tensor_peak_source": peak_src},
-    }
-    if world == 1:
-        line["roofline_env"] = roof_env
-        torch.set_num_threads(os.cpu_count() or 1)
-        calls = 300 if B <= 256 else 36
-        val, dt = cpu_baseline(wl, calls)
-        line["cpu_baseline"] = {"value": val, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{calls} learn() calls of the same workload after 6 warm-up calls ({dt:.1f} s); oracle/hirl_oracle.py, "
-                                          "bit-identical to the unmodified reference in the build container"}
+    calls = 300 if B <= 256 else 36
+    val, cores, kind, sample = cpu_arm(wl, calls, repeats=3)
+    line["cpu_baseline"] = {"value": val, "unit": "updates/s", "cores": cores, "kind": kind, "sample": sample,
+                            "note": "one CPU process (rank 0): compare with value / n_gpus at N > 1"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -421,6 +526,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="soft256", choices=sorted(WORKLOADS))
     ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU for the ensemble workload")
+    ap.add_argument("--no-subrecords", action="store_true", help="skip the configs.fixed4096 / configs.ensemble128 sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
