@@ -44,7 +44,7 @@ class _MemoryView:
             i += r._size
         if not 0 <= i < r._size:
             raise IndexError("list index out of range")
-        if r._dev_ranges:
+        if r._n_stale:
             r.sync_host()
         row = r._rows[i]
         return Transition(row[0:S].copy(), row[S:S + A].copy(), row[S + A:S + A + S].copy(), float(row[30]),
@@ -68,7 +68,13 @@ class UniformMemory(object):
         self._dirty_from = None   # first dirty slot (ring order) and count
         self._dirty_n = 0
         self._backend = None      # (handle, buffer id) once attached to an agent
-        self._dev_ranges = []     # [(first_slot, n, flags tensor)] appended on the device, not mirrored on the host yet
+        # Device-side appends (store_batch_dev) are tracked PER SLOT, so the bookkeeping is bounded by the ring whatever
+        # the number of appends: which slots hold rows / step_success values the host mirror has not seen yet, and one
+        # device array of the step_success values (no reference to the caller's flag tensors is kept).
+        self._rows_stale = None   # np.bool_[capacity], allocated on the first device append
+        self._succ_stale = None
+        self._dev_success = None  # torch.int8[capacity] on the agent's device
+        self._n_stale = 0         # slots with a stale host row or step_success
         self.memory = _MemoryView(self)
 
     # ---- device attachment -------------------------------------------------------------
@@ -117,7 +123,21 @@ class UniformMemory(object):
         _lib.check(lib.hirl_store_transitions_dev(handle, 0, which, self.position, n, states.data_ptr(), actions.data_ptr(),
                                                   next_states.data_ptr(), rewards.data_ptr(), flags.data_ptr(),
                                                   stream.cuda_stream))
-        self._dev_ranges.append((self.position, n, flags))
+        if self._rows_stale is None:
+            self._rows_stale = np.zeros(self.capacity, np.bool_)
+            self._succ_stale = np.zeros(self.capacity, np.bool_)
+            self._dev_success = torch.zeros(self.capacity, dtype=torch.int8, device=states.device)
+        idx = (self.position + np.arange(n)) % self.capacity
+        succ = ((flags >> 8) & 0xFF).to(torch.int8)          # byte 1 of the flag word = step_success (two's complement)
+        if self.position + n <= self.capacity:
+            self._dev_success[self.position:self.position + n] = succ
+        else:
+            k = self.capacity - self.position
+            self._dev_success[self.position:] = succ[:k]
+            self._dev_success[:n - k] = succ[k:]
+        self._rows_stale[idx] = True     # a slot overwritten by ring wrap is simply marked again: nothing accumulates
+        self._succ_stale[idx] = True
+        self._n_stale = int(np.count_nonzero(self._rows_stale | self._succ_stale))
         self._dev_event = torch.cuda.Event()
         self._dev_event.record(stream)
         if self.upsample:   # the weighted draw needs step_success on the host (buffer.py:21-29)
@@ -133,33 +153,43 @@ class UniformMemory(object):
             self._dev_event = None
 
     def sync_host(self, rows=True):
-        """Brings step_success (and with rows=True the row contents) of device-appended transitions to the host."""
-        if not self._dev_ranges:
+        """Brings step_success (and with rows=True the row contents) of device-appended slots to the host mirror."""
+        if not self._n_stale:
             return
         handle, which = self._backend
         lib = _lib.load()
-        keep = []
-        for first, n, flags in self._dev_ranges:
-            idx = (first + np.arange(n)) % self.capacity
-            if flags is not None:
-                succ = ((flags.cpu().numpy().astype(np.int32) >> 8) & 0xFF).astype(np.uint8).view(np.int8)
-                self._success[idx] = succ
-                if self.upsample:
-                    self.priorities_memory[idx] = np.where(succ == 1, 1.0, 0.1)
-            if rows:
+        sidx = np.flatnonzero(self._succ_stale)
+        if sidx.size:
+            torch.cuda.synchronize()                          # appends may have been queued on any stream
+            succ = self._dev_success.cpu().numpy()
+            self._success[sidx] = succ[sidx]
+            if self.upsample:
+                self.priorities_memory[sidx] = np.where(succ[sidx] == 1, 1.0, 0.1)
+            self._succ_stale[:] = False
+        if rows:
+            ridx = np.flatnonzero(self._rows_stale)
+            if ridx.size:
+                self.flush()                                  # host-dirty rows first (they never share a slot with a stale one)
                 torch.cuda.synchronize()
-                idx32 = _lib.i32c(idx)
+                idx32 = _lib.i32c(ridx)
+                n = int(ridx.size)
                 out = np.empty((n, ROW), np.float32)
                 on, ex = (idx32, None) if which == _lib.BUF_ONLINE else (None, idx32)
                 _lib.check(lib.hirl_gather(handle, 0, None if on is None else _lib.ptr(on), 0 if on is None else n,
                                            None if ex is None else _lib.ptr(ex), 0 if ex is None else n, _lib.ptr(out)))
-                self._rows[idx] = out
-            else:
-                keep.append((first, n, None))
-        self._dev_ranges = keep
+                self._rows[ridx] = out
+                self._rows_stale[:] = False
+        self._n_stale = int(np.count_nonzero(self._rows_stale)) if self._rows_stale is not None else 0
+
+    def _host_wrote(self, p):
+        """A host-side store into slot p supersedes whatever the device appended there."""
+        if self._n_stale and (self._rows_stale[p] or self._succ_stale[p]):
+            self._rows_stale[p] = self._succ_stale[p] = False
+            self._n_stale -= 1
 
     # ---- reference surface ---------------------------------------------------------------
     def store(self, state, action, next_state, reward, done, step_success):
+        self._host_wrote(self.position)
         row = self._rows[self.position]
         row[0:S] = state            # float64 -> float32, the cast the reference does at sample time
         row[S:S + A] = action
@@ -181,6 +211,7 @@ class UniformMemory(object):
         rows32 = np.ascontiguousarray(rows32, np.float32).reshape(-1, ROW)
         for i in range(rows32.shape[0]):
             p = self.position
+            self._host_wrote(p)
             self._rows[p] = rows32[i]
             self._success[p] = 0 if success is None else success[i]
             if self.upsample:

@@ -108,3 +108,40 @@ def test_upsampling_priorities_follow_device_appends():
     pr = ag.buffer.priorities_memory[100:100 + n]
     assert np.array_equal(pr, np.where(succ == 1, 1.0, 0.1))                              # buffer.py:21-29
     assert ag.buffer.memory[101].step_success == -1
+
+
+def test_device_append_bookkeeping_is_bounded_and_respects_later_host_stores():
+    """a long act -> env -> store_batch_dev -> learn loop must not accumulate per-append state, a ring
+    wrap must not replay stale ranges, and a host store() issued AFTER a device append into the same slot must survive the
+    lazy mirror refresh."""
+    sc = scenarios.make_scenario(40, 400)
+    ag = scenarios.build_agent(Agent, sc, 16, 0, hp={"bufferSize": 64})
+    buf = ag.buffer
+    d = torch.device("cuda", 0)
+    rng = np.random.default_rng(11)
+    n = 24
+    for it in range(40):                                    # 960 device-appended rows through a 64-slot ring
+        s, a, s2 = (torch.from_numpy(x.astype(np.float32)).to(d) for x in (synth.env_states(rng, n), synth.env_actions(rng, n), synth.env_states(rng, n)))
+        r = torch.full((n,), float(it), device=d)
+        fl = torch.full((n,), ((it % 3 - 1) & 0xFF) << 8, dtype=torch.int32, device=d)
+        ag.store_batch_dev(s, a, s2, r, fl)
+        if it % 10 == 9:
+            assert all(np.isfinite(float(x)) for x in ag.learn(0.5, 0, 0))
+    assert not hasattr(buf, "_dev_ranges") and buf._n_stale <= buf.capacity
+    assert buf._rows_stale.shape == (64,) and buf._dev_success.shape == (64,)
+    pos = buf.position
+    last = (pos - 1) % 64
+    # newest row: iteration 39; the slot 24 places behind it: iteration 38; 48 behind: iteration 37 (partly overwritten ring)
+    ag.store(sc["s"][1], sc["a"][1], sc["s2"][1], -5.0, True, 1)          # host store lands at `pos`, over a device-appended slot
+    assert buf.memory[last].reward == 39.0 and buf.memory[last].step_success == (39 % 3 - 1)
+    assert buf.memory[(last - 24) % 64].reward == 38.0 and buf.memory[(last - 24) % 64].step_success == (38 % 3 - 1)
+    tr = buf.memory[pos]
+    assert tr.reward == -5.0 and tr.done is True and tr.step_success == 1   # not clobbered by the device gather
+    assert buf._n_stale == 0
+    # and the device sees the host row too
+    got = np.empty((1, 32), np.float32)
+    idx = np.array([pos], np.int32)
+    buf.flush()
+    torch.cuda.synchronize()
+    _lib.check(_lib.load().hirl_gather(ag._h, 0, _lib.ptr(idx), 1, None, 0, _lib.ptr(got)))
+    assert got[0, 30] == -5.0 and got[0, 31] == 1.0

@@ -137,6 +137,62 @@ def _teacher_forced(B, bcw, en, steps):
     print(f"B={B}: worst gradient rel-L2 vs torch fp32 over {steps} teacher-forced steps: {worst:.2e}")
 
 
+DB_RLQ, DB_SOFTQ = 14, 15   # csrc/common.cuh: enum DebugBuf
+
+
+def test_soft_count_is_tie_aware_per_row():
+    """the soft BC weight is a COUNT of strict per-row comparisons soft_Q > rl_Q (HIRL.py:303).  Per row the
+    kernel's two Q values must match the oracle's to fp32 accuracy, its comparison may differ from the oracle's only where
+    the oracle's own margin |soft_Q - rl_Q| is below eps (a tie that summation order decides), and the weight the call
+    returns must be exactly the mean of the kernel's own per-row comparisons."""
+    B, en = 256, 64
+    sc = scenarios.make_scenario(1500, 900)
+    orc = scenarios.build_agent(OracleAgent, sc, B, 0)
+    ag = scenarios.build_agent(Agent, sc, B, 0)
+    scenarios.seed_all(7)
+    checked = flips = 0
+    for t in range(10):
+        r32 = {}
+        actor_step = orc.actorTrainable
+        out32 = orc.learn(100, en, 0, rec=r32)
+        d = orc.last_draws
+        out = ag.learn(100, en, 0, forced={"online": d["online"], "expert": d["expert"], "bc": d["bc"], "noise": d["noise"]})
+        if actor_step:
+            softq, rlq = ag.debug_buffer(DB_SOFTQ)[:B].astype(np.float64), ag.debug_buffer(DB_RLQ)[:B].astype(np.float64)
+            o_s, o_r = r32["soft_q"].double().numpy().ravel(), r32["rl_q"].double().numpy().ravel()
+            scale = max(1.0, float(np.abs(o_r).max()), float(np.abs(o_s).max()))
+            assert np.abs(softq - o_s).max() <= 1e-5 * scale and np.abs(rlq - o_r).max() <= 1e-5 * scale
+            mine, theirs = softq > rlq, o_s > o_r
+            eps = 2e-5 * scale
+            flipped = mine != theirs
+            assert not (flipped & (np.abs(o_s - o_r) >= eps)).any(), f"step {t}: comparison differs on a row with a clear margin"
+            assert out[5] == min(np.float32(mine.sum()) / np.float32(B), 1.0), f"step {t}: returned weight {out[5]} vs own count {mine.sum()}"
+            assert abs(int(mine.sum()) - int(theirs.sum())) <= int(flipped.sum())
+            checked += 1
+            flips += int(flipped.sum())
+        sync_to_oracle(ag, orc)
+    assert checked == 5
+    print(f"soft count: {checked} actor calls x {B} rows compared, {flips} tie rows decided differently")
+
+
+def test_soft_count_exact_ties_count_as_not_greater():
+    """bc_actor == actor makes Q1(s, a_bc) and Q1(s, pi(s)) the same number on every row: the reference's strict '>' gives
+    weight 0.0.  The kernel evaluates both through the same code on the same inputs, so it must see exact ties too."""
+    B = 128
+    sc = scenarios.make_scenario(1000, 600)
+    orc = scenarios.build_agent(OracleAgent, sc, B, 0)
+    ag = scenarios.build_agent(Agent, sc, B, 0)
+    orc.bc_actor.load_state_dict(orc.actor.state_dict())
+    ag.bc_actor.load_state_dict(orc.actor.state_dict())
+    ag.push_parameters()
+    scenarios.seed_all(3)
+    out32 = orc.learn(100, 16, 0)
+    d = orc.last_draws
+    out = ag.learn(100, 16, 0, forced={"online": d["online"], "expert": d["expert"], "bc": d["bc"], "noise": d["noise"]})
+    assert out32[5] == 0.0 and out[5] == 0.0
+    assert np.array_equal(ag.debug_buffer(DB_SOFTQ)[:B], ag.debug_buffer(DB_RLQ)[:B])
+
+
 @pytest.mark.parametrize("name", ["soft32", "fixed32", "soft256"])
 def test_free_run_matches_reference_fixture(golden_dir, name):
     """Same seeds as the unmodified reference: own RNG draws, own weights, 12 free-running calls."""
