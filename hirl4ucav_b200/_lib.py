@@ -74,6 +74,8 @@ SYMBOLS = {
     "hirl_env_offline_dev": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "hirl_env_offline": (_i, [_i, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "hirl_expert_scan": (_i, [_i, _vp, _vp, _i, _vp, _vp, C.POINTER(_i)]),
+    "hirl_env_offline_f64": (_i, [_i, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "hirl_expert_scan_f64": (_i, [_i, _vp, _vp, _i, _vp, _vp, C.POINTER(_i)]),
     "hirl_measure_fp32_peak": (_i, [_i, C.POINTER(C.c_double)]),
 }
 

@@ -240,8 +240,12 @@ class Agent(object):
             noise = noise.to(device=states.device, dtype=torch.float32).contiguous()
             nrows = noise.numel() // 4
             nz = noise.data_ptr()
-        _lib.check(self._lib.hirl_act_dev(self._h, 0, ids[net], states.data_ptr(), n, out.data_ptr(), nz, nrows,
-                                          torch.cuda.current_stream(states.device).cuda_stream))
+        stream = torch.cuda.current_stream(states.device)
+        _lib.check(self._lib.hirl_act_dev(self._h, 0, ids[net], states.data_ptr(), n, out.data_ptr(), nz, nrows, stream.cuda_stream))
+        # the act kernel READS the actor on the caller's stream while learn() WRITES it on the agent's own stream:
+        # the next update must wait for this launch (acting interleaved with training without a store in between)
+        self._act_event = torch.cuda.Event()
+        self._act_event.record(stream)
         return out
 
     def store_batch_dev(self, states, actions, next_states, rewards, flags):
@@ -377,6 +381,9 @@ class Agent(object):
         self.expert_buffer.flush()
         if getattr(self.buffer, "_dev_event", None) is not None:   # device-side appends run on the caller's stream
             self.buffer.wait_device_appends(self._update_stream())
+        if getattr(self, "_act_event", None) is not None:           # so do device-side acting launches (they read the actor)
+            self._update_stream().wait_event(self._act_event)
+            self._act_event = None
 
     def _launch(self, k_steps, predraw_for=None):
         self._pre_launch()

@@ -82,7 +82,10 @@ __device__ __forceinline__ void env_one(const float4 &q0, const float4 &q1, cons
     bool done = (pay < 500.0) || (pay > 10000.0);
     const bool ep = health <= 0.0;
     done = done || ep;
-    o.flags = (int)done | ((int)ep << 1) | ((int)fire_success << 2) | ((int)fired << 3) | ((succ & 0xFF) << 8);
+    // bit 3: the policy's fire rule a[3] > 0 (GYM.py:150); bit 4: the EXPERT's fire rule on the new observation,
+    // obs[7] > 0 and obs[8] > 0 = target locked and missile slot loaded (data/straight_line/ai_data_col.py:63-64)
+    const bool expert_fire = locked_now && missile_now;
+    o.flags = (int)done | ((int)ep << 1) | ((int)fire_success << 2) | ((int)fired << 3) | ((int)expert_fire << 4) | ((succ & 0xFF) << 8);
 }
 
 // one thread per state; outputs are staged through shared memory so that every global store is
@@ -130,12 +133,15 @@ __global__ void __launch_bounds__(ENV_THREADS, HIRL_ENV_MIN_BLOCKS) env_step_ker
     }
 }
 
-// offline reward / termination on normalised observations (GYM.py:299-336)
-__global__ void __launch_bounds__(ENV_THREADS) env_offline_kernel(const float *__restrict__ s, const float *__restrict__ a,
-                                                                  const float *__restrict__ s2, long long n, float *__restrict__ reward,
+// offline reward / termination on normalised observations (GYM.py:299-336).  T = float: replay-shaped fp32 rows;
+// T = double: the expert CSV as read_data delivers it (utils/data_processor.py:5-11) -- the reference evaluates these
+// thresholds on the float64 values, and (double)(float)x <= 0.1 is not x <= 0.1 for x = 0.1.
+template <typename T>
+__global__ void __launch_bounds__(ENV_THREADS) env_offline_kernel(const T *__restrict__ s, const T *__restrict__ a,
+                                                                  const T *__restrict__ s2, long long n, float *__restrict__ reward,
                                                                   signed char *__restrict__ success, unsigned char *__restrict__ done) {
     for (long long i = (long long)blockIdx.x * ENV_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * ENV_THREADS) {
-        const float *p = s + 13 * i, *q = s2 + 13 * i;
+        const T *p = s + 13 * i, *q = s2 + 13 * i;
         const double x = (double)q[0] * 10000.0, y = (double)q[1] * 10000.0, z = (double)q[2] * 10000.0;
         const double loc = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
         double r = 0.0;

@@ -1124,37 +1124,42 @@ int hirl_env_offline_dev(const float *s13_dev, const float *a4_dev, const float 
                          uint8_t *done_dev, void *stream) {
     if (n < 0 || (n > 0 && (!s13_dev || !a4_dev || !s2_13_dev || !reward_dev || !success_dev || !done_dev))) return fail(HIRL_E_INVALID, "bad argument");
     if (n == 0) return 0;
-    env_offline_kernel<<<env_grid(n, ENV_THREADS), ENV_THREADS, 0, (cudaStream_t)stream>>>(s13_dev, a4_dev, s2_13_dev, n, reward_dev,
+    env_offline_kernel<float><<<env_grid(n, ENV_THREADS), ENV_THREADS, 0, (cudaStream_t)stream>>>(s13_dev, a4_dev, s2_13_dev, n, reward_dev,
                                                                                             reinterpret_cast<signed char *>(success_dev), done_dev);
     CU(cudaGetLastError());
     return 0;
 }
-int hirl_env_offline(int device, const float *s13, const float *a4, const float *s2_13, int64_t n, float *reward, int8_t *success, uint8_t *done) {
+}  // extern "C"
+// host-buffer form of the offline pass for fp32 rows (T = float) and for the float64 expert table (T = double)
+template <typename T>
+static int env_offline_host(int device, const T *s13, const T *a4, const T *s2_13, int64_t n, float *reward, int8_t *success, uint8_t *done) {
     if (n < 0 || (n > 0 && (!s13 || !a4 || !s2_13 || !reward || !success || !done))) return fail(HIRL_E_INVALID, "bad argument");
     if (n == 0) return 0;
     CU(cudaSetDevice(device));
-    float *d_s = nullptr, *d_a = nullptr, *d_s2 = nullptr, *d_r = nullptr;
+    T *d_s = nullptr, *d_a = nullptr, *d_s2 = nullptr;
+    float *d_r = nullptr;
     int8_t *d_su = nullptr;
     uint8_t *d_d = nullptr;
-    CU(cudaMalloc(&d_s, (size_t)n * 52)); CU(cudaMalloc(&d_a, (size_t)n * 16)); CU(cudaMalloc(&d_s2, (size_t)n * 52));
+    const size_t w = sizeof(T);
+    CU(cudaMalloc(&d_s, (size_t)n * 13 * w)); CU(cudaMalloc(&d_a, (size_t)n * 4 * w)); CU(cudaMalloc(&d_s2, (size_t)n * 13 * w));
     CU(cudaMalloc(&d_r, (size_t)n * 4)); CU(cudaMalloc(&d_su, (size_t)n)); CU(cudaMalloc(&d_d, (size_t)n));
-    CU(cudaMemcpy(d_s, s13, (size_t)n * 52, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d_a, a4, (size_t)n * 16, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d_s2, s2_13, (size_t)n * 52, cudaMemcpyHostToDevice));
-    int rc = hirl_env_offline_dev(d_s, d_a, d_s2, n, d_r, d_su, d_d, nullptr);
-    if (!rc) {
-        CU(cudaMemcpy(reward, d_r, (size_t)n * 4, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(success, d_su, (size_t)n, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(done, d_d, (size_t)n, cudaMemcpyDeviceToHost));
-    }
+    CU(cudaMemcpy(d_s, s13, (size_t)n * 13 * w, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_a, a4, (size_t)n * 4 * w, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_s2, s2_13, (size_t)n * 13 * w, cudaMemcpyHostToDevice));
+    env_offline_kernel<T><<<env_grid(n, ENV_THREADS), ENV_THREADS>>>(d_s, d_a, d_s2, n, d_r, reinterpret_cast<signed char *>(d_su), d_d);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(reward, d_r, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(success, d_su, (size_t)n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(done, d_d, (size_t)n, cudaMemcpyDeviceToHost));
     cudaFree(d_s); cudaFree(d_a); cudaFree(d_s2); cudaFree(d_r); cudaFree(d_su); cudaFree(d_d);
-    return rc;
+    return 0;
 }
-
 // train_all.py:287-306.  The reward/flag pass over all consecutive pairs runs on the GPU; the
 // data-dependent "skip the row after a terminal next-state" walk is a sequential scan over n
-// bytes on the host (it has a loop-carried dependence and costs microseconds).
-int hirl_expert_scan(int device, const float *states13, const float *actions4, int n, float *out_rows32, int8_t *out_success, int *n_rows_out) {
+// bytes on the host (it has a loop-carried dependence and costs microseconds).  Stored rows are the fp32 casts
+// the reference makes at sample time (HIRL.py:229-233), whatever the input precision.
+template <typename T>
+static int expert_scan_host(int device, const T *states13, const T *actions4, int n, float *out_rows32, int8_t *out_success, int *n_rows_out) {
     if (!states13 || !actions4 || !out_rows32 || !out_success || !n_rows_out || n < 0) return fail(HIRL_E_INVALID, "bad argument");
     *n_rows_out = 0;
     if (n < 2) return 0;
@@ -1162,13 +1167,13 @@ int hirl_expert_scan(int device, const float *states13, const float *actions4, i
     std::vector<float> r(m);
     std::vector<int8_t> su(m);
     std::vector<uint8_t> d(m);
-    if (int rc = hirl_env_offline(device, states13, actions4, states13 + S, m, r.data(), su.data(), d.data())) return rc;
+    if (int rc = env_offline_host<T>(device, states13, actions4, states13 + S, m, r.data(), su.data(), d.data())) return rc;
     int kept = 0;
     for (int i = 0; i < m;) {
         float *row = out_rows32 + (size_t)kept * ROW;
-        std::memcpy(row, states13 + (size_t)i * S, S * 4);
-        std::memcpy(row + S, actions4 + (size_t)i * A, A * 4);
-        std::memcpy(row + SA, states13 + (size_t)(i + 1) * S, S * 4);
+        for (int k = 0; k < S; ++k) row[k] = (float)states13[(size_t)i * S + k];
+        for (int k = 0; k < A; ++k) row[S + k] = (float)actions4[(size_t)i * A + k];
+        for (int k = 0; k < S; ++k) row[SA + k] = (float)states13[(size_t)(i + 1) * S + k];
         row[30] = r[i];
         row[31] = d[i] ? 1.f : 0.f;
         out_success[kept] = su[i];
@@ -1177,6 +1182,19 @@ int hirl_expert_scan(int device, const float *states13, const float *actions4, i
     }
     *n_rows_out = kept;
     return 0;
+}
+extern "C" {
+int hirl_env_offline(int device, const float *s13, const float *a4, const float *s2_13, int64_t n, float *reward, int8_t *success, uint8_t *done) {
+    return env_offline_host<float>(device, s13, a4, s2_13, n, reward, success, done);
+}
+int hirl_env_offline_f64(int device, const double *s13, const double *a4, const double *s2_13, int64_t n, float *reward, int8_t *success, uint8_t *done) {
+    return env_offline_host<double>(device, s13, a4, s2_13, n, reward, success, done);
+}
+int hirl_expert_scan(int device, const float *states13, const float *actions4, int n, float *out_rows32, int8_t *out_success, int *n_rows_out) {
+    return expert_scan_host<float>(device, states13, actions4, n, out_rows32, out_success, n_rows_out);
+}
+int hirl_expert_scan_f64(int device, const double *states13, const double *actions4, int n, float *out_rows32, int8_t *out_success, int *n_rows_out) {
+    return expert_scan_host<double>(device, states13, actions4, n, out_rows32, out_success, n_rows_out);
 }
 
 int hirl_measure_fp32_peak(int device, double *tflops_out) {

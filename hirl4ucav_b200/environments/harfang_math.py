@@ -24,7 +24,7 @@ import torch
 from .. import _lib
 
 F_LOCKED_PREV, F_LOCKED_NOW, F_MISSILE_PREV, F_MISSILE_NOW, F_FIRE_SUCCESS = 1, 2, 4, 8, 16
-O_DONE, O_EPISODE_SUCCESS, O_FIRE_SUCCESS, O_FIRED = 1, 2, 4, 8
+O_DONE, O_EPISODE_SUCCESS, O_FIRE_SUCCESS, O_FIRED, O_EXPERT_FIRE = 1, 2, 4, 8, 16
 
 
 def pack_raw(p_ally, e_ally, p_opp, e_opp, angle_deg, health, act_fire, flags) -> np.ndarray:
@@ -41,7 +41,12 @@ def decode_flags(flags):
     f = np.asarray(flags, np.int32)
     succ = ((f >> 8) & 0xFF).astype(np.uint8).view(np.int8).astype(np.int32)
     return {"done": (f & O_DONE) != 0, "episode_success": (f & O_EPISODE_SUCCESS) != 0,
-            "fire_success": (f & O_FIRE_SUCCESS) != 0, "fired": (f & O_FIRED) != 0, "step_success": succ}
+            "fire_success": (f & O_FIRE_SUCCESS) != 0, "fired": (f & O_FIRED) != 0, "expert_fire": (f & O_EXPERT_FIRE) != 0,
+            "step_success": succ}
+
+
+def _f64c(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
 
 
 def _stream_ptr():
@@ -84,21 +89,29 @@ def offline_reward(s, a, s2, device=0):
             _lib.check(lib.hirl_env_offline_dev(s.data_ptr(), a.data_ptr(), s2.data_ptr(), n, rew.data_ptr(), su.data_ptr(),
                                                 dn.data_ptr(), _stream_ptr()))
         return rew, su, dn.bool()
-    s, a, s2 = _lib.f32c(s).reshape(-1, 13), _lib.f32c(a).reshape(-1, 4), _lib.f32c(s2).reshape(-1, 13)
+    # float64 inputs (the expert CSV, Python floats) keep their precision: the reference compares them in float64
+    f64 = any(np.asarray(x).dtype == np.float64 for x in (s, a, s2))
+    cast = _f64c if f64 else _lib.f32c
+    s, a, s2 = cast(s).reshape(-1, 13), cast(a).reshape(-1, 4), cast(s2).reshape(-1, 13)
     n = s.shape[0]
     rew, su, dn = np.empty(n, np.float32), np.empty(n, np.int8), np.empty(n, np.uint8)
-    _lib.check(lib.hirl_env_offline(device, _lib.ptr(s), _lib.ptr(a), _lib.ptr(s2), n, _lib.ptr(rew), _lib.ptr(su), _lib.ptr(dn)))
+    fn = lib.hirl_env_offline_f64 if f64 else lib.hirl_env_offline
+    _lib.check(fn(device, _lib.ptr(s), _lib.ptr(a), _lib.ptr(s2), n, _lib.ptr(rew), _lib.ptr(su), _lib.ptr(dn)))
     return rew, su, dn.astype(bool)
 
 
 def expert_scan(expert_states, expert_actions, device=0):
     """train_all.py:287-306 as one batched pass: rows (M,32) f32 and step_success (M,) i8."""
-    es, ea = _lib.f32c(expert_states).reshape(-1, 13), _lib.f32c(expert_actions).reshape(-1, 4)
+    f64 = np.asarray(expert_states).dtype == np.float64 or np.asarray(expert_actions).dtype == np.float64
+    cast = _f64c if f64 else _lib.f32c
+    es, ea = cast(expert_states).reshape(-1, 13), cast(expert_actions).reshape(-1, 4)
     n = es.shape[0]
     rows = np.empty((max(n - 1, 0), 32), np.float32)
     succ = np.empty(max(n - 1, 0), np.int8)
     kept = C.c_int(0)
-    _lib.check(_lib.load().hirl_expert_scan(device, _lib.ptr(es), _lib.ptr(ea), n, _lib.ptr(rows), _lib.ptr(succ), C.byref(kept)))
+    lib = _lib.load()
+    fn = lib.hirl_expert_scan_f64 if f64 else lib.hirl_expert_scan
+    _lib.check(fn(device, _lib.ptr(es), _lib.ptr(ea), n, _lib.ptr(rows), _lib.ptr(succ), C.byref(kept)))
     return rows[:kept.value], succ[:kept.value]
 
 
@@ -120,8 +133,9 @@ class HarfangEnvMath:
         return float(r[0]), int(su[0])
 
     def get_termination(self, state):
-        z = np.zeros((1, 13), np.float32)
-        _, _, dn = offline_reward(z, np.zeros((1, 4), np.float32), np.asarray(state)[None], self.device)
+        st = np.asarray(state)[None]
+        z = np.zeros((1, 13), st.dtype if st.dtype == np.float64 else np.float32)
+        _, _, dn = offline_reward(z, np.zeros((1, 4), z.dtype), st, self.device)
         return bool(dn[0])
 
     @staticmethod

@@ -188,7 +188,8 @@ int hirl_debug_profile(hirl_agent_t *h, int enable, long long *dst, size_t n);
  * action_fire flags(u32: b0 locked_prev b1 locked_now b2 missile_prev b3 missile_now
  * b4 fire_success).  Outputs: obs[13] fp32 (GYM.py:193-268), reward fp32 (GYM.py:101-137),
  * flags int32: b0 done b1 episode_success (GYM.py:160-169) b2 fire_success b3 fired
- * (GYM.py:150) byte1 step_success int8.  counters (may be NULL): int64[3] running totals
+ * (the policy's rule a[3] > 0, GYM.py:150) b4 expert_fire (the expert's rule obs[7] > 0 and obs[8] > 0 on
+ * the new observation, data/straight_line/ai_data_col.py:63-64) byte1 step_success int8.  counters (may be NULL): int64[3] running totals
  * fired-with-missile, successful fires, dones (Infinite env, GYM.py:519-527). */
 int hirl_env_step_dev(const float *raw16_dev, int64_t n, float *obs13_dev, float *reward_dev,
                       int32_t *flags_dev, unsigned long long *counters3_dev, void *stream);
@@ -200,10 +201,18 @@ int hirl_env_offline_dev(const float *s13_dev, const float *a4_dev, const float 
                          float *reward_dev, int8_t *success_dev, uint8_t *done_dev, void *stream);
 int hirl_env_offline(int device, const float *s13, const float *a4, const float *s2_13, int64_t n,
                      float *reward, int8_t *success, uint8_t *done);
+/* the same on float64 inputs: the reference evaluates get_reward/get_termination on the float64 expert CSV
+ * (train_all.py:295-297 on read_data's arrays), and a threshold such as next_state[12] <= 0.1 (GYM.py:334)
+ * differs between 0.1 and float32(0.1) */
+int hirl_env_offline_f64(int device, const double *s13, const double *a4, const double *s2_13, int64_t n,
+                         float *reward, int8_t *success, uint8_t *done);
 /* expert-buffer construction (train_all.py:287-306): from the (n,13)/(n,4) expert table builds
  * the stored transitions; out_rows32 holds up to n-1 rows, *n_rows_out how many were kept. */
 int hirl_expert_scan(int device, const float *states13, const float *actions4, int n, float *out_rows32,
                      int8_t *out_success, int *n_rows_out);
+/* float64 expert table (what read_data returns): thresholds in float64, stored rows cast to fp32 */
+int hirl_expert_scan_f64(int device, const double *states13, const double *actions4, int n, float *out_rows32,
+                         int8_t *out_success, int *n_rows_out);
 
 /* ---- measurement helper -----------------------------------------------------------------
  * Register-resident FFMA loop on every SM, timed with CUDA events: the FP32-FMA roofline

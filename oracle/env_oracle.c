@@ -63,7 +63,8 @@ void env_oracle_online(const float *raw, long n, double *obs, double *reward, in
         int done = (alt < 500) || (alt > 10000);
         int ep = x[13] <= 0;
         if (ep) done = 1;
-        out_flags[i] = done | ep << 1 | fire_success << 2 | fired << 3 | ((succ & 0xFF) << 8);
+        int expert_fire = o[7] > 0 && o[8] > 0;   /* data/straight_line/ai_data_col.py:63-64 on the new observation */
+        out_flags[i] = done | ep << 1 | fire_success << 2 | fired << 3 | expert_fire << 4 | ((succ & 0xFF) << 8);
     }
 }
 

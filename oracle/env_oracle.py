@@ -39,7 +39,7 @@ POS_NORM = 10000          # constants.py:14  NormStates["Plane_position"]
 EULER_NORM = math.pi      # constants.py:15  NormStates["Plane_Euler_angles"]
 
 F_LOCKED_PREV, F_LOCKED_NOW, F_MISSILE_PREV, F_MISSILE_NOW, F_FIRE_SUCCESS = 1, 2, 4, 8, 16
-O_DONE, O_EPISODE_SUCCESS, O_FIRE_SUCCESS, O_FIRED = 1, 2, 4, 8
+O_DONE, O_EPISODE_SUCCESS, O_FIRE_SUCCESS, O_FIRED, O_EXPERT_FIRE = 1, 2, 4, 8, 16
 
 
 def split_raw(raw: np.ndarray):
@@ -110,7 +110,8 @@ def online_step(raw: np.ndarray):
     """obs (N,13) f64, reward (N,) f64, out_flags (N,) int32 for N raw states.
 
     out_flags: bit0 done, bit1 episode_success, bit2 fire_success (sticky, after this
-    step), bit3 fired, byte1 = step_success as signed int8 (-1, 0, +1).
+    step), bit3 fired (policy rule a[3] > 0, GYM.py:150), bit4 the expert's fire rule on the new observation
+    (obs[7] > 0 and obs[8] > 0, data/straight_line/ai_data_col.py:63-64), byte1 = step_success as signed int8 (-1, 0, +1).
     """
     x, fl = split_raw(raw)
     pa, ea, po, eo = x[:, 0:3], x[:, 3:6], x[:, 6:9], x[:, 9:12]
@@ -154,6 +155,7 @@ def online_step(raw: np.ndarray):
     done = done | ep
     out = (done.astype(np.int32) * O_DONE | ep.astype(np.int32) * O_EPISODE_SUCCESS
            | fire_success.astype(np.int32) * O_FIRE_SUCCESS | fired.astype(np.int32) * O_FIRED
+           | ((obs[:, 7] > 0) & (obs[:, 8] > 0)).astype(np.int32) * O_EXPERT_FIRE      # ai_data_col.py:63-64
            | ((step_success & 0xFF) << 8))
     return obs, r, out.astype(np.int32)
 
@@ -162,7 +164,8 @@ def decode_flags(out_flags: np.ndarray):
     f = np.asarray(out_flags, np.int32)
     succ = ((f >> 8) & 0xFF).astype(np.uint8).view(np.int8).astype(np.int32)
     return {"done": (f & O_DONE) != 0, "episode_success": (f & O_EPISODE_SUCCESS) != 0,
-            "fire_success": (f & O_FIRE_SUCCESS) != 0, "fired": (f & O_FIRED) != 0, "step_success": succ}
+            "fire_success": (f & O_FIRE_SUCCESS) != 0, "fired": (f & O_FIRED) != 0, "expert_fire": (f & O_EXPERT_FIRE) != 0,
+            "step_success": succ}
 
 
 def infinite_counters(out_flags: np.ndarray):

@@ -157,7 +157,9 @@ def run_online_steps(raw: np.ndarray, kind="HarfangEnv"):
             obs[i] = n_state
             rew[i] = reward
             out[i] = (int(bool(done)) | int(bool(env.episode_success)) << 1 | int(bool(env.fire_success)) << 2
-                      | int(bool(env.now_missile_state)) << 3 | ((int(success) & 0xFF) << 8))
+                      | int(bool(env.now_missile_state)) << 3
+                      | int(bool(n_state[7] > 0 and n_state[8] > 0)) << 4     # the expert's rule, verbatim from data/straight_line/ai_data_col.py:63-64
+                      | ((int(success) & 0xFF) << 8))
     return obs, rew, out
 
 

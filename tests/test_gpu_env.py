@@ -98,6 +98,42 @@ def test_offline_functions(golden_dir):
     assert env.get_termination(fo["s2"][3]) == bool(fo["done"][3])
 
 
+def test_offline_thresholds_use_float64_inputs():
+    """the reference evaluates get_reward / get_termination on the float64 CSV values; health == 0.1 (double)
+    satisfies next_state[12] <= 0.1 (GYM.py:334) while float32(0.1) = 0.10000000149 does not."""
+    s = np.zeros((4, 13)); a = np.zeros((4, 4)); s2 = np.zeros((4, 13))
+    s2[:, 12] = [0.1, float(np.float32(0.1)), np.nextafter(0.1, 0.0), 0.2]
+    s[:, 8] = 1.0; s[:, 7] = [1.0, -1.0, 1e-50, 1.0]; a[:, 3] = [1e-60, 1.0, 1.0, -1.0]
+    r, su, dn = hm.offline_reward(s, a, s2)
+    o_r, o_su = env_oracle.offline_reward(s, a, s2)
+    assert list(dn) == [True, False, True, False] == list(env_oracle.offline_done(s2))
+    assert np.array_equal(su.astype(np.int32), o_su) and list(o_su) == [1, -1, 1, 0]
+    assert np.array_equal(r, o_r.astype(np.float32))
+    env = hm.HarfangEnvMath()
+    assert env.get_termination(s2[0]) is True and env.get_termination(s2[0].astype(np.float32)) is False
+    # the expert-buffer walk (train_all.py:287-306) follows the float64 done flags
+    es = np.zeros((6, 13)); ea = np.zeros((6, 4))
+    es[:, 12] = [0.5, 0.1, 0.5, float(np.float32(0.1)), 0.5, 0.5]
+    es[:, 0] = np.arange(6) * 0.01
+    rows, succ = hm.expert_scan(es, ea)
+    use, r_o, d_o, s_o = env_oracle.expert_scan(es, ea)
+    assert list(use) == [0, 2, 3, 4] and len(rows) == 4
+    assert np.array_equal(rows[:, 0], es[use, 0].astype(np.float32)) and np.array_equal(rows[:, 31] != 0, d_o)
+
+
+def test_expert_fire_rule_is_a_flag_bit():
+    """the expert fires iff obs[7] > 0 and obs[8] > 0 (data/straight_line/ai_data_col.py:63-64) -- emitted
+    by env_step_kernel as flag bit 4 next to the policy's rule a[3] > 0 (bit 3, GYM.py:150); both bit-exact."""
+    raw = synth.raw_states(np.random.default_rng(12), 200_003)
+    obs, rew, fl = hm.step_math(raw)
+    d = hm.decode_flags(fl)
+    assert np.array_equal(d["expert_fire"], (obs[:, 7] > 0) & (obs[:, 8] > 0))
+    assert np.array_equal(d["expert_fire"], hm.HarfangEnvMath.expert_fires(obs))
+    assert np.array_equal(d["fired"], hm.HarfangEnvMath.agent_fires(raw[:, 11:15]))
+    od = env_oracle.decode_flags(env_oracle.online_step(raw)[2])
+    assert np.array_equal(d["expert_fire"], od["expert_fire"]) and 0.05 < d["expert_fire"].mean() < 0.5
+
+
 def test_expert_scan_matches_oracle():
     rng = np.random.default_rng(3)
     es, ea = synth.env_states(rng, 5000), synth.env_actions(rng, 5000, expert=True)
