@@ -36,6 +36,7 @@ __device__ __forceinline__ uint32_t cluster_id_x() {
 }
 // all threads of all CTAs of the cluster; release/acquire at cluster scope (orders global and shared::cluster accesses)
 __device__ __forceinline__ void cluster_sync_all() {
+    __syncwarp();   // the .aligned barrier needs a converged warp (see team_sync in update.cuh)
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {

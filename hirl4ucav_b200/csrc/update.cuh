@@ -86,6 +86,10 @@ struct Team {
 // everything the other CTAs wrote before arriving.  (release store + fence.acq_rel instead of two
 // fence.sc: 1.6 % faster on the batch-256 step, same results.)
 __device__ __forceinline__ void team_sync(Team &t) {
+    // Stage functions end in lane-divergent tails (e.g. `if (lane == 0) *rs_out = rstd;`): compute-sanitizer's synccheck
+    // found warps arriving at the aligned barrier below before they had reconverged ("divergent thread(s) in block",
+    // profiles/r2_sanitizer_summary.txt).  An aligned bar.sync in a diverged warp is undefined behaviour, so converge first.
+    __syncwarp();
     __syncthreads();
     t.gen += 1u;
     if (threadIdx.x < 32) {
@@ -1301,7 +1305,14 @@ __device__ __noinline__ void stage_r7(const AgentCtx &c, const hirl_step_t &st, 
 // forceinline, unlike the other stages: as a separate function the nvcc 12.9 build of this stage read a wrong
 // dW2-partials base in warps 1-7 (compute-sanitizer: out-of-bounds __ldcg in adam_arena) although the SASS data
 // flow looks right and any probe added to it made the fault disappear; inlined it is exact (tests/test_gpu_update.py).
+#ifndef HIRL_G8_NOINLINE
+#define HIRL_G8_NOINLINE 0   // 1: build stage_g8 as a separate function again (tools/sanitize_all.sh re-tests the round-1 fault)
+#endif
+#if HIRL_G8_NOINLINE
+__device__ __noinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+#else
 __device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+#endif
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
     const int P = gsize < nchunks ? gsize : nchunks;
     const int nslots = st.mode == 0 ? 2 * P : P;
@@ -1357,7 +1368,10 @@ __device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm
     // kernel and lets them read caller registers directly; with a second call site (a separate BC sequence) the
     // actor Adam received a corrupted pointer in some threads.  One call site each keeps that analysis trivially
     // consistent; modes skip stages with conditions instead.
+    // Control flow uses register copies taken here: racecheck flagged the read of st.do_actor AFTER the last team barrier of
+    // a critic-only call against the next call's write of `st` by a warp that is already one call ahead.
     const bool bc_only = st.mode == 2;   // behaviour cloning (BC.py:160-185): expert-state actor pass, backward, Adam
+    const bool do_actor = st.do_actor != 0;
     HIRL_STAGE(ST_R0, stage_r0(c, st, step, tm, smem))
     HIRL_STAGE(ST_G1, stage_g1(c, st, tm, smem))
     if (!bc_only) {
@@ -1368,7 +1382,7 @@ __device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm
         HIRL_STAGE(ST_R3, stage_r3(c, tm, smem))
         HIRL_STAGE(ST_G4, stage_g4(c, st, tm))
     }
-    if (bc_only || st.do_actor) {
+    if (bc_only || do_actor) {
         if (!bc_only) {
             HIRL_STAGE(ST_R4, stage_r4(c, st, tm))
             HIRL_STAGE(ST_G5, stage_g5(c, st, tm, smem))
