@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.environ.get("HIRL_LIB_PATH") or os.path.join(OUT_DIR, "libhirl_b200.so")   # override: A/B builds
 SOURCES = ["hirl_b200.cu"]
-DEPS = ["common.cuh", "update.cuh", "cluster_update.cuh", "cluster_gemm.cuh", "tc_gemm.cuh", "env.cuh", "host_rng.h", "../../include/hirl_b200.h"]
+DEPS = ["common.cuh", "update.cuh", "cluster_update.cuh", "cluster_gemm.cuh", "tc_gemm.cuh", "tcc_update.cuh", "tcc_mma.cuh", "env.cuh", "host_rng.h", "../../include/hirl_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"] + (os.environ.get("HIRL_NVCC_EXTRA", "").split())
 

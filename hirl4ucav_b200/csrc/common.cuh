@@ -113,6 +113,26 @@ struct Scratch {
     float *PART2A;   // [clusters][PA_WORDS] same for the actor, per branch
 };
 
+// Tensor-core cluster kernel (csrc/tcc_update.cuh): operand images of every W2 and its scratch
+struct TccPtrs {
+    // forward images: per tower [8 feature slices][8 k-blocks][hi 2048 | lo 2048 floats], SWIZZLE_128B tiles of [64][32]
+    float *img_actor, *img_tactor, *img_bc, *img_critic, *img_tcritic;
+    // input-gradient images (W2 read along its output features): per tower [8 slices][2 m-blocks][2 k-chunks][hi 4096 | lo 4096]
+    float *imgt_actor, *imgt_critic;
+    float *DH1P;     // [units][8 CTAs][64 rows][H1]  K-split partials of dH1
+    float *GW2PC;    // [2 towers][4 row blocks][H2][H1] per-row-block dW2 of the critic
+    float *GW2PA;    // [2 branches * 4 row blocks][H2][H1] of the actor
+    float *PARTC;    // [4 row blocks * 8 CTAs][2 towers][CriticL::SMALL] small-parameter partials
+    float *PARTA;    // [2 branches * 4 row blocks * 8 CTAs][ActorL::SMALL]
+    float *TQX;      // [4][2][64] target Q of a tower, exchanged between the two tower clusters of a row block
+    float *SOFTQX;   // [4][64]
+    float *XH2S;     // [4][64][H2] normalised second-layer rows of the actor pass, parked while the Q pass runs
+    float *LPT;      // [16] per-unit loss partials: critic [r][t] at 0..7, cloning (sum sq, fire sq) at 8 + 2 r
+    float *CNT;      // [4][2] soft count and sum of rl_Q per row block
+    unsigned *pflags;   // [16][32] point-to-point flags (generations keep counting across launches)
+    unsigned *gen_ctr;  // calls executed so far by this agent: base of the flag generations of a launch
+};
+
 // Everything one replica's update needs.  Passed to the kernel by value (per-replica array in
 // global memory for ensembles).
 struct AgentCtx {
@@ -141,6 +161,8 @@ struct AgentCtx {
     int tc_g1;             // 1: only the forward GEMMs of stage G1 on tcgen05 (mid-size batches, see hirl_agent_create)
     int dw_split;          // split-K factor of the dW2 GEMMs (reduction over the batch), >= 1
     int BT;                // batch rounded up to 32: leading dimension of the transposed buffers
+    int use_tcc;           // 1: tensor-core cluster kernel (csrc/tcc_update.cuh)
+    TccPtrs tcc;
     int use_cluster;       // 1: cluster-resident kernel (csrc/cluster_update.cuh); rows per block = 2 * cluster_ri
     int cluster_ri, Bpad;  // Bpad = row blocks * rows per block
     float gamma, tau, noise_clamp, loss_lambda;

@@ -11,6 +11,7 @@
 #include "env.cuh"
 #include "update.cuh"
 #include "cluster_update.cuh"
+#include "tcc_update.cuh"
 #include "host_rng.h"
 
 using namespace hirl;
@@ -234,6 +235,7 @@ struct hirl_agent {
     size_t scratch_elems[32];
     bool coop_ok = true;         // cooperative attribute accepted for cluster launches
     int ncl = 0;                 // cluster kernel: co-resident clusters of 8 CTAs used per launch
+    int tcc_ncl = 0;             // tensor-core cluster kernel: clusters per launch
 };
 
 template <class T>
@@ -311,7 +313,23 @@ static int flat_import(hirl_agent *h, int replica, int net, int kind, const floa
     } else tower_to_internal<ActorL>(src, tmp.data());
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(d, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+    // on the agent's stream: a blocking cudaMemcpy from pageable memory may return before the last staged chunk has landed,
+    // and kernels launched on h->stream right afterwards (the image builder below) are not ordered behind the legacy stream
+    CU(cudaMemcpyAsync(d, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (kind == 0 && h->ctxs[replica].use_tcc) {   // tensor-core operand images of W2 (csrc/tcc_update.cuh), rebuilt on the device
+        AgentCtx &c = h->ctxs[replica];
+        const int towers = cr ? 2 : 1;
+        const int w2off = cr ? CriticL::W2 : ActorL::W2, tsize = cr ? CriticL::SIZE : ActorL::SIZE;
+        float *img = net == HIRL_NET_ACTOR ? c.tcc.img_actor : net == HIRL_NET_TARGET_ACTOR ? c.tcc.img_tactor : net == HIRL_NET_BC_ACTOR ? c.tcc.img_bc
+                     : net == HIRL_NET_CRITIC ? c.tcc.img_critic : c.tcc.img_tcritic;
+        float *imgt = net == HIRL_NET_ACTOR ? c.tcc.imgt_actor : net == HIRL_NET_CRITIC ? c.tcc.imgt_critic : nullptr;
+        for (int tw = 0; tw < towers; ++tw)
+            tcc::tcc_images_kernel<<<128, 256, 0, h->stream>>>(d + (size_t)tw * tsize + w2off, img + (size_t)tw * tcc::IMG_FWD,
+                                                                imgt ? imgt + (size_t)tw * tcc::IMG_T : nullptr);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+    }
     if (kind == 0 && h->ctxs[replica].use_cluster) {   // padded W2 image ([H2][H1 + 4] per tower) streamed by the cluster kernel
         const int towers = cr ? 2 : 1;
         const int w2off = cr ? CriticL::W2 : ActorL::W2, tsize = cr ? CriticL::SIZE : ActorL::SIZE;
@@ -452,6 +470,28 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     if (const char *e = getenv("HIRL_CLUSTER")) proto.use_cluster = (atoi(e) != 0 && R == 1) ? 1 : 0;
     proto.cluster_ri = 8;
     proto.Bpad = ((cfg->batch + 15) / 16) * 16;
+    // Tensor-core cluster kernel (csrc/tcc_update.cuh): single HIRL agent (relu or leaky_relu), batch <= 256.  HIRL_TCC=0/1
+    // overrides; TD3 / BC step modes are not implemented there, the wrapper classes of those agents pass HIRL_TCC=0 semantics
+    // through cfg->activation == leaky (TD3.py, BC.py) -> stage kernel.
+    proto.use_tcc = 0;   // opt-in until validated: (R == 1 && cfg->batch <= 4 * tcc::RB && cfg->activation == HIRL_ACT_RELU && !proto.use_cluster)
+    if (const char *e = getenv("HIRL_TCC")) proto.use_tcc = (atoi(e) != 0 && R == 1 && cfg->batch <= 4 * tcc::RB && !proto.use_cluster) ? 1 : 0;
+    if (proto.use_tcc && (getenv("HIRL_TC") || getenv("HIRL_NSPLIT") || getenv("HIRL_DW_SPLIT")) && !getenv("HIRL_TCC")) proto.use_tcc = 0;   // explicit stage-kernel knobs select the stage kernel
+    if (proto.use_tcc) {
+        CU(cudaFuncSetAttribute(tcc::hirl_tcc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcc::SMEM_BYTES));
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(tcc::MAX_NCL * tcc::CL); lc.blockDim = dim3(tcc::TTHREADS); lc.dynamicSmemBytes = tcc::SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = tcc::CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        int ncl = 0;
+        CU(cudaOccupancyMaxActiveClusters(&ncl, (const void *)tcc::hirl_tcc_kernel, &lc));
+        ncl = std::min(ncl, tcc::MAX_NCL);
+        if (const char *e = getenv("HIRL_NCL")) ncl = std::min(ncl, std::max(1, atoi(e)));
+        const int nrb = (cfg->batch + tcc::RB - 1) / tcc::RB;
+        if (ncl < 3 * nrb) proto.use_tcc = 0;                        // every unit of a phase needs its own co-resident cluster
+        h->tcc_ncl = ncl;
+        if (proto.use_tcc) proto.use_tc = proto.tc_g1 = 0;
+    }
     if (proto.use_cluster) {
         proto.use_tc = proto.tc_g1 = 0;
         // how many clusters of 8 CTAs are co-resident on this part (B200: 15 or 16, depends on the floor plan of the die)
@@ -545,6 +585,28 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
         if ((rc = dev_alloc(h, &c.carry, 8))) return rc;
         if ((rc = dev_alloc(h, &c.w2t_actor, (size_t)H1 * H2))) return rc;
         if ((rc = dev_alloc(h, &c.w2t_critic, (size_t)2 * H1 * H2))) return rc;
+        if (proto.use_tcc) {
+            TccPtrs &t = c.tcc;
+            if ((rc = dev_alloc(h, &t.img_actor, tcc::IMG_FWD))) return rc;
+            if ((rc = dev_alloc(h, &t.img_tactor, tcc::IMG_FWD))) return rc;
+            if ((rc = dev_alloc(h, &t.img_bc, tcc::IMG_FWD))) return rc;
+            if ((rc = dev_alloc(h, &t.img_critic, 2 * tcc::IMG_FWD))) return rc;
+            if ((rc = dev_alloc(h, &t.img_tcritic, 2 * tcc::IMG_FWD))) return rc;
+            if ((rc = dev_alloc(h, &t.imgt_actor, tcc::IMG_T))) return rc;
+            if ((rc = dev_alloc(h, &t.imgt_critic, 2 * tcc::IMG_T))) return rc;
+            if ((rc = dev_alloc(h, &t.DH1P, (size_t)tcc::MAX_NCL * tcc::CL * tcc::RB * H1))) return rc;
+            if ((rc = dev_alloc(h, &t.GW2PC, (size_t)2 * tcc::MAX_RB * H2 * H1))) return rc;
+            if ((rc = dev_alloc(h, &t.GW2PA, (size_t)2 * tcc::MAX_RB * H2 * H1))) return rc;
+            if ((rc = dev_alloc(h, &t.PARTC, (size_t)tcc::MAX_RB * tcc::CL * 2 * CriticL::SMALL))) return rc;
+            if ((rc = dev_alloc(h, &t.PARTA, (size_t)2 * tcc::MAX_RB * tcc::CL * ActorL::SMALL))) return rc;
+            if ((rc = dev_alloc(h, &t.TQX, (size_t)tcc::MAX_RB * 2 * tcc::RB))) return rc;
+            if ((rc = dev_alloc(h, &t.SOFTQX, (size_t)tcc::MAX_RB * tcc::RB))) return rc;
+            if ((rc = dev_alloc(h, &t.XH2S, (size_t)tcc::MAX_RB * tcc::RB * H2))) return rc;
+            if ((rc = dev_alloc(h, &t.LPT, 16))) return rc;
+            if ((rc = dev_alloc(h, &t.CNT, 8))) return rc;
+            if ((rc = dev_alloc(h, &t.pflags, (size_t)tcc::PF_WORDS * FLAG_STRIDE))) return rc;
+            if ((rc = dev_alloc(h, &t.gen_ctr, 1))) return rc;
+        }
         if (proto.use_cluster) {
             if ((rc = dev_alloc(h, &c.w2p_actor, (size_t)H2 * cl::WLD))) return rc;
             if ((rc = dev_alloc(h, &c.w2p_tactor, (size_t)H2 * cl::WLD))) return rc;
@@ -684,7 +746,30 @@ static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_de
     const size_t B = h->cfg.batch;
     // Barrier flags are never reset: every CTA of a team leaves a launch with the same generation in its flag and
     // resumes from it (no memset per launch, no per-launch kernel argument; the comparison in team_sync is wrap-safe).
-    if (R == 1 && h->ctxs[0].use_cluster) {
+    if (R == 1 && h->ctxs[0].use_tcc) {
+        tcc::TccLaunch L;
+        L.agent = h->ctxs[0];
+        AgentCtx &c = L.agent;
+        c.steps = steps_dev; c.idx_online = ion; c.idx_expert = iex; c.idx_bc = ibc; c.out_scalars = out_dev;
+        L.bar_flags = h->d_bar; L.k_steps = k_steps; L.ncl = h->tcc_ncl;
+        L.prof = h->prof_on ? h->d_prof : nullptr;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(h->tcc_ncl * tcc::CL); lc.blockDim = dim3(tcc::TTHREADS);
+        lc.dynamicSmemBytes = tcc::SMEM_BYTES;
+        lc.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;     // clusters spin on each other's flags: they must be co-resident
+        lc.attrs = at; lc.numAttrs = h->coop_ok ? 1 : 0;
+        void *args[] = {&L};
+        cudaError_t e = cudaLaunchKernelExC(&lc, (const void *)tcc::hirl_tcc_kernel, args);
+        if (e != cudaSuccess && h->coop_ok) {
+            cudaGetLastError();
+            h->coop_ok = false;
+            lc.numAttrs = 0;
+            e = cudaLaunchKernelExC(&lc, (const void *)tcc::hirl_tcc_kernel, args);
+        }
+        if (e != cudaSuccess) return fail(HIRL_E_CUDA, std::string("tcc kernel launch: ") + cudaGetErrorString(e));
+    } else if (R == 1 && h->ctxs[0].use_cluster) {
         cl::ClusterLaunch L;
         L.agent = h->ctxs[0];
         AgentCtx &c = L.agent;
@@ -746,6 +831,7 @@ static int check_steps(hirl_agent *h, int k_steps, const hirl_step_t *steps) {
         if (s.mode != 2 && (s.n_online < 0 || s.n_expert < 0 || s.n_online + s.n_expert != h->cfg.batch))
             return fail(HIRL_E_INVALID, "n_online + n_expert must equal the batch size");
         if (s.mode < 0 || s.mode > 2) return fail(HIRL_E_INVALID, "bad step mode");
+        if (s.mode != 0 && h->ctxs[0].use_tcc) return fail(HIRL_E_INVALID, "TD3 / BC step modes run on the stage kernel (create the agent with HIRL_TCC=0)");
         if (s.mode != 1 && s.do_actor && h->cfg.bc_rows < h->cfg.batch) return fail(HIRL_E_INVALID, "expert table smaller than the batch (np.random.choice without replacement)");
     }
     return 0;

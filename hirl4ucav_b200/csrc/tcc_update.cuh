@@ -1,0 +1,1129 @@
+// tcc_update.cuh -- the tensor-core cluster kernel: the fused HIRL update (reference hirl/agents/HIRL.py:221-334) for a
+// single agent at batch <= 256, re-cut so that a thread-block CLUSTER of 8 CTAs carries a block of 64 batch rows through
+// whole networks (forward AND backward) with every 256<->512 contraction on tcgen05 (3xTF32), and grid-wide barriers
+// remain only where a weight gradient has to be complete.
+//
+//   phase A  unit (row block r, critic tower t) -> one cluster:
+//              gather rows -> target actor (redundantly in both tower clusters) -> a' -> target critic tower t -> tq_t
+//              -> published to the partner cluster through a flag in global memory
+//              -> critic tower t forward -> TD target y -> loss -> backward: dz2, dH1 (K-split over the cluster, summed
+//              through L2), LayerNorm1 / first-layer backward, dW2 (per row block) -> partial gradients in global memory
+//   ---- grid barrier ----
+//   phase B  critic Adam over the whole grid (fixed-order sums of the partials); refreshes the tensor-core operand
+//            images of the weights it changed
+//   ---- grid barrier ----                                                                  (critic-only calls end here)
+//   phase C  units (r, role): role A : actor(s) -> pi -> Q1(s,pi) [updated critic] -> backward to d pi
+//                             role S : bc_actor(s) -> a_bc -> Q1(s,a_bc) -> soft Q published to role A (flag)
+//                             role AB: actor(s_bc) -> pi_bc -> cloning loss
+//            role A counts soft_Q > rl_Q per row block and publishes the count (flag); once every block's count is there
+//            the Q-filter weight w (HIRL.py:303-308) is known and roles A / AB run their actor backward passes
+//   ---- grid barrier ----
+//   phase D  actor Adam, Polyak every 3rd actor update (HIRL.py:327-330), operand images, returned scalars
+//   ---- grid barrier ----
+//
+// CTA j of a cluster owns the output features 64 j .. 64 j + 63 of the 512-wide layers.  Per pass:
+//   * first layer (K = 13 / 17) + LayerNorm1 + activation in FP32 FMAs (one warp = 8 rows, 4 rows register-blocked),
+//     written hi/lo-split straight into the SWIZZLE_128B K-major operand tile H1[64][256] (128 KB of shared memory);
+//   * second layer: tcgen05.mma M=64 N=64, A = H1 tile, B = this CTA's slice of a pre-split, pre-swizzled image of W2
+//     streamed by cp.async.bulk through a 3-slot ring; accumulators (main + correction) in TMEM;
+//   * LayerNorm2 / head from the accumulator with ONE THREAD PER ROW (tcgen05.ld): the row statistics and the head dot
+//     products are completed across the 8 CTAs by pushing partials into every CTA's shared memory (st.shared::cluster)
+//     and one barrier.cluster -- no shuffles, no global round trip;
+//   * backward: dz2 per thread-row -> K-major tile D;  dH1^T[256][64] = W2T-image . dz2  (M=128 x 2, this CTA's 64
+//     features = its K slice) -> partial through L2 -> row owner sums 8 partials -> LayerNorm1 backward;
+//     dW2^T[256][64] = H1^T . dz2^T with H1^T RECOMPUTED into the same 128 KB while the dH1 MMAs run (tf32 has no
+//     MN-major twin of the K-major SWIZZLE_128B layout, tools/tcc_probe.cu) and dz2^T written into the idle ring.
+// Everything is reduced in a fixed order: results are run-to-run deterministic.  FP32-accurate: rel-L2 <= 1e-5 against
+// torch fp32 per step (tests/test_gpu_update.py, back-end "tcc").
+#pragma once
+#include "tcc_mma.cuh"
+#include "update.cuh"
+
+namespace hirl {
+namespace tcc {
+
+constexpr int CL = 8;              // CTAs per cluster
+constexpr int RB = 64;             // batch rows per row block (= MMA M)
+constexpr int NSL = H2 / CL;       // 64 output features per CTA
+constexpr int TTHREADS = 256;
+constexpr int MAX_NCL = 16;        // clusters per launch
+constexpr int MAX_RB = 4;          // row blocks (batch <= 256)
+constexpr int SLOT_BYTES = 16384, NSLOT = 3;
+// shared-memory carve-up (bytes from a 1024-aligned base)
+constexpr int O_R = 0;                                   // 128 KB  H1 [8 blocks][64 x 128 B] hi | lo   /  H1^T [2 blocks][256 x 128 B] hi | lo  / staging
+constexpr int R_LO = 65536;
+constexpr int O_RING = 131072;                           // 48 KB   weight stream ring  /  dz2^T [2 blocks][64 x 128 B] hi | lo
+constexpr int O_D = O_RING + NSLOT * SLOT_BYTES;         // 32 KB   dz2 [2 blocks][64 x 128 B] hi | lo  /  exchange slots  /  first-layer column sums
+constexpr int O_X = O_D + 32768;                         // 8 KB    gathered rows [64][32]
+constexpr int O_ACT = O_X + 8192;                        // 1 KB    action columns of the critic input [64][4]
+constexpr int O_GPI = O_ACT + 1024;                      // 1 KB    d pi [64][4]
+constexpr int O_PC = O_GPI + 1024;                       // 2 KB    parameter cache of the pass: b2 | g2 | be2 | w3[nout] for this CTA's 64 features
+constexpr int O_RED = O_PC + 2048;                       // 1 KB    small reductions
+constexpr int SMEM_USED = O_RED + 1024;
+constexpr size_t SMEM_BYTES = SMEM_USED + 1024;          // + alignment slack
+static_assert(SMEM_BYTES + 2048 <= 232448, "shared memory budget (227 KB per CTA incl. static)");
+// TMEM columns
+constexpr int T_MAIN = 0, T_CORR = 64, T_DH = 128, T_DW = 256;
+
+// image geometry (floats)
+constexpr size_t IMG_FWD = (size_t)H2 * H1 * 2;          // per tower: [8 slices][8 k-blocks][hi 2048 | lo 2048]... 4096 floats per (slice, block)
+constexpr size_t IMG_T = (size_t)H2 * H1 * 2;            // per tower: [8 slices][2 m-blocks][2 k-chunks][hi 4096 | lo 4096]
+__host__ __device__ __forceinline__ uint32_t sw128_words(int row, int kk) {
+    return (uint32_t)((row >> 3) * 256 + (row & 7) * 32 + ((((kk >> 2) ^ (row & 7)) << 2) | (kk & 3)));
+}
+__host__ __device__ __forceinline__ size_t img_fwd_index(int n, int k) {     // W2[n][k] -> hi word (lo at + 2048)
+    return ((size_t)(n >> 6) * 8 + (k >> 5)) * 4096 + sw128_words(n & 63, k & 31);
+}
+__host__ __device__ __forceinline__ size_t img_t_index(int n, int k) {       // W2[n][k] -> hi word (lo at + 4096)
+    return ((((size_t)(n >> 6) * 2 + (k >> 7)) * 2 + ((n & 63) >> 5)) * 2) * 4096 + sw128_words(k & 127, n & 31);
+}
+
+// p2p flag words (each on its own 128-byte line)
+enum { PF_TQ = 0 /* [r][t] */, PF_SOFTQ = 8 /* [r] */, PF_CNT = 12 /* [r] */, PF_WORDS = 16 };
+constexpr int PROF_WORDS = 96;
+
+struct TccLaunch {
+    AgentCtx agent;
+    unsigned *bar_flags;   // [MAX_NCL][32] cluster flags of the grid barrier
+    int k_steps, ncl;
+    long long *prof;       // [PROF_STEPS][PROF_WORDS] SM-clock stamps of cluster 0 / CTA 0 (may be null)
+};
+
+struct Ctl {
+    char *sm;
+    uint64_t *full, *empty, *acc;
+    uint32_t tm;
+    int crank, cid, ncl, warp, lane, sub, wh, row;   // row: batch row of this thread inside the block (thread-per-row epilogues)
+    bool act;                                         // lane < 16: this thread owns (row, 32 columns)
+    unsigned ring_n, acc_n[2], xr, gen, pgen;
+    unsigned *flags, *pflags;
+    long long *pr;
+    int pb;   // base index of the fine-grained stamps of the current pass (0: off)
+};
+__device__ __forceinline__ void stamp(const Ctl &k, int id) { if (k.pr && threadIdx.x == 0) k.pr[id] = clock64(); }
+__device__ __forceinline__ void pstamp(const Ctl &k, int i) { if (k.pr && k.pb && threadIdx.x == 0) k.pr[k.pb + i] = clock64(); }
+
+// ---- synchronisation -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_sync(Ctl &k) {
+    cluster_sync();
+    k.gen += 1u;
+    if (k.crank == 0 && threadIdx.x < 32) {
+        if (threadIdx.x == 0) st_release_u32(k.flags + k.cid * FLAG_STRIDE, k.gen);
+        bool pending = true;
+        const long long t0 = clock64();
+        while (pending) {
+            pending = (int)threadIdx.x < k.ncl && (int)(ld_relaxed_u32(k.flags + threadIdx.x * FLAG_STRIDE) - k.gen) < 0;
+            pending = __any_sync(0xffffffffu, pending);
+            if (pending && clock64() - t0 > 8000000000LL) {
+                if (threadIdx.x == 0) printf("hirl tcc kernel: grid barrier timed out (cluster %d gen %u)\n", k.cid, k.gen);
+                __trap();
+            }
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    cluster_sync();
+}
+// producer side of a point-to-point flag: the CTA's global writes, then one release store
+__device__ __forceinline__ void flag_publish(Ctl &k, int word, unsigned value) {
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_u32(k.pflags + word * FLAG_STRIDE, value);
+}
+__device__ __forceinline__ void flag_wait(Ctl &k, int word, unsigned value) {
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_u32(k.pflags + word * FLAG_STRIDE) - value) < 0) {
+            if (clock64() - t0 > 8000000000LL) {
+                printf("hirl tcc kernel: flag %d timed out (cluster %d cta %d want %u)\n", word, k.cid, k.crank, value);
+                __trap();
+            }
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+// ---- cluster-wide per-row exchange: every (CTA, column half) contributes one float4 per row; afterwards every thread
+//      reads the 16 contributions of its row from its own shared memory (slots alias the dz2 tile, double-buffered) --------
+__device__ __forceinline__ float4 *xslot(const Ctl &k, int buf, int src, int row) {
+    return reinterpret_cast<float4 *>(k.sm + O_D + buf * 16384 + (src * RB + row) * 16);
+}
+__device__ __forceinline__ void exchange_push(Ctl &k, float a, float b, float c, float d) {
+    const int buf = k.xr & 1;
+    if (k.act) {
+        const uint32_t local = smem_u32(xslot(k, buf, 2 * k.crank + k.wh, k.row));
+#pragma unroll
+        for (int dst = 0; dst < CL; ++dst) st_dsmem_f32x4(map_to_cta(local, dst), a, b, c, d);
+    }
+    cluster_sync();
+    k.xr += 1u;
+}
+__device__ __forceinline__ float4 exchange_get(const Ctl &k, int src) {   // after exchange_push: contribution `src` (0..15) of this thread's row
+    return *xslot(k, (k.xr - 1u) & 1, src, k.row);
+}
+
+// ---- weight stream ------------------------------------------------------------------------------------------------
+// units of 16 KB, contiguous in global memory.  Called by ALL threads (uniform arguments); thread 32 issues the copies.
+// `blocking == false` issues only units whose ring slot is known to be free already (the first NSLOT after an idle ring).
+__device__ __forceinline__ void stream_units(Ctl &k, const float *src, int first, int count) {
+    if (threadIdx.x == 32) {
+        for (int u = first; u < first + count; ++u) {
+            const unsigned n = k.ring_n + (unsigned)u;
+            const int s = (int)(n % NSLOT);
+            if (n >= NSLOT) tc::mbar_wait(k.empty + s, ((n / NSLOT) - 1u) & 1u, 500 + u);
+            mbar_expect_tx(k.full + s, SLOT_BYTES);
+            bulk_g2s(k.sm + O_RING + s * SLOT_BYTES, reinterpret_cast<const char *>(src) + (size_t)u * SLOT_BYTES, SLOT_BYTES, k.full + s);
+        }
+    }
+}
+__device__ __forceinline__ void ring_wait_full(Ctl &k, unsigned n) {   // consumer thread
+    tc::mbar_wait(k.full + (n % NSLOT), (n / NSLOT) & 1u, 600);
+    tc::tc_fence_after();
+}
+__device__ __forceinline__ void acc_wait(Ctl &k, int which) {          // all threads
+    tc::mbar_wait(k.acc + which, k.acc_n[which] & 1u, 700 + which);
+    k.acc_n[which] += 1u;
+    tc::tc_fence_after();
+}
+// operands written with ordinary stores become visible to the tensor core (async proxy); then a CTA barrier
+__device__ __forceinline__ void publish_operands() {
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+}
+
+// ---- first layer + LayerNorm1 + activation into an operand tile ------------------------------------------------------
+// x_k of row b:  k < 13: xs[b][soff + k];  k >= 13 (critic): acts[b][k - 13]  (acts == nullptr: xs[b][k], the stored action)
+// TR == false: H1[b][n]  (forward A operand, 8 blocks of [64 rows][32]);  TR == true: H1^T[n][b] (2 blocks of [256 rows][32])
+template <class L, bool TR>
+__device__ __noinline__ void l1_tile(char *sm, const float *tw, int soff, const float *acts, float slope) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float *xs = reinterpret_cast<const float *>(sm + O_X);
+    float b1[8], g1[8], be1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        b1[j] = tw[L::B1 + lane + 32 * j];
+        g1[j] = tw[L::G1 + lane + 32 * j];
+        be1[j] = tw[L::BE1 + lane + 32 * j];
+    }
+    for (int grp = 0; grp < 2; ++grp) {
+        float z[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) z[i][j] = b1[j];
+#pragma unroll
+        for (int kk = 0; kk < L::k0; ++kk) {
+            float w[8], xv[4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = tw[L::W1T + kk * H1 + lane + 32 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int b = warp + 8 * (4 * grp + i);
+                xv[i] = kk < S ? xs[b * 32 + soff + kk] : (acts ? acts[b * 4 + (kk - S)] : xs[b * 32 + kk]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) z[i][j] = fmaf(xv[i], w[j], z[i][j]);
+        }
+        float s[4], v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[i] += z[i][j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s[i] *= (1.f / H1);
+            v[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = z[i][j] - s[i];
+                v[i] = fmaf(d, d, v[i]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int b = warp + 8 * (4 * grp + i);
+            const float rstd = 1.f / sqrtf(v[i] * (1.f / H1) + LN_EPS);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (z[i][j] - s[i]) * rstd;
+                const float hv = act_f(fmaf(xh, g1[j], be1[j]), slope);
+                const float hi = tf32_hi(hv);
+                uint32_t off;
+                if (!TR) off = (uint32_t)j * 8192u + sw128_off(b, lane);
+                else off = (uint32_t)(b >> 5) * 32768u + sw128_off(lane + 32 * j, b & 31);
+                *reinterpret_cast<float *>(sm + O_R + off) = hi;
+                *reinterpret_cast<float *>(sm + O_R + R_LO + off) = hv - hi;
+            }
+        }
+    }
+}
+
+// parameter cache of a pass: b2 | g2 | be2 | w3[o] restricted to this CTA's 64 features
+template <class L>
+__device__ __forceinline__ void load_pc(const Ctl &k, const float *tw) {
+    float *pc = reinterpret_cast<float *>(k.sm + O_PC);
+    for (int i = threadIdx.x; i < (3 + L::nout) * NSL; i += TTHREADS) {
+        const int a = i >> 6, c = i & 63;
+        const int off = a == 0 ? L::B2 : a == 1 ? L::G2 : a == 2 ? L::BE2 : L::W3 + (a - 3) * H2;
+        pc[i] = tw[off + NSL * k.crank + c];
+    }
+}
+
+// ---- forward pass: first layer, second layer on the tensor cores, LayerNorm2 + head per thread-row --------------------
+// out[o]: the head output of this thread's row (identical in every CTA); xh / rstd: this thread's 32 normalised columns.
+template <class L>
+__device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const float *img, int soff, const float *acts, float slope,
+                                             float (&xh)[32], float &rstd, float (&out)[L::nout]) {
+    char *sm = k.sm;
+    const float *unit0 = img + (size_t)k.crank * 8 * 4096;            // this CTA's slice: 8 k-blocks of hi | lo
+    stream_units(k, unit0, 0, NSLOT);                                  // lands while the first layer runs
+    load_pc<L>(k, tw);
+    pstamp(k, 0);
+    l1_tile<L, false>(sm, tw, soff, acts, slope);
+    pstamp(k, 1);
+    publish_operands();
+    stream_units(k, unit0, NSLOT, 8 - NSLOT);
+    if (threadIdx.x == 0) {
+        tc::tc_fence_after();
+        const uint32_t id = idesc(RB, NSL, 0, 0), r = smem_u32(sm + O_R), ring = smem_u32(sm + O_RING);
+        for (int c = 0; c < 8; ++c) {
+            const unsigned n = k.ring_n + (unsigned)c;
+            ring_wait_full(k, n);
+            const uint32_t slot = ring + (n % NSLOT) * SLOT_BYTES;
+            mma3(k.tm + T_MAIN, k.tm + T_CORR, desc_k(r + c * 8192), desc_k(r + R_LO + c * 8192), desc_k(slot), desc_k(slot + 8192), 4, 2, 2, id, c == 0);
+            tc::mma_commit(k.empty + (n % NSLOT));
+        }
+        tc::mma_commit(k.acc + 0);
+    }
+    __syncwarp();
+    k.ring_n += 8u;
+    pstamp(k, 2);
+    acc_wait(k, 0);
+    pstamp(k, 3);
+    const float *pc = reinterpret_cast<const float *>(sm + O_PC) + 32 * k.wh;
+    const uint32_t lane_addr = k.tm + ((uint32_t)(k.sub * 32) << 16) + 32 * k.wh;
+    float z[32];
+    {
+        float c[32];
+        tmem_ld32(lane_addr + T_MAIN, z);
+        tmem_ld32(lane_addr + T_CORR, c);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) z[e] = (z[e] + c[e]) + pc[e];
+    }
+    tc::tc_fence_before();
+    // LayerNorm2 statistics: local (mean, M2) over 32 columns, combined over the 16 contributions of the row (Chan)
+    float m = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) m += z[e];
+    m *= (1.f / 32.f);
+    float q = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        const float d = z[e] - m;
+        q = fmaf(d, d, q);
+    }
+    pstamp(k, 4);
+    exchange_push(k, m, q, 0.f, 0.f);
+    pstamp(k, 5);
+    float mean = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int s = 0; s < 2 * CL; ++s) mean += exchange_get(k, s).x;
+    mean *= (1.f / (2 * CL));
+#pragma unroll
+    for (int s = 0; s < 2 * CL; ++s) {
+        const float4 p = exchange_get(k, s);
+        const float d = p.x - mean;
+        m2 += fmaf(32.f * d, d, p.y);
+    }
+    rstd = 1.f / sqrtf(m2 * (1.f / H2) + LN_EPS);
+    float p[L::nout];
+#pragma unroll
+    for (int o = 0; o < L::nout; ++o) p[o] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        xh[e] = (z[e] - mean) * rstd;
+        const float h = act_f(fmaf(xh[e], pc[64 + e], pc[128 + e]), slope);
+#pragma unroll
+        for (int o = 0; o < L::nout; ++o) p[o] = fmaf(h, pc[192 + 64 * o + e], p[o]);
+    }
+    exchange_push(k, p[0], L::nout > 1 ? p[1 % L::nout] : 0.f, L::nout > 2 ? p[2 % L::nout] : 0.f, L::nout > 3 ? p[3 % L::nout] : 0.f);
+#pragma unroll
+    for (int o = 0; o < L::nout; ++o) out[o] = 0.f;
+#pragma unroll
+    for (int s = 0; s < 2 * CL; ++s) {
+        const float4 t = exchange_get(k, s);
+        out[0] += t.x;
+        if (L::nout > 1) { out[1 % L::nout] += t.y; out[2 % L::nout] += t.z; out[3 % L::nout] += t.w; }
+    }
+#pragma unroll
+    for (int o = 0; o < L::nout; ++o) out[o] += tw[L::B3 + o];
+    pstamp(k, 6);
+}
+
+// ---- backward through head + LayerNorm2 of this thread's 32 columns --------------------------------------------------
+// in: xh, rstd, dout[nout].  out: dz (grad of the pre-LayerNorm row), dy (grad at the LayerNorm output), h (activations)
+template <class L>
+__device__ __forceinline__ void head_ln2_backward(Ctl &k, const float (&xh)[32], float rstd, const float (&dout)[L::nout], float slope,
+                                                  float (&dz)[32], float (&dy)[32], float (&h)[32]) {
+    const float *pc = reinterpret_cast<const float *>(k.sm + O_PC) + 32 * k.wh;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        const float pre = fmaf(xh[e], pc[64 + e], pc[128 + e]);
+        h[e] = act_f(pre, slope);
+        float g = 0.f;
+#pragma unroll
+        for (int o = 0; o < L::nout; ++o) g = fmaf(dout[o], pc[192 + 64 * o + e], g);
+        dy[e] = g * act_g(pre, slope);
+        dz[e] = dy[e] * pc[64 + e];
+        s1 += dz[e];
+        s2 = fmaf(dz[e], xh[e], s2);
+    }
+    exchange_push(k, s1, s2, 0.f, 0.f);
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int s = 0; s < 2 * CL; ++s) {
+        const float4 p = exchange_get(k, s);
+        t1 += p.x;
+        t2 += p.y;
+    }
+    t1 *= (1.f / H2);
+    t2 *= (1.f / H2);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) dz[e] = rstd * (dz[e] - t1 - xh[e] * t2);
+}
+
+// column sums over the 64 rows of the block of up to 7 per-thread arrays (second-layer small parameters), staged through
+// the (dead) H1 region.  val(a, e): value of array a at this thread's column e.  Result a, column c -> dst[a * dst_stride + c].
+constexpr int CS_LD = 68;
+template <int NA, class F>
+__device__ __forceinline__ void column_sums(Ctl &k, F val, float *dst, int dst_stride) {
+    float *st = reinterpret_cast<float *>(k.sm + O_R);
+    if (k.act) {
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            float *row = st + (a * RB + k.row) * CS_LD + 32 * k.wh;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) st4(row + e, make_float4(val(a, e), val(a, e + 1), val(a, e + 2), val(a, e + 3)));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NA * NSL; i += TTHREADS) {
+        const int a = i >> 6, c = i & 63;
+        const float *col = st + a * RB * CS_LD + c;
+        float s = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < RB; ++r) s += col[r * CS_LD];
+        dst[a * dst_stride + c] = s;
+    }
+    __syncthreads();
+}
+
+// ---- backward GEMMs of one pass ---------------------------------------------------------------------------------------
+// dz: this thread's 32 columns of dz2.  Produces (a) the LayerNorm1-backward result of the CTA's own 8 rows (dz1 / dy1 rows
+// in the D region, see ln1_rows) and, if WITH_DW, (b) this row block's dW2 partial of the CTA's 64 features.
+struct BwdOut { float dz1[8], dy1[8], xh1[8]; int b; };   // own row (warp w <-> row 8 crank + w), lane owns n = lane + 32 j
+template <class L, bool WITH_DW>
+__device__ __forceinline__ void pass_backward(Ctl &k, const float *tw, const float *imgt, int soff, const float *acts, float slope,
+                                              const float (&dz)[32], float *dh1p_unit, float *gw2p_slot, BwdOut &o) {
+    char *sm = k.sm;
+    const float *units = imgt + (size_t)k.crank * 8 * 4096;          // 8 sub-units: (mb, cc, hi | lo)
+    stream_units(k, units, 0, NSLOT);
+    // (1) dz2 tile, K-major: block wh, row = batch row
+    if (k.act) {
+        char *dh = sm + O_D + k.wh * 8192 + (k.row >> 3) * 1024 + (k.row & 7) * 128;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+            float4 hi, lo;
+            hi.x = tf32_hi(dz[4 * c4]); hi.y = tf32_hi(dz[4 * c4 + 1]); hi.z = tf32_hi(dz[4 * c4 + 2]); hi.w = tf32_hi(dz[4 * c4 + 3]);
+            lo.x = dz[4 * c4] - hi.x; lo.y = dz[4 * c4 + 1] - hi.y; lo.z = dz[4 * c4 + 2] - hi.z; lo.w = dz[4 * c4 + 3] - hi.w;
+            const int off = (c4 ^ (k.row & 7)) << 4;
+            *reinterpret_cast<float4 *>(dh + off) = hi;
+            *reinterpret_cast<float4 *>(dh + 16384 + off) = lo;
+        }
+    }
+    pstamp(k, 0);
+    publish_operands();
+    stream_units(k, units, NSLOT, 8 - NSLOT);
+    // (2) dH1^T[256][64] = W2T-image[256][64 features] . dz2[64 rows][64 features]^T : M = 128 x 2, N = 64, K = 64
+    if (threadIdx.x == 0) {
+        tc::tc_fence_after();
+        const uint32_t id = idesc(128, RB, 0, 0), d = smem_u32(sm + O_D), ring = smem_u32(sm + O_RING);
+        for (int mb = 0; mb < 2; ++mb)
+            for (int cc = 0; cc < 2; ++cc) {
+                const uint32_t acc = k.tm + T_DH + 64 * mb;
+                const uint64_t bhi = desc_k(d + cc * 8192), blo = desc_k(d + 16384 + cc * 8192);
+                unsigned n = k.ring_n + (unsigned)((mb * 2 + cc) * 2);
+                ring_wait_full(k, n);
+                uint64_t a = desc_k(ring + (n % NSLOT) * SLOT_BYTES);
+                for (int s = 0; s < 4; ++s) {
+                    mma_ss(acc, a + 2 * s, bhi + 2 * s, id, (cc == 0 && s == 0) ? 0u : 1u);
+                    mma_ss(acc, a + 2 * s, blo + 2 * s, id, 1u);
+                }
+                tc::mma_commit(k.empty + (n % NSLOT));
+                n += 1u;
+                ring_wait_full(k, n);
+                a = desc_k(ring + (n % NSLOT) * SLOT_BYTES);
+                for (int s = 0; s < 4; ++s) mma_ss(acc, a + 2 * s, bhi + 2 * s, id, 1u);
+                tc::mma_commit(k.empty + (n % NSLOT));
+            }
+        tc::mma_commit(k.acc + 0);
+    }
+    __syncwarp();
+    k.ring_n += 8u;
+    pstamp(k, 1);
+    if (WITH_DW) {
+        // (3) H1^T recomputed into the H1 region while the dH1 MMAs run
+        l1_tile<L, true>(sm, tw, soff, acts, slope);
+    }
+    pstamp(k, 2);
+    acc_wait(k, 0);                                                   // dH1^T complete: the ring and the dz2 tile are idle
+    if (WITH_DW) {
+        // (4) dz2^T tile [64 features][64 rows] into the ring region (K = batch row), re-read from the K-major tile (hi + lo is exact)
+        if (k.act) {
+            const char *dh = sm + O_D + k.wh * 8192 + (k.row >> 3) * 1024 + (k.row & 7) * 128;
+            char *e0 = sm + O_RING + (k.row >> 5) * 8192;
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const int off = (c4 ^ (k.row & 7)) << 4;
+                const float4 hi = *reinterpret_cast<const float4 *>(dh + off), lo = *reinterpret_cast<const float4 *>(dh + 16384 + off);
+                const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t w = sw128_off(32 * k.wh + 4 * c4 + q, k.row & 31);
+                    *reinterpret_cast<float *>(e0 + w) = hv[q];
+                    *reinterpret_cast<float *>(e0 + 16384 + w) = lv[q];
+                }
+            }
+        }
+        publish_operands();
+        // (5) dW2^T[256][64] = H1^T[256][64 rows] . dz2^T[64 features][64 rows]^T : M = 128 x 2, N = 64, K = 64
+        if (threadIdx.x == 0) {
+            tc::tc_fence_after();
+            const uint32_t id = idesc(128, NSL, 0, 0), r = smem_u32(sm + O_R), e = smem_u32(sm + O_RING);
+            for (int mb = 0; mb < 2; ++mb) {
+                const uint32_t acc = k.tm + T_DW + 64 * mb;
+                for (int bb = 0; bb < 2; ++bb) {
+                    const uint64_t ahi = desc_k(r + bb * 32768 + mb * 16384), alo = desc_k(r + R_LO + bb * 32768 + mb * 16384);
+                    const uint64_t bhi = desc_k(e + bb * 8192), blo = desc_k(e + 16384 + bb * 8192);
+                    for (int s = 0; s < 4; ++s) {
+                        mma_ss(acc, ahi + 2 * s, bhi + 2 * s, id, (bb == 0 && s == 0) ? 0u : 1u);
+                        mma_ss(acc, alo + 2 * s, bhi + 2 * s, id, 1u);
+                        mma_ss(acc, ahi + 2 * s, blo + 2 * s, id, 1u);
+                    }
+                }
+            }
+            tc::mma_commit(k.acc + 1);
+        }
+        __syncwarp();
+    }
+    pstamp(k, 3);
+    // (6) dH1^T partial -> global [64 rows][256], coalesced along the 256 (lane = feature of H1)
+    {
+        const uint32_t lane_addr = k.tm + ((uint32_t)(k.sub * 32) << 16) + 32 * k.wh;
+        float *dst = dh1p_unit + (size_t)k.crank * RB * H1;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+            float v[32];
+            tmem_ld32(lane_addr + T_DH + 64 * mb, v);
+            const int n = 128 * mb + 32 * k.sub + k.lane;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[(size_t)(32 * k.wh + i) * H1 + n] = v[i];
+        }
+        tc::tc_fence_before();
+    }
+    pstamp(k, 4);
+    cluster_sync();                                                   // every CTA's partial is visible (cluster-scope release / acquire)
+    pstamp(k, 5);
+    // (7) the CTA's own 8 rows: sum the 8 partials in a fixed order, LayerNorm1 backward (first layer recomputed for the row)
+    {
+        const int b = 8 * k.crank + k.warp, lane = k.lane;
+        o.b = b;
+        float dh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dh[j] = 0.f;
+        for (int src = 0; src < CL; ++src) {
+            const float *p = dh1p_unit + ((size_t)src * RB + b) * H1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dh[j] += __ldcg(p + lane + 32 * j);
+        }
+        const float *xs = reinterpret_cast<const float *>(sm + O_X);
+        float z[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = tw[L::B1 + lane + 32 * j];
+#pragma unroll
+        for (int kk = 0; kk < L::k0; ++kk) {
+            const float xv = kk < S ? xs[b * 32 + soff + kk] : (acts ? acts[b * 4 + (kk - S)] : xs[b * 32 + kk]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) z[j] = fmaf(xv, tw[L::W1T + kk * H1 + lane + 32 * j], z[j]);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += z[j];
+        const float mean = warp_sum(s) * (1.f / H1);
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = z[j] - mean;
+            v = fmaf(d, d, v);
+        }
+        const float rstd = 1.f / sqrtf(warp_sum(v) * (1.f / H1) + LN_EPS);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.xh1[j] = (z[j] - mean) * rstd;
+        ln1_backward<L>(tw, dh, o.xh1, rstd, slope, lane, o.dz1, o.dy1);
+    }
+    pstamp(k, 6);
+    if (WITH_DW) {
+        // (8) dW2^T partial of this row block -> global [512][256] slot, rows 64 crank .. + 63
+        acc_wait(k, 1);
+        const uint32_t lane_addr = k.tm + ((uint32_t)(k.sub * 32) << 16) + 32 * k.wh;
+        float *dst = gw2p_slot + (size_t)NSL * k.crank * H1;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+            float v[32];
+            tmem_ld32(lane_addr + T_DW + 64 * mb, v);
+            const int kcol = 128 * mb + 32 * k.sub + k.lane;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[(size_t)(32 * k.wh + i) * H1 + kcol] = v[i];
+        }
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    pstamp(k, 7);
+}
+
+// first-layer parameter gradients of the CTA's 8 rows (one per warp) -> partial slot (L layout, first-layer section)
+template <class L>
+__device__ __forceinline__ void ln1_param_partials(Ctl &k, const BwdOut &o, int soff, const float *acts, float *part) {
+    float *t_dz = reinterpret_cast<float *>(k.sm + O_D), *t_dg = t_dz + 8 * H1, *t_dbe = t_dg + 8 * H1, *t_x = t_dbe + 8 * H1;   // [8][256] x 3 + [8][32]
+    const float *xs = reinterpret_cast<const float *>(k.sm + O_X);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int n = k.lane + 32 * j;
+        t_dz[k.warp * H1 + n] = o.dz1[j];
+        t_dg[k.warp * H1 + n] = o.dy1[j] * o.xh1[j];
+        t_dbe[k.warp * H1 + n] = o.dy1[j];
+    }
+    if (k.lane < L::k0) t_x[k.warp * 32 + k.lane] = k.lane < S ? xs[o.b * 32 + soff + k.lane] : (acts ? acts[o.b * 4 + (k.lane - S)] : xs[o.b * 32 + k.lane]);
+    __syncthreads();
+    {
+        const int n = threadIdx.x;   // 256 threads = 256 columns
+        float db1 = 0.f, dg1 = 0.f, dbe1 = 0.f, dw[L::k0];
+#pragma unroll
+        for (int kk = 0; kk < L::k0; ++kk) dw[kk] = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const float dzv = t_dz[w * H1 + n];
+            db1 += dzv;
+            dg1 += t_dg[w * H1 + n];
+            dbe1 += t_dbe[w * H1 + n];
+#pragma unroll
+            for (int kk = 0; kk < L::k0; ++kk) dw[kk] = fmaf(dzv, t_x[w * 32 + kk], dw[kk]);
+        }
+        part[L::B1 + n] = db1;
+        part[L::G1 + n] = dg1;
+        part[L::BE1 + n] = dbe1;
+#pragma unroll
+        for (int kk = 0; kk < L::k0; ++kk) part[L::W1T + kk * H1 + n] = dw[kk];
+    }
+    __syncthreads();
+}
+
+// ---- gather ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gather_rows(Ctl &k, const AgentCtx &c, const hirl_step_t &st, int step, int r, bool bc_rows) {
+    float *xs = reinterpret_cast<float *>(k.sm + O_X);
+    const int32_t *ion = c.idx_online + (size_t)step * c.B, *iex = c.idx_expert + (size_t)step * c.B, *ibc = c.idx_bc + (size_t)step * c.B;
+    for (int i = k.warp; i < RB; i += 8) {
+        int b = RB * r + i;
+        if (b >= c.B) b = c.B - 1;                                   // padded rows repeat the last row; their contributions are masked
+        float w;
+        if (bc_rows) {
+            const float *src = c.bctab + (size_t)__ldg(ibc + b) * BCW;
+            w = k.lane < BCW ? __ldg(src + k.lane) : 0.f;
+        } else {
+            const float *src = b < st.n_online ? c.online + (size_t)__ldg(ion + b) * ROW : c.expert + (size_t)__ldg(iex + (b - st.n_online)) * ROW;
+            w = __ldg(src + k.lane);
+        }
+        xs[i * 32 + k.lane] = w;
+    }
+    __syncthreads();
+}
+
+// sum over the 64 rows of a per-row value held by the (wh == 0) row threads, in row order; result valid in thread 0
+__device__ __forceinline__ float row_sum(Ctl &k, float v, int slot) {
+    float *red = reinterpret_cast<float *>(k.sm + O_RED) + 64 * slot;
+    if (k.act && k.wh == 0) red[k.row] = v;
+    __syncthreads();
+    float s = 0.f;
+    if (threadIdx.x == 0)
+        for (int r = 0; r < RB; ++r) s += red[r];
+    __syncthreads();
+    return s;
+}
+
+// ---- Adam over one network (all CTAs of the grid), fixed-order sums of the partials, operand images ------------------
+//   w2parts [tower][nparts][H2*H1]; part: slots of L::SMALL floats, slot s of tower t at ((s * ntowers) + t) * L::SMALL;
+//   first-layer entries are summed over slots 0 .. n1-1, second-layer small entries over slots 0, 8, 16, .. (nq of them)
+template <class L>
+__device__ __forceinline__ void adam_tcc(int rank, int size, int ntowers, float *w, float *gw, const float *w2parts, int nparts, float *m, float *v,
+                                         const float *part, int n1, int nq, float neg_step, float bc2_sqrt, float *img, float *imgt,
+                                         float *target, float *timg, bool polyak, float tau, float omt) {
+    const int total = ntowers * L::SIZE;
+    for (int e = rank * TTHREADS + threadIdx.x; e < total; e += size * TTHREADS) {
+        const int tower = e / L::SIZE, off = e - tower * L::SIZE;
+        const bool in_w2 = off >= L::W2 && off < L::B2;
+        float g;
+        if (in_w2) {
+            const float *p0 = w2parts + (size_t)tower * nparts * H2 * H1 + (off - L::W2);
+            g = __ldcg(p0);
+            for (int q = 1; q < nparts; ++q) g += __ldcg(p0 + (size_t)q * H2 * H1);
+        } else {
+            const int si = L::small_index(off);
+            const bool first = off < L::W2;
+            const int ns = first ? n1 : nq, stride = first ? 1 : CL;
+            g = 0.f;
+            for (int s = 0; s < ns; ++s) g += __ldcg(part + ((size_t)(s * stride) * ntowers + tower) * L::SMALL + si);
+        }
+        gw[e] = g;
+        float wv = w[e], mv = m[e], vv = v[e];
+        adam_elem(g, wv, mv, vv, neg_step, bc2_sqrt);
+        w[e] = wv; m[e] = mv; v[e] = vv;
+        float tv = 0.f;
+        if (polyak) { tv = polyak_elem(target[e], wv, tau, omt); target[e] = tv; }
+        if (in_w2) {
+            const int i = off - L::W2, n = i / H1, kk = i - n * H1;
+            const float hi = tf32_hi(wv);
+            float *f = img + (size_t)tower * IMG_FWD + img_fwd_index(n, kk);
+            f[0] = hi; f[2048] = wv - hi;
+            if (imgt) {
+                float *t = imgt + (size_t)tower * IMG_T + img_t_index(n, kk);
+                t[0] = hi; t[4096] = wv - hi;
+            }
+            if (polyak) {
+                const float th = tf32_hi(tv);
+                float *f2 = timg + (size_t)tower * IMG_FWD + img_fwd_index(n, kk);
+                f2[0] = th; f2[2048] = tv - th;
+            }
+        }
+    }
+}
+// Polyak of a network whose online copy did not change in this phase (the critic, in phase D)
+template <class L>
+__device__ __forceinline__ void polyak_tcc(int rank, int size, int ntowers, const float *w, float *target, float *timg, float tau, float omt) {
+    const int total = ntowers * L::SIZE;
+    for (int e = rank * TTHREADS + threadIdx.x; e < total; e += size * TTHREADS) {
+        const int tower = e / L::SIZE, off = e - tower * L::SIZE;
+        const float tv = polyak_elem(target[e], w[e], tau, omt);
+        target[e] = tv;
+        if (off >= L::W2 && off < L::B2) {
+            const int i = off - L::W2, n = i / H1, kk = i - n * H1;
+            const float th = tf32_hi(tv);
+            float *f2 = timg + (size_t)tower * IMG_FWD + img_fwd_index(n, kk);
+            f2[0] = th; f2[2048] = tv - th;
+        }
+    }
+}
+
+// rebuilds the operand images of one tower from its arena (after hirl_params_import)
+__global__ void tcc_images_kernel(const float *w2, float *img, float *imgt) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H2 * H1; i += gridDim.x * blockDim.x) {
+        const int n = i / H1, kk = i - n * H1;
+        const float wv = w2[i], hi = tf32_hi(wv);
+        float *f = img + img_fwd_index(n, kk);
+        f[0] = hi; f[2048] = wv - hi;
+        if (imgt) {
+            float *t = imgt + img_t_index(n, kk);
+            t[0] = hi; t[4096] = wv - hi;
+        }
+    }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_tcc_kernel(const __grid_constant__ TccLaunch Lc) {
+    extern __shared__ float4 smem4[];
+    __shared__ AgentCtx ctx;
+    __shared__ hirl_step_t st;
+    __shared__ uint64_t bars[2 * NSLOT + 2];
+    __shared__ uint32_t tmem_slot;
+    {
+        const int *src = reinterpret_cast<const int *>(&Lc.agent);
+        int *dst = reinterpret_cast<int *>(&ctx);
+        for (int i = threadIdx.x; i < (int)(sizeof(AgentCtx) / sizeof(int)); i += TTHREADS) dst[i] = src[i];
+    }
+    Ctl k;
+    k.sm = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem4) + 1023) & ~(uintptr_t)1023);
+    k.full = bars; k.empty = bars + NSLOT; k.acc = bars + 2 * NSLOT;
+    k.crank = (int)cluster_ctarank(); k.cid = (int)cluster_id_x(); k.ncl = Lc.ncl;
+    k.warp = threadIdx.x >> 5; k.lane = threadIdx.x & 31; k.sub = k.warp & 3; k.wh = k.warp >> 2;
+    k.act = k.lane < 16; k.row = 16 * k.sub + (k.lane & 15);
+    k.ring_n = 0u; k.acc_n[0] = k.acc_n[1] = 0u; k.xr = 0u;
+    k.flags = Lc.bar_flags;
+    k.gen = ld_relaxed_u32(k.flags + k.cid * FLAG_STRIDE);
+    k.pr = nullptr; k.pb = 0;
+    if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot);
+    if (threadIdx.x == 32) {
+        for (int i = 0; i < 2 * NSLOT + 2; ++i) tc::mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    k.tm = tmem_slot;
+    const AgentCtx &c = ctx;
+    k.pflags = c.tcc.pflags;
+    k.pgen = ld_relaxed_u32(c.tcc.gen_ctr);
+    cluster_sync();                                                    // peers' shared memory is live before anybody pushes into it
+    const float slope = slope_of(c);
+    const int B = c.B, nrb = (B + RB - 1) / RB;
+    float *acts = reinterpret_cast<float *>(k.sm + O_ACT), *gpi = reinterpret_cast<float *>(k.sm + O_GPI);
+    const int grank = k.cid * CL + k.crank, gsize = k.ncl * CL;
+    const float tau = c.tau, omt = (float)(1.0 - (double)c.tau);
+
+    for (int step = 0; step < Lc.k_steps; ++step) {
+        __syncthreads();
+        if (threadIdx.x < (int)(sizeof(hirl_step_t) / sizeof(int)))
+            reinterpret_cast<int *>(&st)[threadIdx.x] = reinterpret_cast<const int *>(c.steps + step)[threadIdx.x];
+        __syncthreads();
+        const bool do_actor = st.do_actor != 0, soft = st.bc_weight_now == 100.f, do_polyak = st.do_polyak != 0;
+        const unsigned fgen = k.pgen + (unsigned)step + 1u;
+        k.pr = (Lc.prof && step < PROF_STEPS && k.cid == 0 && k.crank == 0) ? Lc.prof + (size_t)step * PROF_WORDS : nullptr;
+        stamp(k, 0);
+        // =============================== phase A: critic forward / backward ===============================
+        if (k.cid < 2 * nrb) {
+            const int r = k.cid >> 1, t = k.cid & 1, unit = k.cid;
+            const int bg = RB * r + k.row;                             // global batch row of this thread
+            const bool valid = bg < B;
+            gather_rows(k, c, st, step, r, false);
+            stamp(k, 1);
+            float xh[32], rstd;
+            // target actor on next_state (HIRL.py:264) -> a' (HIRL.py:265-267)
+            {
+                float out[A];
+                k.pb = 20;
+                pass_forward<ActorL>(k, c.tactor, c.tcc.img_tactor, SA, nullptr, slope, xh, rstd, out);
+                k.pb = 0;
+                if (k.act && k.wh == 0) {
+#pragma unroll
+                    for (int j = 0; j < A; ++j) {
+                        const float nz = fminf(fmaxf(st.noise[j], -c.noise_clamp), c.noise_clamp);
+                        acts[k.row * 4 + j] = fminf(fmaxf(tanhf(out[j]) + nz, -1.f), 1.f);
+                    }
+                }
+                __syncthreads();
+            }
+            stamp(k, 2);
+            // target critic tower t on (next_state, a') (HIRL.py:270)
+            float tq_own;
+            {
+                float out[1];
+                pass_forward<CriticL>(k, c.tcritic + t * CriticL::SIZE, c.tcc.img_tcritic + (size_t)t * IMG_FWD, SA, acts, slope, xh, rstd, out);
+                tq_own = out[0];
+                if (k.crank == 0 && k.act && k.wh == 0) c.tcc.TQX[(r * 2 + t) * RB + k.row] = tq_own;
+                flag_publish(k, PF_TQ + r * 2 + t, fgen);
+            }
+            stamp(k, 3);
+            // critic tower t on (state, action) (HIRL.py:277)
+            float q1[1];
+            k.pb = 28;
+            pass_forward<CriticL>(k, c.critic + t * CriticL::SIZE, c.tcc.img_critic + (size_t)t * IMG_FWD, 0, nullptr, slope, xh, rstd, q1);
+            k.pb = 0;
+            stamp(k, 4);
+            flag_wait(k, PF_TQ + r * 2 + (1 - t), fgen);
+            stamp(k, 36);
+            const float tq_other = __ldcg(c.tcc.TQX + (r * 2 + (1 - t)) * RB + k.row);
+            const float *xs = reinterpret_cast<const float *>(k.sm + O_X);
+            const float rew = xs[k.row * 32 + 30], dn = xs[k.row * 32 + 31];
+            const float tq = t == 0 ? fminf(tq_own, tq_other) : fminf(tq_other, tq_own);
+            const float y = __fadd_rn(rew, __fmul_rn(__fmul_rn(c.gamma, tq), __fsub_rn(1.f, dn)));          // HIRL.py:274
+            const float delta = q1[0] - y;
+            if (k.crank == 0 && k.act && k.wh == 0 && valid) {
+                c.sc.Q[(size_t)t * B + bg] = q1[0];
+                c.sc.TQ[(size_t)t * B + bg] = tq_own;
+                if (t == 0) c.sc.Y[bg] = y;
+            }
+            {
+                const float ls = row_sum(k, valid ? delta * delta : 0.f, 0);
+                if (k.crank == 0 && threadIdx.x == 0) c.tcc.LPT[unit] = ls;
+            }
+            float dout[1] = {valid ? (2.f / (float)B) * delta : 0.f};                                          // mse_loss backward, mean reduction
+            float dz[32], dy[32], h[32];
+            head_ln2_backward<CriticL>(k, xh, rstd, dout, slope, dz, dy, h);
+            __syncthreads();                                                                                   // exchange slots (D region) read by everybody
+            // second-layer small parameters of this CTA's 64 features: db2, dgamma2, dbeta2, dW3 (+ db3 by CTA 0)
+            float *part = c.tcc.PARTC + ((size_t)(unit >> 1) * CL * 2 + t) * CriticL::SMALL;                   // slot 8 r (+ tower)
+            {
+                float *p2 = part + CriticL::small_index(CriticL::B2) + NSL * k.crank;
+                const float dq = dout[0];
+                column_sums<4>(k, [&](int a, int e) { return a == 0 ? dz[e] : a == 1 ? dy[e] * xh[e] : a == 2 ? dy[e] : dq * h[e]; }, p2, H2);
+                const float sdq = row_sum(k, dq, 1);
+                if (k.crank == 0 && threadIdx.x == 0) part[CriticL::small_index(CriticL::B3)] = sdq;
+            }
+            stamp(k, 37);
+            BwdOut bo;
+            k.pb = 40;
+            pass_backward<CriticL, true>(k, c.critic + t * CriticL::SIZE, c.tcc.imgt_critic + (size_t)t * IMG_T, 0, nullptr, slope, dz,
+                                         c.tcc.DH1P + (size_t)unit * CL * RB * H1, c.tcc.GW2PC + ((size_t)t * MAX_RB + r) * H2 * H1, bo);
+            k.pb = 0;
+            ln1_param_partials<CriticL>(k, bo, 0, nullptr, c.tcc.PARTC + ((size_t)(r * CL + k.crank) * 2 + t) * CriticL::SMALL);
+            stamp(k, 5);
+        }
+        grid_sync(k);
+        stamp(k, 6);
+        // =============================== phase B: critic Adam ===============================
+        adam_tcc<CriticL>(grank, gsize, 2, c.critic, c.g_critic, c.tcc.GW2PC, MAX_RB, c.m_critic, c.v_critic, c.tcc.PARTC, CL * nrb, nrb,
+                          st.critic_neg_step, st.critic_bc2_sqrt, c.tcc.img_critic, c.tcc.imgt_critic, nullptr, nullptr, false, 0.f, 0.f);
+        if (grank == gsize - 1 && threadIdx.x == 0) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int r = 0; r < nrb; ++r) { s0 += __ldcg(c.tcc.LPT + 2 * r); s1 += __ldcg(c.tcc.LPT + 2 * r + 1); }
+            c.carry[0] = __fadd_rn(s0 / (float)B, s1 / (float)B);                                              // HIRL.py:284
+        }
+        stamp(k, 7);
+        grid_sync(k);
+        stamp(k, 8);
+        if (do_actor) {
+            // =============================== phase C: actor forward / backward ===============================
+            BcWeight bw;
+            bw.w = 0.f; bw.one_minus_w = 1.f; bw.count = 0.f;
+            auto resolve_weight = [&]() {                               // HIRL.py:292-308, identical in every CTA
+                double w = (double)st.bc_weight_now;
+                if (soft) {
+                    float cnt = 0.f;
+                    for (int r = 0; r < nrb; ++r) {
+                        flag_wait(k, PF_CNT + r, fgen);
+                        cnt += __ldcg(c.tcc.CNT + 2 * r);
+                    }
+                    bw.count = cnt;
+                    const float mean = st.force_soft_weight >= 0.f ? st.force_soft_weight : cnt / (float)B;
+                    w = (double)mean + (double)st.bc_warm_up;
+                }
+                if (w > 1.0) w = 1.0;
+                bw.w = (float)w;
+                bw.one_minus_w = (float)(1.0 - w);
+            };
+            const int role = k.cid % 3, r = k.cid / 3;
+            if (k.cid < 3 * nrb && (role != 1 || soft)) {
+                const int bg = RB * r + k.row;
+                const bool valid = bg < B;
+                float xh[32], rstd;
+                if (role == 0) {
+                    // ---- role A: pi = actor(s), rl_Q = Q1(s, pi) with the updated critic (HIRL.py:295-297)
+                    gather_rows(k, c, st, step, r, false);
+                    float out[A], pi[A];
+                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, xh, rstd, out);
+#pragma unroll
+                    for (int j = 0; j < A; ++j) pi[j] = tanhf(out[j]);
+                    if (k.act && k.wh == 0) {
+#pragma unroll
+                        for (int j = 0; j < A; ++j) acts[k.row * 4 + j] = pi[j];
+                        if (k.crank == 0 && valid) {
+#pragma unroll
+                            for (int j = 0; j < A; ++j) c.sc.PI[(size_t)bg * A + j] = pi[j];
+                        }
+                    }
+                    if (k.act) {                                        // the actor pass' state is parked in L2 while the Q pass uses the registers
+                        float *xs2 = c.tcc.XH2S + ((size_t)r * RB + k.row) * H2 + NSL * k.crank + 32 * k.wh;
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) st4(xs2 + e, make_float4(xh[e], xh[e + 1], xh[e + 2], xh[e + 3]));
+                    }
+                    const float rstd_a = rstd;
+                    __syncthreads();
+                    stamp(k, 10);
+                    float q[1];
+                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, xh, rstd, q);
+                    stamp(k, 11);
+                    float softq = 0.f;
+                    if (soft) {
+                        flag_wait(k, PF_SOFTQ + r, fgen);
+                        softq = __ldcg(c.tcc.SOFTQX + r * RB + k.row);
+                    }
+                    if (k.crank == 0 && k.act && k.wh == 0 && valid) {
+                        c.sc.RLQ[bg] = q[0];
+                        if (soft) c.sc.SOFTQ[bg] = softq;
+                    }
+                    {
+                        const float cnt = row_sum(k, (valid && soft && softq > q[0]) ? 1.f : 0.f, 0);          // HIRL.py:303
+                        const float sq = row_sum(k, valid ? q[0] : 0.f, 1);
+                        if (k.crank == 0 && threadIdx.x == 0) { c.tcc.CNT[2 * r] = cnt; c.tcc.CNT[2 * r + 1] = sq; }
+                        flag_publish(k, PF_CNT + r, fgen);
+                    }
+                    // backward of rl_loss = -mean(Q1) to the action input; (1 - w) is applied where it meets the actor
+                    float dout[1] = {valid ? -1.f / (float)B : 0.f};
+                    float dz[32], dy[32], h[32];
+                    head_ln2_backward<CriticL>(k, xh, rstd, dout, slope, dz, dy, h);
+                    __syncthreads();
+                    BwdOut bo;
+                    pass_backward<CriticL, false>(k, c.critic, c.tcc.imgt_critic, 0, acts, slope, dz, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, nullptr, bo);
+                    {
+                        float g[A];
+#pragma unroll
+                        for (int j2 = 0; j2 < A; ++j2) {
+                            float p = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) p = fmaf(bo.dz1[j], c.critic[CriticL::W1T + (S + j2) * H1 + k.lane + 32 * j], p);
+                            g[j2] = warp_sum(p);
+                        }
+                        if (k.lane < CL) st_dsmem_f32x4(map_to_cta(smem_u32(gpi + bo.b * 4), k.lane), g[0], g[1], g[2], g[3]);
+                        if (k.crank == 0 && k.lane == 0 && RB * r + bo.b < B) {
+#pragma unroll
+                            for (int j = 0; j < A; ++j) c.sc.GPI[(size_t)(RB * r + bo.b) * A + j] = g[j];
+                        }
+                        cluster_sync();
+                    }
+                    stamp(k, 12);
+                    resolve_weight();
+                    stamp(k, 13);
+                    // actor backward, RL branch
+                    load_pc<ActorL>(k, c.actor);
+                    if (k.act) {
+                        const float *xs2 = c.tcc.XH2S + ((size_t)r * RB + k.row) * H2 + NSL * k.crank + 32 * k.wh;
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            const float4 v4 = __ldcg(reinterpret_cast<const float4 *>(xs2 + e));
+                            xh[e] = v4.x; xh[e + 1] = v4.y; xh[e + 2] = v4.z; xh[e + 3] = v4.w;
+                        }
+                    }
+                    __syncthreads();
+                    float dpre[A];
+#pragma unroll
+                    for (int j = 0; j < A; ++j) {
+                        const float dpi = valid ? bw.one_minus_w * gpi[k.row * 4 + j] : 0.f;
+                        dpre[j] = dpi * (1.f - pi[j] * pi[j]);
+                    }
+                    head_ln2_backward<ActorL>(k, xh, rstd_a, dpre, slope, dz, dy, h);
+                    __syncthreads();
+                    float *part = c.tcc.PARTA + (size_t)(r * CL) * ActorL::SMALL;                               // branch 0, slot 8 r
+                    {
+                        float *p2 = part + ActorL::small_index(ActorL::B2) + NSL * k.crank;
+                        column_sums<7>(k, [&](int a, int e) { return a == 0 ? dz[e] : a == 1 ? dy[e] * xh[e] : a == 2 ? dy[e] : dpre[a - 3] * h[e]; }, p2, H2);
+#pragma unroll
+                        for (int j = 0; j < A; ++j) {
+                            const float sd = row_sum(k, dpre[j], 1);
+                            if (k.crank == 0 && threadIdx.x == 0) part[ActorL::small_index(ActorL::B3) + j] = sd;
+                        }
+                    }
+                    pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, 0, nullptr, slope, dz, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1,
+                                                c.tcc.GW2PA + (size_t)r * H2 * H1, bo);
+                    ln1_param_partials<ActorL>(k, bo, 0, nullptr, c.tcc.PARTA + (size_t)(r * CL + k.crank) * ActorL::SMALL);
+                    stamp(k, 14);
+                } else if (role == 1) {
+                    // ---- role S: a_bc = bc_actor(s), soft_Q = Q1(s, a_bc) (HIRL.py:300-302)
+                    gather_rows(k, c, st, step, r, false);
+                    float out[A];
+                    pass_forward<ActorL>(k, c.bc, c.tcc.img_bc, 0, nullptr, slope, xh, rstd, out);
+                    if (k.act && k.wh == 0) {
+#pragma unroll
+                        for (int j = 0; j < A; ++j) {
+                            const float a = tanhf(out[j]);
+                            acts[k.row * 4 + j] = a;
+                            if (k.crank == 0 && valid) c.sc.ABC[(size_t)bg * A + j] = a;
+                        }
+                    }
+                    __syncthreads();
+                    float q[1];
+                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, xh, rstd, q);
+                    if (k.crank == 0 && k.act && k.wh == 0) c.tcc.SOFTQX[r * RB + k.row] = q[0];
+                    flag_publish(k, PF_SOFTQ + r, fgen);
+                } else {
+                    // ---- role AB: pi_bc = actor(s_bc), cloning loss (HIRL.py:310-319), actor backward of the BC branch
+                    gather_rows(k, c, st, step, r, true);
+                    float out[A], pi[A], diff[A];
+                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, xh, rstd, out);
+                    const float *xs = reinterpret_cast<const float *>(k.sm + O_X);
+                    float sq = 0.f, fire = 0.f;
+#pragma unroll
+                    for (int j = 0; j < A; ++j) {
+                        pi[j] = tanhf(out[j]);
+                        diff[j] = pi[j] - xs[k.row * 32 + S + j];
+                        sq = fmaf(diff[j], diff[j], sq);
+                    }
+                    fire = diff[3] * diff[3];
+                    if (k.crank == 0 && k.act && k.wh == 0 && valid) {
+#pragma unroll
+                        for (int j = 0; j < A; ++j) c.sc.PIB[(size_t)bg * A + j] = pi[j];
+                    }
+                    {
+                        const float s0 = row_sum(k, valid ? sq : 0.f, 0);
+                        const float s1 = row_sum(k, valid ? fire : 0.f, 1);
+                        if (k.crank == 0 && threadIdx.x == 0) { c.tcc.LPT[8 + 2 * r] = s0; c.tcc.LPT[8 + 2 * r + 1] = s1; }
+                    }
+                    resolve_weight();
+                    const float bc_scale = bw.w * c.loss_lambda;
+                    float dpre[A];
+#pragma unroll
+                    for (int j = 0; j < A; ++j) {
+                        const float dpi = valid ? ((2.f / (float)(A * B)) * diff[j]) * bc_scale : 0.f;
+                        dpre[j] = dpi * (1.f - pi[j] * pi[j]);
+                    }
+                    float dz[32], dy[32], h[32];
+                    head_ln2_backward<ActorL>(k, xh, rstd, dpre, slope, dz, dy, h);
+                    __syncthreads();
+                    float *part = c.tcc.PARTA + (size_t)((MAX_RB + r) * CL) * ActorL::SMALL;                    // branch 1, slot 8 (4 + r)
+                    {
+                        float *p2 = part + ActorL::small_index(ActorL::B2) + NSL * k.crank;
+                        column_sums<7>(k, [&](int a, int e) { return a == 0 ? dz[e] : a == 1 ? dy[e] * xh[e] : a == 2 ? dy[e] : dpre[a - 3] * h[e]; }, p2, H2);
+#pragma unroll
+                        for (int j = 0; j < A; ++j) {
+                            const float sd = row_sum(k, dpre[j], 1);
+                            if (k.crank == 0 && threadIdx.x == 0) part[ActorL::small_index(ActorL::B3) + j] = sd;
+                        }
+                    }
+                    BwdOut bo;
+                    pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, 0, nullptr, slope, dz, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1,
+                                                c.tcc.GW2PA + (size_t)(MAX_RB + r) * H2 * H1, bo);
+                    ln1_param_partials<ActorL>(k, bo, 0, nullptr, c.tcc.PARTA + (size_t)((MAX_RB + r) * CL + k.crank) * ActorL::SMALL);
+                }
+            }
+            grid_sync(k);
+            stamp(k, 15);
+            // =============================== phase D: actor Adam, Polyak, scalars ===============================
+            adam_tcc<ActorL>(grank, gsize, 1, c.actor, c.g_actor, c.tcc.GW2PA, 2 * MAX_RB, c.m_actor, c.v_actor, c.tcc.PARTA, 2 * MAX_RB * CL, 2 * MAX_RB,
+                             st.actor_neg_step, st.actor_bc2_sqrt, c.tcc.img_actor, c.tcc.imgt_actor, c.tactor, c.tcc.img_tactor, do_polyak, tau, omt);
+            if (do_polyak) polyak_tcc<CriticL>(grank, gsize, 2, c.critic, c.tcritic, c.tcc.img_tcritic, tau, omt);
+            if (grank == gsize - 1 && threadIdx.x == 0) {
+                // the weight once more, from the published counts (every flag has been passed by now)
+                double w = (double)st.bc_weight_now;
+                float cnt = 0.f, sumq = 0.f, bsq = 0.f, fsq = 0.f;
+                for (int r = 0; r < nrb; ++r) {
+                    cnt += __ldcg(c.tcc.CNT + 2 * r); sumq += __ldcg(c.tcc.CNT + 2 * r + 1);
+                    bsq += __ldcg(c.tcc.LPT + 8 + 2 * r); fsq += __ldcg(c.tcc.LPT + 8 + 2 * r + 1);
+                }
+                if (soft) {
+                    const float mean = st.force_soft_weight >= 0.f ? st.force_soft_weight : cnt / (float)B;
+                    w = (double)mean + (double)st.bc_warm_up;
+                } else cnt = 0.f;
+                if (w > 1.0) w = 1.0;
+                const float wf = (float)w, omw = (float)(1.0 - w);
+                const float rl_loss = -(sumq / (float)B);                                                     // HIRL.py:297
+                const float bc_loss = __fmul_rn(bsq / (float)(A * B), c.loss_lambda);                          // HIRL.py:311
+                c.carry[1] = __fadd_rn(__fmul_rn(bc_loss, wf), __fmul_rn(rl_loss, omw));                       // HIRL.py:321
+                c.carry[2] = bc_loss;
+                c.carry[3] = rl_loss;
+                c.carry[4] = fsq / (float)B;                                                                   // HIRL.py:319 (x lambda on the host)
+                c.carry[5] = wf;
+                c.carry[6] = cnt;
+            }
+            grid_sync(k);
+            stamp(k, 16);
+        }
+        if (grank == gsize - 1 && threadIdx.x < HIRL_OUT_SCALARS) c.out_scalars[(size_t)step * HIRL_OUT_SCALARS + threadIdx.x] = c.carry[threadIdx.x];
+    }
+    if (grank == 0 && threadIdx.x == 0) *c.tcc.gen_ctr = k.pgen + (unsigned)Lc.k_steps;
+    tc::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tc::tmem_dealloc(k.tm);
+}
+
+}  // namespace tcc
+}  // namespace hirl

@@ -72,16 +72,22 @@ def check_step(tag, got, ref32, ref64, tol=1e-5):
 def _backend(monkeypatch, mode):
     """'cluster' / 'cluster18': the cluster-resident kernel (row blocks of 16 / 18 rows); '0' / '1' / '2': round 1's
     stage-structured kernel with FP32 tiles / tcgen05 everywhere / tcgen05 for stage G1 only."""
-    if mode.startswith("cluster"):
+    if mode == "tcc":          # the tensor-core cluster kernel (csrc/tcc_update.cuh)
         monkeypatch.delenv("HIRL_TC", raising=False)
+        monkeypatch.setenv("HIRL_CLUSTER", "0")
+        monkeypatch.setenv("HIRL_TCC", "1")
+    elif mode.startswith("cluster"):
+        monkeypatch.delenv("HIRL_TC", raising=False)
+        monkeypatch.setenv("HIRL_TCC", "0")
         monkeypatch.setenv("HIRL_CLUSTER", "1")
         monkeypatch.setenv("HIRL_RI", "9" if mode == "cluster18" else "8")
     else:
         monkeypatch.setenv("HIRL_CLUSTER", "0")
+        monkeypatch.setenv("HIRL_TCC", "0")
         monkeypatch.setenv("HIRL_TC", mode)
 
 
-@pytest.mark.parametrize("tc_mode", ["cluster", "cluster18", "0", "1", "2"])
+@pytest.mark.parametrize("tc_mode", ["tcc", "cluster", "cluster18", "0", "1", "2"])
 @pytest.mark.parametrize("B,bcw,en,steps", [(32, 100, 8, 12), (32, 0.5, 0, 12), (256, 100, 64, 12), (100, 100, 33, 6), (5, 0.3, 2, 6)])
 def test_teacher_forced_parity(B, bcw, en, steps, tc_mode, monkeypatch):
     _backend(monkeypatch, tc_mode)
