@@ -127,6 +127,8 @@ struct TccPtrs {
     float *TQX;      // [4][2][64] target Q of a tower, exchanged between the two tower clusters of a row block
     float *SOFTQX;   // [4][64]
     float *XH2S;     // [4][64][H2] normalised second-layer rows of the actor pass, parked while the Q pass runs
+    float *H1TI;     // [units][32768] transposed first-layer activation tiles (hi | lo) of back-propagated passes
+    float *RSUM;     // [units][8] per-unit row sums (scratch)
     float *LPT;      // [16] per-unit loss partials: critic [r][t] at 0..7, cloning (sum sq, fire sq) at 8 + 2 r
     float *CNT;      // [4][2] soft count and sum of rl_Q per row block
     unsigned *pflags;   // [16][32] point-to-point flags (generations keep counting across launches)

@@ -602,6 +602,8 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
             if ((rc = dev_alloc(h, &t.TQX, (size_t)tcc::MAX_RB * 2 * tcc::RB))) return rc;
             if ((rc = dev_alloc(h, &t.SOFTQX, (size_t)tcc::MAX_RB * tcc::RB))) return rc;
             if ((rc = dev_alloc(h, &t.XH2S, (size_t)tcc::MAX_RB * tcc::RB * H2))) return rc;
+            if ((rc = dev_alloc(h, &t.H1TI, (size_t)tcc::MAX_NCL * tcc::H1T_FLOATS))) return rc;
+            if ((rc = dev_alloc(h, &t.RSUM, (size_t)tcc::MAX_NCL * 8))) return rc;
             if ((rc = dev_alloc(h, &t.LPT, 16))) return rc;
             if ((rc = dev_alloc(h, &t.CNT, 8))) return rc;
             if ((rc = dev_alloc(h, &t.pflags, (size_t)tcc::PF_WORDS * FLAG_STRIDE))) return rc;

@@ -22,17 +22,20 @@
 //   ---- grid barrier ----
 //
 // CTA j of a cluster owns the output features 64 j .. 64 j + 63 of the 512-wide layers.  Per pass:
-//   * first layer (K = 13 / 17) + LayerNorm1 + activation in FP32 FMAs (one warp = 8 rows, 4 rows register-blocked),
-//     written hi/lo-split straight into the SWIZZLE_128B K-major operand tile H1[64][256] (128 KB of shared memory);
+//   * first layer (K = 13 / 17) + LayerNorm1 + activation in FP32 FMAs from weights staged in shared memory (one bulk
+//     copy), 4 rows register-blocked per warp, written hi/lo-split straight into the SWIZZLE_128B K-major operand tile
+//     H1[64][256] (128 KB of shared memory); for back-propagated passes the CTA also writes its own 8 rows of the
+//     TRANSPOSED tile image to L2 (tf32 has no MN-major twin of this layout, tools/tcc_probe.cu);
 //   * second layer: tcgen05.mma M=64 N=64, A = H1 tile, B = this CTA's slice of a pre-split, pre-swizzled image of W2
-//     streamed by cp.async.bulk through a 3-slot ring; accumulators (main + correction) in TMEM;
-//   * LayerNorm2 / head from the accumulator with ONE THREAD PER ROW (tcgen05.ld): the row statistics and the head dot
-//     products are completed across the 8 CTAs by pushing partials into every CTA's shared memory (st.shared::cluster)
-//     and one barrier.cluster -- no shuffles, no global round trip;
-//   * backward: dz2 per thread-row -> K-major tile D;  dH1^T[256][64] = W2T-image . dz2  (M=128 x 2, this CTA's 64
+//     streamed by cp.async.bulk through a 3-slot ring; the three products of the 3xTF32 split are issued by three threads
+//     into three TMEM accumulators (a single issuing thread costs ~90 cycles per MMA and was the critical path);
+//   * LayerNorm2 / head from the accumulators with ONE THREAD PER ROW (tcgen05.ld): row statistics and head dot products
+//     are completed across the 8 CTAs by st.async pushes into every CTA's shared memory, each signalling the receiver's
+//     mbarrier -- no shuffles, no cluster barrier, no global round trip;
+//   * backward: dz2 per thread-row -> K-major tile;  dH1^T[256][64] = W2T-image . dz2  (M=128 x 2, this CTA's 64
 //     features = its K slice) -> partial through L2 -> row owner sums 8 partials -> LayerNorm1 backward;
-//     dW2^T[256][64] = H1^T . dz2^T with H1^T RECOMPUTED into the same 128 KB while the dH1 MMAs run (tf32 has no
-//     MN-major twin of the K-major SWIZZLE_128B layout, tools/tcc_probe.cu) and dz2^T written into the idle ring.
+//     dW2^T[256][64] = H1^T . dz2^T with the H1^T image bulk-loaded from L2 and dz2^T written into the idle ring; the
+//     dW2 MMAs run while the dH1 partials are exchanged.
 // Everything is reduced in a fixed order: results are run-to-run deterministic.  FP32-accurate: rel-L2 <= 1e-5 against
 // torch fp32 per step (tests/test_gpu_update.py, back-end "tcc").
 #pragma once
@@ -49,25 +52,28 @@ constexpr int TTHREADS = 256;
 constexpr int MAX_NCL = 16;        // clusters per launch
 constexpr int MAX_RB = 4;          // row blocks (batch <= 256)
 constexpr int SLOT_BYTES = 16384, NSLOT = 3;
+constexpr int ISSUERS = 3;         // one thread per product of the 3xTF32 split
 // shared-memory carve-up (bytes from a 1024-aligned base)
 constexpr int O_R = 0;                                   // 128 KB  H1 [8 blocks][64 x 128 B] hi | lo   /  H1^T [2 blocks][256 x 128 B] hi | lo  / staging
 constexpr int R_LO = 65536;
 constexpr int O_RING = 131072;                           // 48 KB   weight stream ring  /  dz2^T [2 blocks][64 x 128 B] hi | lo
-constexpr int O_D = O_RING + NSLOT * SLOT_BYTES;         // 32 KB   dz2 [2 blocks][64 x 128 B] hi | lo  /  exchange slots  /  first-layer column sums
-constexpr int O_X = O_D + 32768;                         // 8 KB    gathered rows [64][32]
+constexpr int O_D = O_RING + NSLOT * SLOT_BYTES;         // 33 KB   [0,16K) exchange slots, [16K,33K) W1 of the pass | [0,32K) dz2 tile, first-layer column sums
+constexpr int O_W1 = O_D + 16384;
+constexpr int O_X = O_D + 16384 + 17408;                        // 8 KB    gathered rows [64][32]
 constexpr int O_ACT = O_X + 8192;                        // 1 KB    action columns of the critic input [64][4]
 constexpr int O_GPI = O_ACT + 1024;                      // 1 KB    d pi [64][4]
-constexpr int O_PC = O_GPI + 1024;                       // 2 KB    parameter cache of the pass: b2 | g2 | be2 | w3[nout] for this CTA's 64 features
-constexpr int O_RED = O_PC + 2048;                       // 1 KB    small reductions
-constexpr int SMEM_USED = O_RED + 1024;
+constexpr int O_PC = O_GPI + 1024;                       // 2 KB    parameter cache of the pass: b2 | g2 | be2 | w3[nout] (this CTA's 64 features) | b3
+constexpr int O_RED = O_PC + 2048;                       // 2 KB    [1K,2K) half-row combine scratch of the exchanges
+constexpr int SMEM_USED = O_RED + 2048;
 constexpr size_t SMEM_BYTES = SMEM_USED + 1024;          // + alignment slack
-static_assert(SMEM_BYTES + 2048 <= 232448, "shared memory budget (227 KB per CTA incl. static)");
-// TMEM columns
-constexpr int T_MAIN = 0, T_CORR = 64, T_DH = 128, T_DW = 256;
+static_assert(SMEM_BYTES + 1200 <= 232448, "shared memory budget (227 KB per CTA incl. static)");
+// TMEM columns: forward accumulators (main, Alo.Bhi, Ahi.Blo); backward accumulators (m-block, product) at 64 (3 mb + p)
+constexpr int T_MAIN = 0, T_C1 = 64, T_C2 = 128;
 
 // image geometry (floats)
-constexpr size_t IMG_FWD = (size_t)H2 * H1 * 2;          // per tower: [8 slices][8 k-blocks][hi 2048 | lo 2048]... 4096 floats per (slice, block)
+constexpr size_t IMG_FWD = (size_t)H2 * H1 * 2;          // per tower: [8 slices][8 k-blocks][hi 2048 | lo 2048]
 constexpr size_t IMG_T = (size_t)H2 * H1 * 2;            // per tower: [8 slices][2 m-blocks][2 k-chunks][hi 4096 | lo 4096]
+constexpr size_t H1T_FLOATS = 32768;                     // H1^T image of one row block: hi [2 blocks][256 x 32] | lo
 __host__ __device__ __forceinline__ uint32_t sw128_words(int row, int kk) {
     return (uint32_t)((row >> 3) * 256 + (row & 7) * 32 + ((((kk >> 2) ^ (row & 7)) << 2) | (kk & 3)));
 }
@@ -81,6 +87,7 @@ __host__ __device__ __forceinline__ size_t img_t_index(int n, int k) {       // 
 // p2p flag words (each on its own 128-byte line)
 enum { PF_TQ = 0 /* [r][t] */, PF_SOFTQ = 8 /* [r] */, PF_CNT = 12 /* [r] */, PF_WORDS = 16 };
 constexpr int PROF_WORDS = 96;
+enum { B_FULL = 0, B_EMPTY = NSLOT, B_ACC = 2 * NSLOT, B_W1 = 2 * NSLOT + 2, B_H1T, B_X0, B_X1, N_BARS };
 
 struct TccLaunch {
     AgentCtx agent;
@@ -91,11 +98,12 @@ struct TccLaunch {
 
 struct Ctl {
     char *sm;
-    uint64_t *full, *empty, *acc;
+    unsigned pad;      // sm = (dynamic shared memory symbol) + pad
+    uint64_t *bars;
     uint32_t tm;
     int crank, cid, ncl, warp, lane, sub, wh, row;   // row: batch row of this thread inside the block (thread-per-row epilogues)
     bool act;                                         // lane < 16: this thread owns (row, 32 columns)
-    unsigned ring_n, acc_n[2], xr, gen, pgen;
+    unsigned ring_n, acc_n[2], w1_n, h1t_n, xr, gen, pgen;
     unsigned *flags, *pflags;
     long long *pr;
     int pb;   // base index of the fine-grained stamps of the current pass (0: off)
@@ -105,10 +113,10 @@ __device__ __forceinline__ void pstamp(const Ctl &k, int i) { if (k.pr && k.pb &
 
 // ---- synchronisation -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grid_sync(Ctl &k) {
-    cluster_sync();
+    cluster_sync();                                                    // the whole cluster has arrived (cluster-scope release / acquire)
     k.gen += 1u;
-    if (k.crank == 0 && threadIdx.x < 32) {
-        if (threadIdx.x == 0) st_release_u32(k.flags + k.cid * FLAG_STRIDE, k.gen);
+    if (threadIdx.x < 32) {                                            // one flag per cluster, polled by every CTA (no second cluster barrier)
+        if (k.crank == 0 && threadIdx.x == 0) st_release_u32(k.flags + k.cid * FLAG_STRIDE, k.gen);
         bool pending = true;
         const long long t0 = clock64();
         while (pending) {
@@ -121,7 +129,7 @@ __device__ __forceinline__ void grid_sync(Ctl &k) {
         }
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
-    cluster_sync();
+    __syncthreads();
 }
 // producer side of a point-to-point flag: the CTA's global writes, then one release store
 __device__ __forceinline__ void flag_publish(Ctl &k, int word, unsigned value) {
@@ -142,45 +150,58 @@ __device__ __forceinline__ void flag_wait(Ctl &k, int word, unsigned value) {
     __syncthreads();
 }
 
-// ---- cluster-wide per-row exchange: every (CTA, column half) contributes one float4 per row; afterwards every thread
-//      reads the 16 contributions of its row from its own shared memory (slots alias the dz2 tile, double-buffered) --------
+// ---- cluster-wide per-row exchange ------------------------------------------------------------------------------------
+// Every CTA contributes one float4 per row (its two column halves combined locally first); the contribution is pushed
+// into the slot [src CTA][row] of EVERY CTA with st.async, which signals the receiver's mbarrier (16 bytes each); a round
+// is complete for a CTA when its own mbarrier has seen 8 x 64 x 16 bytes.  Two slot buffers / barriers alternate.
+// `chan`: the halves are (mean, M2) pairs over 32 values each and are merged with Chan's formula, else plain sums.
 __device__ __forceinline__ float4 *xslot(const Ctl &k, int buf, int src, int row) {
-    return reinterpret_cast<float4 *>(k.sm + O_D + buf * 16384 + (src * RB + row) * 16);
+    return reinterpret_cast<float4 *>(k.sm + O_D + buf * 8192 + (src * RB + row) * 16);
 }
-__device__ __forceinline__ void exchange_push(Ctl &k, float a, float b, float c, float d) {
+__device__ __forceinline__ void exchange_push(Ctl &k, float a, float b, float c, float d, bool chan) {
     const int buf = k.xr & 1;
-    if (k.act) {
-        const uint32_t local = smem_u32(xslot(k, buf, 2 * k.crank + k.wh, k.row));
+    float4 *half = reinterpret_cast<float4 *>(k.sm + O_RED + 1024);               // [64 rows] contribution of the upper column half
+    if (k.act && k.wh == 1) half[k.row] = make_float4(a, b, c, d);
+    if (threadIdx.x == 0) mbar_expect_tx(k.bars + B_X0 + buf, CL * RB * 16);
+    __syncthreads();
+    if (k.act && k.wh == 0) {
+        const float4 o = half[k.row];
+        float4 v;
+        if (chan) {
+            const float mean = 0.5f * (a + o.x), dl = o.x - a;
+            v = make_float4(mean, (b + o.y) + 16.f * dl * dl, 0.f, 0.f);       // n = 32 + 32: M2 = M2a + M2b + d^2 * 32*32/64
+        } else v = make_float4(a + o.x, b + o.y, c + o.z, d + o.w);
+        const uint32_t local = smem_u32(xslot(k, buf, k.crank, k.row)), bar = smem_u32(k.bars + B_X0 + buf);
 #pragma unroll
-        for (int dst = 0; dst < CL; ++dst) st_dsmem_f32x4(map_to_cta(local, dst), a, b, c, d);
+        for (int dst = 0; dst < CL; ++dst) st_async_f32x4(map_to_cta(local, dst), v.x, v.y, v.z, v.w, map_to_cta(bar, dst));
     }
-    cluster_sync();
+    tc::mbar_wait(k.bars + B_X0 + buf, (k.xr >> 1) & 1u, 800);
     k.xr += 1u;
 }
-__device__ __forceinline__ float4 exchange_get(const Ctl &k, int src) {   // after exchange_push: contribution `src` (0..15) of this thread's row
+__device__ __forceinline__ float4 exchange_get(const Ctl &k, int src) {   // after exchange_push: contribution of CTA `src` for this thread's row
     return *xslot(k, (k.xr - 1u) & 1, src, k.row);
 }
 
 // ---- weight stream ------------------------------------------------------------------------------------------------
-// units of 16 KB, contiguous in global memory.  Called by ALL threads (uniform arguments); thread 32 issues the copies.
-// `blocking == false` issues only units whose ring slot is known to be free already (the first NSLOT after an idle ring).
+// units of 16 KB, contiguous in global memory.  Called by ALL threads (uniform arguments); lane 0 of warp 3 issues the copies.
+constexpr int PRODUCER = 96;
 __device__ __forceinline__ void stream_units(Ctl &k, const float *src, int first, int count) {
-    if (threadIdx.x == 32) {
+    if (threadIdx.x == PRODUCER) {
         for (int u = first; u < first + count; ++u) {
             const unsigned n = k.ring_n + (unsigned)u;
             const int s = (int)(n % NSLOT);
-            if (n >= NSLOT) tc::mbar_wait(k.empty + s, ((n / NSLOT) - 1u) & 1u, 500 + u);
-            mbar_expect_tx(k.full + s, SLOT_BYTES);
-            bulk_g2s(k.sm + O_RING + s * SLOT_BYTES, reinterpret_cast<const char *>(src) + (size_t)u * SLOT_BYTES, SLOT_BYTES, k.full + s);
+            if (n >= NSLOT) tc::mbar_wait(k.bars + B_EMPTY + s, ((n / NSLOT) - 1u) & 1u, 500 + u);
+            mbar_expect_tx(k.bars + B_FULL + s, SLOT_BYTES);
+            bulk_g2s(k.sm + O_RING + s * SLOT_BYTES, reinterpret_cast<const char *>(src) + (size_t)u * SLOT_BYTES, SLOT_BYTES, k.bars + B_FULL + s);
         }
     }
 }
-__device__ __forceinline__ void ring_wait_full(Ctl &k, unsigned n) {   // consumer thread
-    tc::mbar_wait(k.full + (n % NSLOT), (n / NSLOT) & 1u, 600);
+__device__ __forceinline__ void ring_wait_full(Ctl &k, unsigned n) {   // issuer threads
+    tc::mbar_wait(k.bars + B_FULL + (n % NSLOT), (n / NSLOT) & 1u, 600);
     tc::tc_fence_after();
 }
 __device__ __forceinline__ void acc_wait(Ctl &k, int which) {          // all threads
-    tc::mbar_wait(k.acc + which, k.acc_n[which] & 1u, 700 + which);
+    tc::mbar_wait(k.bars + B_ACC + which, k.acc_n[which] & 1u, 700 + which);
     k.acc_n[which] += 1u;
     tc::tc_fence_after();
 }
@@ -191,20 +212,29 @@ __device__ __forceinline__ void publish_operands() {
     __syncthreads();
 }
 
-// ---- first layer + LayerNorm1 + activation into an operand tile ------------------------------------------------------
+// ---- first layer + LayerNorm1 + activation into the forward operand tile ------------------------------------------------
 // x_k of row b:  k < 13: xs[b][soff + k];  k >= 13 (critic): acts[b][k - 13]  (acts == nullptr: xs[b][k], the stored action)
-// TR == false: H1[b][n]  (forward A operand, 8 blocks of [64 rows][32]);  TR == true: H1^T[n][b] (2 blocks of [256 rows][32])
-template <class L, bool TR>
-__device__ __noinline__ void l1_tile(char *sm, const float *tw, int soff, const float *acts, float slope) {
+// W1T [k0 x 256] is staged in shared memory (stage_w1); b1 / g1 / be1 come from the arena.  H1[b][n] -> 8 blocks of [64 rows][32] hi | lo.
+// own_xh / own_rstd: xhat1 / rstd1 of the CTA's own row of this warp (row 8 crank + warp), kept for the backward pass.
+// h1t (may be null): global H1^T image of the row block; this warp writes the column of its own row.
+template <class L>
+__device__ __noinline__ void l1_tile(unsigned pad, const float *tw, uint64_t *w1bar, unsigned w1par, int soff, bool use_acts, float slope, int crank, float *h1t,
+                                     float (&own_xh)[8], float &own_rstd, long long *dbg) {
+    // pointers are derived from the shared-memory symbol itself (not passed in as generic pointers): LDS / STS instead of LD / ST
+    extern __shared__ float4 smem4[];
+    char *sm = reinterpret_cast<char *>(smem4) + pad;
+    const float *acts = use_acts ? reinterpret_cast<const float *>(sm + O_ACT) : nullptr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float *xs = reinterpret_cast<const float *>(sm + O_X);
+    const float *xs = reinterpret_cast<const float *>(sm + O_X), *w1s = reinterpret_cast<const float *>(sm + O_W1);
     float b1[8], g1[8], be1[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 8; ++j) {                                      // in flight while the bulk copy of W1 lands
         b1[j] = tw[L::B1 + lane + 32 * j];
         g1[j] = tw[L::G1 + lane + 32 * j];
         be1[j] = tw[L::BE1 + lane + 32 * j];
     }
+    tc::mbar_wait(w1bar, w1par, 900);
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
     for (int grp = 0; grp < 2; ++grp) {
         float z[4][8];
 #pragma unroll
@@ -215,7 +245,7 @@ __device__ __noinline__ void l1_tile(char *sm, const float *tw, int soff, const 
         for (int kk = 0; kk < L::k0; ++kk) {
             float w[8], xv[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = tw[L::W1T + kk * H1 + lane + 32 * j];
+            for (int j = 0; j < 8; ++j) w[j] = w1s[kk * H1 + lane + 32 * j];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int b = warp + 8 * (4 * grp + i);
@@ -226,6 +256,7 @@ __device__ __noinline__ void l1_tile(char *sm, const float *tw, int soff, const 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) z[i][j] = fmaf(xv[i], w[j], z[i][j]);
         }
+        if (dbg && threadIdx.x == 0) dbg[1 + 3 * grp] = clock64();
         float s[4], v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -251,26 +282,36 @@ __device__ __noinline__ void l1_tile(char *sm, const float *tw, int soff, const 
         for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
             for (int i = 0; i < 4; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+        if (dbg && threadIdx.x == 0) dbg[2 + 3 * grp] = clock64();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int b = warp + 8 * (4 * grp + i);
+            const bool own = (4 * grp + i) == crank;
             const float rstd = 1.f / sqrtf(v[i] * (1.f / H1) + LN_EPS);
+            if (own) own_rstd = rstd;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float xh = (z[i][j] - s[i]) * rstd;
                 const float hv = act_f(fmaf(xh, g1[j], be1[j]), slope);
                 const float hi = tf32_hi(hv);
-                uint32_t off;
-                if (!TR) off = (uint32_t)j * 8192u + sw128_off(b, lane);
-                else off = (uint32_t)(b >> 5) * 32768u + sw128_off(lane + 32 * j, b & 31);
+                const uint32_t off = (uint32_t)j * 8192u + sw128_off(b, lane);
                 *reinterpret_cast<float *>(sm + O_R + off) = hi;
                 *reinterpret_cast<float *>(sm + O_R + R_LO + off) = hv - hi;
+                if (own) {
+                    own_xh[j] = xh;
+                    if (h1t) {
+                        float *t = h1t + (size_t)(b >> 5) * 8192 + sw128_words(lane + 32 * j, b & 31);
+                        t[0] = hi;
+                        t[16384] = hv - hi;
+                    }
+                }
             }
         }
+        if (dbg && threadIdx.x == 0) dbg[3 + 3 * grp] = clock64();
     }
 }
 
-// parameter cache of a pass: b2 | g2 | be2 | w3[o] restricted to this CTA's 64 features
+// parameter cache of a pass: b2 | g2 | be2 | w3[o] restricted to this CTA's 64 features, then b3[o] at 448
 template <class L>
 __device__ __forceinline__ void load_pc(const Ctl &k, const float *tw) {
     float *pc = reinterpret_cast<float *>(k.sm + O_PC);
@@ -279,33 +320,52 @@ __device__ __forceinline__ void load_pc(const Ctl &k, const float *tw) {
         const int off = a == 0 ? L::B2 : a == 1 ? L::G2 : a == 2 ? L::BE2 : L::W3 + (a - 3) * H2;
         pc[i] = tw[off + NSL * k.crank + c];
     }
+    if (threadIdx.x < L::nout) pc[448 + threadIdx.x] = tw[L::B3 + threadIdx.x];
+}
+// first-layer weight matrix of the pass into shared memory (one bulk copy)
+template <class L>
+__device__ __forceinline__ void stage_w1(Ctl &k, const float *tw) {
+    __syncthreads();                                                   // previous readers of the region (and of the exchange slots) are done
+    if (threadIdx.x == PRODUCER) {
+        constexpr uint32_t bytes = L::k0 * H1 * 4;
+        mbar_expect_tx(k.bars + B_W1, bytes);
+        bulk_g2s(k.sm + O_W1, tw + L::W1T, bytes, k.bars + B_W1);
+    }
 }
 
 // ---- forward pass: first layer, second layer on the tensor cores, LayerNorm2 + head per thread-row --------------------
 // out[o]: the head output of this thread's row (identical in every CTA); xh / rstd: this thread's 32 normalised columns.
+struct OwnRow { float xh1[8], rstd1; };
 template <class L>
-__device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const float *img, int soff, const float *acts, float slope,
-                                             float (&xh)[32], float &rstd, float (&out)[L::nout]) {
+__device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const float *img, int soff, const float *acts, float slope, float *h1t,
+                                             bool h1t_arrive, float (&xh)[32], float &rstd, float (&out)[L::nout], OwnRow &own) {
     char *sm = k.sm;
     const float *unit0 = img + (size_t)k.crank * 8 * 4096;            // this CTA's slice: 8 k-blocks of hi | lo
+    stage_w1<L>(k, tw);
     stream_units(k, unit0, 0, NSLOT);                                  // lands while the first layer runs
     load_pc<L>(k, tw);
     pstamp(k, 0);
-    l1_tile<L, false>(sm, tw, soff, acts, slope);
+    l1_tile<L>(k.pad, tw, k.bars + B_W1, k.w1_n & 1u, soff, acts != nullptr, slope, k.crank, h1t, own.xh1, own.rstd1,
+               (k.pr && k.pb) ? k.pr + k.pb + 8 + 20 : nullptr);
+    k.w1_n += 1u;
     pstamp(k, 1);
     publish_operands();
+    if (h1t_arrive) cluster_arrive();                                  // releases this CTA's rows of the H1^T image; the matching wait opens pass_backward
     stream_units(k, unit0, NSLOT, 8 - NSLOT);
-    if (threadIdx.x == 0) {
+    if (k.lane == 0 && k.warp < ISSUERS) {
         tc::tc_fence_after();
-        const uint32_t id = idesc(RB, NSL, 0, 0), r = smem_u32(sm + O_R), ring = smem_u32(sm + O_RING);
+        const int p = k.warp;
+        const uint32_t id = idesc(RB, NSL, 0, 0), r = smem_u32(sm + O_R) + (p == 1 ? R_LO : 0), ring = smem_u32(sm + O_RING) + (p == 2 ? 8192 : 0);
+        const uint32_t acc = k.tm + 64 * p;
         for (int c = 0; c < 8; ++c) {
             const unsigned n = k.ring_n + (unsigned)c;
             ring_wait_full(k, n);
-            const uint32_t slot = ring + (n % NSLOT) * SLOT_BYTES;
-            mma3(k.tm + T_MAIN, k.tm + T_CORR, desc_k(r + c * 8192), desc_k(r + R_LO + c * 8192), desc_k(slot), desc_k(slot + 8192), 4, 2, 2, id, c == 0);
-            tc::mma_commit(k.empty + (n % NSLOT));
+            const uint64_t a = desc_k(r + c * 8192), b = desc_k(ring + (n % NSLOT) * SLOT_BYTES);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) mma_ss(acc, a + 2 * s, b + 2 * s, id, (c == 0 && s == 0) ? 0u : 1u);
+            tc::mma_commit(k.bars + B_EMPTY + (n % NSLOT));
         }
-        tc::mma_commit(k.acc + 0);
+        tc::mma_commit(k.bars + B_ACC + 0);
     }
     __syncwarp();
     k.ring_n += 8u;
@@ -316,14 +376,15 @@ __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const floa
     const uint32_t lane_addr = k.tm + ((uint32_t)(k.sub * 32) << 16) + 32 * k.wh;
     float z[32];
     {
-        float c[32];
+        float c1[32], c2[32];
         tmem_ld32(lane_addr + T_MAIN, z);
-        tmem_ld32(lane_addr + T_CORR, c);
+        tmem_ld32(lane_addr + T_C1, c1);
+        tmem_ld32(lane_addr + T_C2, c2);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) z[e] = (z[e] + c[e]) + pc[e];
+        for (int e = 0; e < 32; ++e) z[e] = (z[e] + (c1[e] + c2[e])) + pc[e];
     }
     tc::tc_fence_before();
-    // LayerNorm2 statistics: local (mean, M2) over 32 columns, combined over the 16 contributions of the row (Chan)
+    // LayerNorm2 statistics: (mean, M2) over this thread's 32 columns, merged over the row's 16 pieces (Chan, fixed order)
     float m = 0.f;
 #pragma unroll
     for (int e = 0; e < 32; ++e) m += z[e];
@@ -335,17 +396,17 @@ __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const floa
         q = fmaf(d, d, q);
     }
     pstamp(k, 4);
-    exchange_push(k, m, q, 0.f, 0.f);
+    exchange_push(k, m, q, 0.f, 0.f, true);
     pstamp(k, 5);
     float mean = 0.f, m2 = 0.f;
 #pragma unroll
-    for (int s = 0; s < 2 * CL; ++s) mean += exchange_get(k, s).x;
-    mean *= (1.f / (2 * CL));
+    for (int s = 0; s < CL; ++s) mean += exchange_get(k, s).x;
+    mean *= (1.f / CL);
 #pragma unroll
-    for (int s = 0; s < 2 * CL; ++s) {
+    for (int s = 0; s < CL; ++s) {
         const float4 p = exchange_get(k, s);
         const float d = p.x - mean;
-        m2 += fmaf(32.f * d, d, p.y);
+        m2 += fmaf(64.f * d, d, p.y);
     }
     rstd = 1.f / sqrtf(m2 * (1.f / H2) + LN_EPS);
     float p[L::nout];
@@ -358,17 +419,18 @@ __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const floa
 #pragma unroll
         for (int o = 0; o < L::nout; ++o) p[o] = fmaf(h, pc[192 + 64 * o + e], p[o]);
     }
-    exchange_push(k, p[0], L::nout > 1 ? p[1 % L::nout] : 0.f, L::nout > 2 ? p[2 % L::nout] : 0.f, L::nout > 3 ? p[3 % L::nout] : 0.f);
+    exchange_push(k, p[0], L::nout > 1 ? p[1 % L::nout] : 0.f, L::nout > 2 ? p[2 % L::nout] : 0.f, L::nout > 3 ? p[3 % L::nout] : 0.f, false);
 #pragma unroll
     for (int o = 0; o < L::nout; ++o) out[o] = 0.f;
 #pragma unroll
-    for (int s = 0; s < 2 * CL; ++s) {
+    for (int s = 0; s < CL; ++s) {
         const float4 t = exchange_get(k, s);
         out[0] += t.x;
         if (L::nout > 1) { out[1 % L::nout] += t.y; out[2 % L::nout] += t.z; out[3 % L::nout] += t.w; }
     }
+    const float *b3 = reinterpret_cast<const float *>(sm + O_PC) + 448;
 #pragma unroll
-    for (int o = 0; o < L::nout; ++o) out[o] += tw[L::B3 + o];
+    for (int o = 0; o < L::nout; ++o) out[o] += b3[o];
     pstamp(k, 6);
 }
 
@@ -391,10 +453,10 @@ __device__ __forceinline__ void head_ln2_backward(Ctl &k, const float (&xh)[32],
         s1 += dz[e];
         s2 = fmaf(dz[e], xh[e], s2);
     }
-    exchange_push(k, s1, s2, 0.f, 0.f);
+    exchange_push(k, s1, s2, 0.f, 0.f, false);
     float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-    for (int s = 0; s < 2 * CL; ++s) {
+    for (int s = 0; s < CL; ++s) {
         const float4 p = exchange_get(k, s);
         t1 += p.x;
         t2 += p.y;
@@ -407,10 +469,11 @@ __device__ __forceinline__ void head_ln2_backward(Ctl &k, const float (&xh)[32],
 
 // column sums over the 64 rows of the block of up to 7 per-thread arrays (second-layer small parameters), staged through
 // the (dead) H1 region.  val(a, e): value of array a at this thread's column e.  Result a, column c -> dst[a * dst_stride + c].
+// Up to 8 per-row scalars (rv) are summed over the rows as well: sum j -> rdst[j] (skipped if rdst == nullptr).
 constexpr int CS_LD = 68;
-template <int NA, class F>
-__device__ __forceinline__ void column_sums(Ctl &k, F val, float *dst, int dst_stride) {
-    float *st = reinterpret_cast<float *>(k.sm + O_R);
+template <int NA, int NR, class F>
+__device__ __forceinline__ void column_sums(Ctl &k, F val, float *dst, int dst_stride, const float (&rv)[NR], float *rdst) {
+    float *st = reinterpret_cast<float *>(k.sm + O_R), *rs = st + NA * RB * CS_LD;
     if (k.act) {
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
@@ -418,29 +481,48 @@ __device__ __forceinline__ void column_sums(Ctl &k, F val, float *dst, int dst_s
 #pragma unroll
             for (int e = 0; e < 32; e += 4) st4(row + e, make_float4(val(a, e), val(a, e + 1), val(a, e + 2), val(a, e + 3)));
         }
+        if (k.wh == 0) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) rs[j * RB + k.row] = rv[j];
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < NA * NSL; i += TTHREADS) {
-        const int a = i >> 6, c = i & 63;
-        const float *col = st + a * RB * CS_LD + c;
-        float s = 0.f;
+    for (int i = threadIdx.x; i < NA * NSL + NR; i += TTHREADS) {
+        if (i < NA * NSL) {
+            const int a = i >> 6, c = i & 63;
+            const float *col = st + a * RB * CS_LD + c;
+            float s = 0.f;
 #pragma unroll 8
-        for (int r = 0; r < RB; ++r) s += col[r * CS_LD];
-        dst[a * dst_stride + c] = s;
+            for (int r = 0; r < RB; ++r) s += col[r * CS_LD];
+            dst[a * dst_stride + c] = s;
+        } else if (rdst) {
+            const int j = i - NA * NSL;
+            float s = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < RB; ++r) s += rs[j * RB + r];
+            rdst[j] = s;
+        }
     }
     __syncthreads();
 }
 
 // ---- backward GEMMs of one pass ---------------------------------------------------------------------------------------
-// dz: this thread's 32 columns of dz2.  Produces (a) the LayerNorm1-backward result of the CTA's own 8 rows (dz1 / dy1 rows
-// in the D region, see ln1_rows) and, if WITH_DW, (b) this row block's dW2 partial of the CTA's 64 features.
-struct BwdOut { float dz1[8], dy1[8], xh1[8]; int b; };   // own row (warp w <-> row 8 crank + w), lane owns n = lane + 32 j
+// dz: this thread's 32 columns of dz2.  Produces the LayerNorm1-backward result of the CTA's own 8 rows (one per warp) and,
+// if WITH_DW, this row block's dW2 partial of the CTA's 64 features (from the H1^T image h1t in L2).
+struct BwdOut { float dz1[8], dy1[8]; int b; };   // own row (warp w <-> row 8 crank + w), lane owns n = lane + 32 j
 template <class L, bool WITH_DW>
-__device__ __forceinline__ void pass_backward(Ctl &k, const float *tw, const float *imgt, int soff, const float *acts, float slope,
-                                              const float (&dz)[32], float *dh1p_unit, float *gw2p_slot, BwdOut &o) {
+__device__ __forceinline__ void pass_backward(Ctl &k, const float *tw, const float *imgt, float slope, const float (&dz)[32], const OwnRow &own,
+                                              float *dh1p_unit, const float *h1t, bool h1t_wait, float *gw2p_slot, BwdOut &o) {
     char *sm = k.sm;
     const float *units = imgt + (size_t)k.crank * 8 * 4096;          // 8 sub-units: (mb, cc, hi | lo)
+    if (WITH_DW && h1t_wait) cluster_wait();                          // every CTA's rows of the H1^T image are visible (arrive: pass_forward)
     stream_units(k, units, 0, NSLOT);
+    if (WITH_DW && threadIdx.x == PRODUCER) {                         // H1^T image of the row block -> the (dead) H1 region
+        fence_proxy_async_all();
+        mbar_expect_tx(k.bars + B_H1T, 131072);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bulk_g2s(sm + O_R + q * 32768, h1t + (size_t)q * 8192, 32768, k.bars + B_H1T);
+    }
     // (1) dz2 tile, K-major: block wh, row = batch row
     if (k.act) {
         char *dh = sm + O_D + k.wh * 8192 + (k.row >> 3) * 1024 + (k.row & 7) * 128;
@@ -457,39 +539,51 @@ __device__ __forceinline__ void pass_backward(Ctl &k, const float *tw, const flo
     pstamp(k, 0);
     publish_operands();
     stream_units(k, units, NSLOT, 8 - NSLOT);
-    // (2) dH1^T[256][64] = W2T-image[256][64 features] . dz2[64 rows][64 features]^T : M = 128 x 2, N = 64, K = 64
-    if (threadIdx.x == 0) {
+    // (2) dH1^T[256][64] = W2T-image[256][64 features] . dz2[64 rows][64 features]^T : M = 128 x 2, N = 64, K = 64.
+    //     issuer p: 0 = Ahi.Bhi, 1 = Alo.Bhi, 2 = Ahi.Blo; accumulator (mb, p); every issuer commits every sub-unit
+    if (k.lane == 0 && k.warp < ISSUERS) {
         tc::tc_fence_after();
-        const uint32_t id = idesc(128, RB, 0, 0), d = smem_u32(sm + O_D), ring = smem_u32(sm + O_RING);
+        const int p = k.warp;
+        const uint32_t id = idesc(128, RB, 0, 0), d = smem_u32(sm + O_D) + (p == 2 ? 16384 : 0), ring = smem_u32(sm + O_RING);
         for (int mb = 0; mb < 2; ++mb)
             for (int cc = 0; cc < 2; ++cc) {
-                const uint32_t acc = k.tm + T_DH + 64 * mb;
-                const uint64_t bhi = desc_k(d + cc * 8192), blo = desc_k(d + 16384 + cc * 8192);
-                unsigned n = k.ring_n + (unsigned)((mb * 2 + cc) * 2);
-                ring_wait_full(k, n);
-                uint64_t a = desc_k(ring + (n % NSLOT) * SLOT_BYTES);
-                for (int s = 0; s < 4; ++s) {
-                    mma_ss(acc, a + 2 * s, bhi + 2 * s, id, (cc == 0 && s == 0) ? 0u : 1u);
-                    mma_ss(acc, a + 2 * s, blo + 2 * s, id, 1u);
+                const uint32_t acc = k.tm + 64 * (3 * mb + p);
+                const uint64_t b = desc_k(d + cc * 8192);
+                for (int part = 0; part < 2; ++part) {
+                    const unsigned n = k.ring_n + (unsigned)(((mb * 2 + cc) * 2) + part);
+                    ring_wait_full(k, n);                              // every issuer, also for sub-units it does not read: keeps its commits in step with the ring
+                    if ((p == 1) == (part == 1)) {
+                        const uint64_t a = desc_k(ring + (n % NSLOT) * SLOT_BYTES);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) mma_ss(acc, a + 2 * s, b + 2 * s, id, (cc == 0 && s == 0) ? 0u : 1u);
+                    }
+                    tc::mma_commit(k.bars + B_EMPTY + (n % NSLOT));
                 }
-                tc::mma_commit(k.empty + (n % NSLOT));
-                n += 1u;
-                ring_wait_full(k, n);
-                a = desc_k(ring + (n % NSLOT) * SLOT_BYTES);
-                for (int s = 0; s < 4; ++s) mma_ss(acc, a + 2 * s, bhi + 2 * s, id, 1u);
-                tc::mma_commit(k.empty + (n % NSLOT));
             }
-        tc::mma_commit(k.acc + 0);
+        tc::mma_commit(k.bars + B_ACC + 0);
     }
     __syncwarp();
     k.ring_n += 8u;
     pstamp(k, 1);
-    if (WITH_DW) {
-        // (3) H1^T recomputed into the H1 region while the dH1 MMAs run
-        l1_tile<L, true>(sm, tw, soff, acts, slope);
-    }
-    pstamp(k, 2);
     acc_wait(k, 0);                                                   // dH1^T complete: the ring and the dz2 tile are idle
+    pstamp(k, 2);
+    // (3) dH1^T partial -> global [64 rows][256], coalesced along the 256 (lane = feature of H1)
+    {
+        const uint32_t lane_addr = k.tm + ((uint32_t)(k.sub * 32) << 16) + 32 * k.wh;
+        float *dst = dh1p_unit + (size_t)k.crank * RB * H1;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+            float v[32], c1[32], c2[32];
+            tmem_ld32(lane_addr + 64 * (3 * mb), v);
+            tmem_ld32(lane_addr + 64 * (3 * mb + 1), c1);
+            tmem_ld32(lane_addr + 64 * (3 * mb + 2), c2);
+            const int n = 128 * mb + 32 * k.sub + k.lane;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[(size_t)(32 * k.wh + i) * H1 + n] = v[i] + (c1[i] + c2[i]);
+        }
+        tc::tc_fence_before();
+    }
+    pstamp(k, 3);
     if (WITH_DW) {
         // (4) dz2^T tile [64 features][64 rows] into the ring region (K = batch row), re-read from the K-major tile (hi + lo is exact)
         if (k.act) {
@@ -508,95 +602,59 @@ __device__ __forceinline__ void pass_backward(Ctl &k, const float *tw, const flo
                 }
             }
         }
-        publish_operands();
+        publish_operands();                                           // also: every thread has read its dH1 accumulators (TMEM is reused)
         // (5) dW2^T[256][64] = H1^T[256][64 rows] . dz2^T[64 features][64 rows]^T : M = 128 x 2, N = 64, K = 64
-        if (threadIdx.x == 0) {
+        if (k.lane == 0 && k.warp < ISSUERS) {
+            tc::mbar_wait(k.bars + B_H1T, k.h1t_n & 1u, 950);
             tc::tc_fence_after();
-            const uint32_t id = idesc(128, NSL, 0, 0), r = smem_u32(sm + O_R), e = smem_u32(sm + O_RING);
+            const int p = k.warp;
+            const uint32_t id = idesc(128, NSL, 0, 0), r = smem_u32(sm + O_R) + (p == 1 ? R_LO : 0), e = smem_u32(sm + O_RING) + (p == 2 ? 16384 : 0);
             for (int mb = 0; mb < 2; ++mb) {
-                const uint32_t acc = k.tm + T_DW + 64 * mb;
+                const uint32_t acc = k.tm + 64 * (3 * mb + p);
                 for (int bb = 0; bb < 2; ++bb) {
-                    const uint64_t ahi = desc_k(r + bb * 32768 + mb * 16384), alo = desc_k(r + R_LO + bb * 32768 + mb * 16384);
-                    const uint64_t bhi = desc_k(e + bb * 8192), blo = desc_k(e + 16384 + bb * 8192);
-                    for (int s = 0; s < 4; ++s) {
-                        mma_ss(acc, ahi + 2 * s, bhi + 2 * s, id, (bb == 0 && s == 0) ? 0u : 1u);
-                        mma_ss(acc, alo + 2 * s, bhi + 2 * s, id, 1u);
-                        mma_ss(acc, ahi + 2 * s, blo + 2 * s, id, 1u);
-                    }
+                    const uint64_t a = desc_k(r + bb * 32768 + mb * 16384), b = desc_k(e + bb * 8192);
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) mma_ss(acc, a + 2 * s, b + 2 * s, id, (bb == 0 && s == 0) ? 0u : 1u);
                 }
             }
-            tc::mma_commit(k.acc + 1);
+            tc::mma_commit(k.bars + B_ACC + 1);
         }
         __syncwarp();
-    }
-    pstamp(k, 3);
-    // (6) dH1^T partial -> global [64 rows][256], coalesced along the 256 (lane = feature of H1)
-    {
-        const uint32_t lane_addr = k.tm + ((uint32_t)(k.sub * 32) << 16) + 32 * k.wh;
-        float *dst = dh1p_unit + (size_t)k.crank * RB * H1;
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-            float v[32];
-            tmem_ld32(lane_addr + T_DH + 64 * mb, v);
-            const int n = 128 * mb + 32 * k.sub + k.lane;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dst[(size_t)(32 * k.wh + i) * H1 + n] = v[i];
-        }
-        tc::tc_fence_before();
+        k.h1t_n += 1u;
     }
     pstamp(k, 4);
-    cluster_sync();                                                   // every CTA's partial is visible (cluster-scope release / acquire)
+    cluster_sync();                                                   // every CTA's dH1 partial is visible (cluster-scope release / acquire)
     pstamp(k, 5);
-    // (7) the CTA's own 8 rows: sum the 8 partials in a fixed order, LayerNorm1 backward (first layer recomputed for the row)
+    // (6) the CTA's own 8 rows: sum the 8 partials in a fixed order, LayerNorm1 backward (xhat1 / rstd1 kept from the forward)
     {
         const int b = 8 * k.crank + k.warp, lane = k.lane;
         o.b = b;
         float dh[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) dh[j] = 0.f;
+#pragma unroll
         for (int src = 0; src < CL; ++src) {
             const float *p = dh1p_unit + ((size_t)src * RB + b) * H1;
 #pragma unroll
             for (int j = 0; j < 8; ++j) dh[j] += __ldcg(p + lane + 32 * j);
         }
-        const float *xs = reinterpret_cast<const float *>(sm + O_X);
-        float z[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) z[j] = tw[L::B1 + lane + 32 * j];
-#pragma unroll
-        for (int kk = 0; kk < L::k0; ++kk) {
-            const float xv = kk < S ? xs[b * 32 + soff + kk] : (acts ? acts[b * 4 + (kk - S)] : xs[b * 32 + kk]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) z[j] = fmaf(xv, tw[L::W1T + kk * H1 + lane + 32 * j], z[j]);
-        }
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += z[j];
-        const float mean = warp_sum(s) * (1.f / H1);
-        float v = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float d = z[j] - mean;
-            v = fmaf(d, d, v);
-        }
-        const float rstd = 1.f / sqrtf(warp_sum(v) * (1.f / H1) + LN_EPS);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o.xh1[j] = (z[j] - mean) * rstd;
-        ln1_backward<L>(tw, dh, o.xh1, rstd, slope, lane, o.dz1, o.dy1);
+        ln1_backward<L>(tw, dh, own.xh1, own.rstd1, slope, lane, o.dz1, o.dy1);
     }
     pstamp(k, 6);
     if (WITH_DW) {
-        // (8) dW2^T partial of this row block -> global [512][256] slot, rows 64 crank .. + 63
+        // (7) dW2^T partial of this row block -> global [512][256] slot, rows 64 crank .. + 63
         acc_wait(k, 1);
         const uint32_t lane_addr = k.tm + ((uint32_t)(k.sub * 32) << 16) + 32 * k.wh;
         float *dst = gw2p_slot + (size_t)NSL * k.crank * H1;
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
-            float v[32];
-            tmem_ld32(lane_addr + T_DW + 64 * mb, v);
+            float v[32], c1[32], c2[32];
+            tmem_ld32(lane_addr + 64 * (3 * mb), v);
+            tmem_ld32(lane_addr + 64 * (3 * mb + 1), c1);
+            tmem_ld32(lane_addr + 64 * (3 * mb + 2), c2);
             const int kcol = 128 * mb + 32 * k.sub + k.lane;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dst[(size_t)(32 * k.wh + i) * H1 + kcol] = v[i];
+            for (int i = 0; i < 32; ++i) dst[(size_t)(32 * k.wh + i) * H1 + kcol] = v[i] + (c1[i] + c2[i]);
         }
         tc::tc_fence_before();
     }
@@ -606,14 +664,14 @@ __device__ __forceinline__ void pass_backward(Ctl &k, const float *tw, const flo
 
 // first-layer parameter gradients of the CTA's 8 rows (one per warp) -> partial slot (L layout, first-layer section)
 template <class L>
-__device__ __forceinline__ void ln1_param_partials(Ctl &k, const BwdOut &o, int soff, const float *acts, float *part) {
+__device__ __forceinline__ void ln1_param_partials(Ctl &k, const BwdOut &o, const OwnRow &own, int soff, const float *acts, float *part) {
     float *t_dz = reinterpret_cast<float *>(k.sm + O_D), *t_dg = t_dz + 8 * H1, *t_dbe = t_dg + 8 * H1, *t_x = t_dbe + 8 * H1;   // [8][256] x 3 + [8][32]
     const float *xs = reinterpret_cast<const float *>(k.sm + O_X);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int n = k.lane + 32 * j;
         t_dz[k.warp * H1 + n] = o.dz1[j];
-        t_dg[k.warp * H1 + n] = o.dy1[j] * o.xh1[j];
+        t_dg[k.warp * H1 + n] = o.dy1[j] * own.xh1[j];
         t_dbe[k.warp * H1 + n] = o.dy1[j];
     }
     if (k.lane < L::k0) t_x[k.warp * 32 + k.lane] = k.lane < S ? xs[o.b * 32 + soff + k.lane] : (acts ? acts[o.b * 4 + (k.lane - S)] : xs[o.b * 32 + k.lane]);
@@ -645,76 +703,110 @@ __device__ __forceinline__ void ln1_param_partials(Ctl &k, const BwdOut &o, int 
 __device__ __forceinline__ void gather_rows(Ctl &k, const AgentCtx &c, const hirl_step_t &st, int step, int r, bool bc_rows) {
     float *xs = reinterpret_cast<float *>(k.sm + O_X);
     const int32_t *ion = c.idx_online + (size_t)step * c.B, *iex = c.idx_expert + (size_t)step * c.B, *ibc = c.idx_bc + (size_t)step * c.B;
-    for (int i = k.warp; i < RB; i += 8) {
-        int b = RB * r + i;
+    const float *src[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                                     // all index loads, then all row loads: independent round trips in flight
+        int b = RB * r + k.warp + 8 * i;
         if (b >= c.B) b = c.B - 1;                                   // padded rows repeat the last row; their contributions are masked
-        float w;
-        if (bc_rows) {
-            const float *src = c.bctab + (size_t)__ldg(ibc + b) * BCW;
-            w = k.lane < BCW ? __ldg(src + k.lane) : 0.f;
-        } else {
-            const float *src = b < st.n_online ? c.online + (size_t)__ldg(ion + b) * ROW : c.expert + (size_t)__ldg(iex + (b - st.n_online)) * ROW;
-            w = __ldg(src + k.lane);
-        }
-        xs[i * 32 + k.lane] = w;
+        if (bc_rows) src[i] = c.bctab + (size_t)__ldg(ibc + b) * BCW;
+        else src[i] = b < st.n_online ? c.online + (size_t)__ldg(ion + b) * ROW : c.expert + (size_t)__ldg(iex + (b - st.n_online)) * ROW;
     }
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = (!bc_rows || k.lane < BCW) ? __ldg(src[i] + k.lane) : 0.f;
+    __syncthreads();                                                  // previous readers of the row buffer are done
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xs[(k.warp + 8 * i) * 32 + k.lane] = w[i];
     __syncthreads();
-}
-
-// sum over the 64 rows of a per-row value held by the (wh == 0) row threads, in row order; result valid in thread 0
-__device__ __forceinline__ float row_sum(Ctl &k, float v, int slot) {
-    float *red = reinterpret_cast<float *>(k.sm + O_RED) + 64 * slot;
-    if (k.act && k.wh == 0) red[k.row] = v;
-    __syncthreads();
-    float s = 0.f;
-    if (threadIdx.x == 0)
-        for (int r = 0; r < RB; ++r) s += red[r];
-    __syncthreads();
-    return s;
 }
 
 // ---- Adam over one network (all CTAs of the grid), fixed-order sums of the partials, operand images ------------------
 //   w2parts [tower][nparts][H2*H1]; part: slots of L::SMALL floats, slot s of tower t at ((s * ntowers) + t) * L::SMALL;
-//   first-layer entries are summed over slots 0 .. n1-1, second-layer small entries over slots 0, 8, 16, .. (nq of them)
-template <class L>
-__device__ __forceinline__ void adam_tcc(int rank, int size, int ntowers, float *w, float *gw, const float *w2parts, int nparts, float *m, float *v,
+//   first-layer entries are summed over slots 0 .. n1-1, second-layer small entries over slots 0, 8, 16, .. (nq of them).
+//   W2 is processed in tiles of [32 features][16 k]: reads / arena writes / forward image coalesced along k, the
+//   input-gradient image (features contiguous) through a shared-memory transpose.
+template <class L, int NPARTS>
+__device__ __forceinline__ void adam_tcc(Ctl &k, int rank, int size, int ntowers, float *w, float *gw, const float *w2parts, float *m, float *v,
                                          const float *part, int n1, int nq, float neg_step, float bc2_sqrt, float *img, float *imgt,
                                          float *target, float *timg, bool polyak, float tau, float omt) {
-    const int total = ntowers * L::SIZE;
-    for (int e = rank * TTHREADS + threadIdx.x; e < total; e += size * TTHREADS) {
-        const int tower = e / L::SIZE, off = e - tower * L::SIZE;
-        const bool in_w2 = off >= L::W2 && off < L::B2;
-        float g;
-        if (in_w2) {
-            const float *p0 = w2parts + (size_t)tower * nparts * H2 * H1 + (off - L::W2);
-            g = __ldcg(p0);
-            for (int q = 1; q < nparts; ++q) g += __ldcg(p0 + (size_t)q * H2 * H1);
-        } else {
-            const int si = L::small_index(off);
-            const bool first = off < L::W2;
-            const int ns = first ? n1 : nq, stride = first ? 1 : CL;
-            g = 0.f;
-            for (int s = 0; s < ns; ++s) g += __ldcg(part + ((size_t)(s * stride) * ntowers + tower) * L::SMALL + si);
-        }
+    // (a) everything but W2
+    const int nsmall = ntowers * L::SMALL;
+    for (int i = rank * TTHREADS + threadIdx.x; i < nsmall; i += size * TTHREADS) {
+        const int tower = i / L::SMALL, si = i - tower * L::SMALL;
+        const int off = si < L::W2 ? si : si + H2 * H1, e = tower * L::SIZE + off;
+        const bool first = off < L::W2;
+        const int ns = first ? n1 : nq, stride = first ? 1 : CL;
+        const float *p0 = part + (size_t)tower * L::SMALL + si;
+        const size_t ps = (size_t)stride * ntowers * L::SMALL;
+        float g = 0.f;
+#pragma unroll 8
+        for (int s = 0; s < ns; ++s) g += __ldcg(p0 + s * ps);
         gw[e] = g;
         float wv = w[e], mv = m[e], vv = v[e];
         adam_elem(g, wv, mv, vv, neg_step, bc2_sqrt);
         w[e] = wv; m[e] = mv; v[e] = vv;
-        float tv = 0.f;
-        if (polyak) { tv = polyak_elem(target[e], wv, tau, omt); target[e] = tv; }
-        if (in_w2) {
-            const int i = off - L::W2, n = i / H1, kk = i - n * H1;
-            const float hi = tf32_hi(wv);
-            float *f = img + (size_t)tower * IMG_FWD + img_fwd_index(n, kk);
-            f[0] = hi; f[2048] = wv - hi;
-            if (imgt) {
-                float *t = imgt + (size_t)tower * IMG_T + img_t_index(n, kk);
-                t[0] = hi; t[4096] = wv - hi;
+        if (polyak) target[e] = polyak_elem(target[e], wv, tau, omt);
+    }
+    // (b) W2 tiles, up to 3 tiles' loads in flight per CTA (the loop is bound by L2 round trips, not by arithmetic)
+    float *ts = reinterpret_cast<float *>(k.sm + O_R);                 // [32 features][17]
+    const int tiles = ntowers * 16 * 16, tk = threadIdx.x & 15, tn = threadIdx.x >> 4;
+    constexpr int UB = 3;
+    for (int t0 = rank; t0 < tiles; t0 += UB * size) {
+        float g[UB][2], wv[UB][2], mv[UB][2], vv[UB][2], tv[UB][2];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int t = t0 + u * size;
+            if (t < tiles) {
+                const int tower = t >> 8, nb = (t >> 4) & 15, kb = t & 15;
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int n = 32 * nb + tn + 16 * it, kk = 16 * kb + tk, i = n * H1 + kk, e = tower * L::SIZE + L::W2 + i;
+                    const float *p0 = w2parts + (size_t)tower * NPARTS * H2 * H1 + i;
+                    float s = __ldcg(p0);
+#pragma unroll
+                    for (int q = 1; q < NPARTS; ++q) s += __ldcg(p0 + (size_t)q * H2 * H1);
+                    g[u][it] = s;
+                    wv[u][it] = w[e]; mv[u][it] = m[e]; vv[u][it] = v[e];
+                    tv[u][it] = polyak ? target[e] : 0.f;
+                }
             }
-            if (polyak) {
-                const float th = tf32_hi(tv);
-                float *f2 = timg + (size_t)tower * IMG_FWD + img_fwd_index(n, kk);
-                f2[0] = th; f2[2048] = tv - th;
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int t = t0 + u * size;
+            if (t < tiles) {
+                const int tower = t >> 8, nb = (t >> 4) & 15, kb = t & 15;
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const int n = 32 * nb + tn + 16 * it, kk = 16 * kb + tk, i = n * H1 + kk, e = tower * L::SIZE + L::W2 + i;
+                    gw[e] = g[u][it];
+                    adam_elem(g[u][it], wv[u][it], mv[u][it], vv[u][it], neg_step, bc2_sqrt);
+                    w[e] = wv[u][it]; m[e] = mv[u][it]; v[e] = vv[u][it];
+                    const float hi = tf32_hi(wv[u][it]);
+                    float *f = img + (size_t)tower * IMG_FWD + img_fwd_index(n, kk);
+                    f[0] = hi; f[2048] = wv[u][it] - hi;
+                    if (polyak) {
+                        const float tnew = polyak_elem(tv[u][it], wv[u][it], tau, omt);
+                        target[e] = tnew;
+                        const float th = tf32_hi(tnew);
+                        float *f2 = timg + (size_t)tower * IMG_FWD + img_fwd_index(n, kk);
+                        f2[0] = th; f2[2048] = tnew - th;
+                    }
+                }
+                if (imgt) {
+                    __syncthreads();
+                    ts[tn * 17 + tk] = wv[u][0];
+                    ts[(tn + 16) * 17 + tk] = wv[u][1];
+                    __syncthreads();
+                    const int n2 = threadIdx.x & 31, k2 = threadIdx.x >> 5;   // 32 features x 8 k per sweep
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        const int kk = 16 * kb + k2 + 8 * it, n = 32 * nb + n2;
+                        const float x = ts[n2 * 17 + k2 + 8 * it], hi = tf32_hi(x);
+                        float *tq = imgt + (size_t)tower * IMG_T + img_t_index(n, kk);
+                        tq[0] = hi; tq[4096] = x - hi;
+                    }
+                }
             }
         }
     }
@@ -755,7 +847,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
     extern __shared__ float4 smem4[];
     __shared__ AgentCtx ctx;
     __shared__ hirl_step_t st;
-    __shared__ uint64_t bars[2 * NSLOT + 2];
+    __shared__ uint64_t bars[N_BARS];
     __shared__ uint32_t tmem_slot;
     {
         const int *src = reinterpret_cast<const int *>(&Lc.agent);
@@ -763,18 +855,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
         for (int i = threadIdx.x; i < (int)(sizeof(AgentCtx) / sizeof(int)); i += TTHREADS) dst[i] = src[i];
     }
     Ctl k;
-    k.sm = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem4) + 1023) & ~(uintptr_t)1023);
-    k.full = bars; k.empty = bars + NSLOT; k.acc = bars + 2 * NSLOT;
+    k.pad = (1024u - (smem_u32(smem4) & 1023u)) & 1023u;
+    k.sm = reinterpret_cast<char *>(smem4) + k.pad;           // plain pointer arithmetic on the shared symbol keeps the address space
+    k.bars = bars;
     k.crank = (int)cluster_ctarank(); k.cid = (int)cluster_id_x(); k.ncl = Lc.ncl;
     k.warp = threadIdx.x >> 5; k.lane = threadIdx.x & 31; k.sub = k.warp & 3; k.wh = k.warp >> 2;
     k.act = k.lane < 16; k.row = 16 * k.sub + (k.lane & 15);
-    k.ring_n = 0u; k.acc_n[0] = k.acc_n[1] = 0u; k.xr = 0u;
+    k.ring_n = 0u; k.acc_n[0] = k.acc_n[1] = 0u; k.w1_n = k.h1t_n = 0u; k.xr = 0u;
     k.flags = Lc.bar_flags;
     k.gen = ld_relaxed_u32(k.flags + k.cid * FLAG_STRIDE);
     k.pr = nullptr; k.pb = 0;
     if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot);
     if (threadIdx.x == 32) {
-        for (int i = 0; i < 2 * NSLOT + 2; ++i) tc::mbar_init(bars + i, 1);
+        for (int i = 0; i < N_BARS; ++i) tc::mbar_init(bars + i, (i >= B_EMPTY && i < B_ACC + 2) ? ISSUERS : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc::tc_fence_before();
@@ -784,7 +877,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
     const AgentCtx &c = ctx;
     k.pflags = c.tcc.pflags;
     k.pgen = ld_relaxed_u32(c.tcc.gen_ctr);
-    cluster_sync();                                                    // peers' shared memory is live before anybody pushes into it
+    cluster_sync();                                                    // peers' shared memory and barriers are live before anybody pushes
     const float slope = slope_of(c);
     const int B = c.B, nrb = (B + RB - 1) / RB;
     float *acts = reinterpret_cast<float *>(k.sm + O_ACT), *gpi = reinterpret_cast<float *>(k.sm + O_GPI);
@@ -808,11 +901,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
             gather_rows(k, c, st, step, r, false);
             stamp(k, 1);
             float xh[32], rstd;
+            OwnRow own;
             // target actor on next_state (HIRL.py:264) -> a' (HIRL.py:265-267)
             {
                 float out[A];
                 k.pb = 20;
-                pass_forward<ActorL>(k, c.tactor, c.tcc.img_tactor, SA, nullptr, slope, xh, rstd, out);
+                pass_forward<ActorL>(k, c.tactor, c.tcc.img_tactor, SA, nullptr, slope, nullptr, false, xh, rstd, out, own);
                 k.pb = 0;
                 if (k.act && k.wh == 0) {
 #pragma unroll
@@ -821,14 +915,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         acts[k.row * 4 + j] = fminf(fmaxf(tanhf(out[j]) + nz, -1.f), 1.f);
                     }
                 }
-                __syncthreads();
             }
             stamp(k, 2);
             // target critic tower t on (next_state, a') (HIRL.py:270)
             float tq_own;
             {
                 float out[1];
-                pass_forward<CriticL>(k, c.tcritic + t * CriticL::SIZE, c.tcc.img_tcritic + (size_t)t * IMG_FWD, SA, acts, slope, xh, rstd, out);
+                pass_forward<CriticL>(k, c.tcritic + t * CriticL::SIZE, c.tcc.img_tcritic + (size_t)t * IMG_FWD, SA, acts, slope, nullptr, false, xh, rstd, out, own);
                 tq_own = out[0];
                 if (k.crank == 0 && k.act && k.wh == 0) c.tcc.TQX[(r * 2 + t) * RB + k.row] = tq_own;
                 flag_publish(k, PF_TQ + r * 2 + t, fgen);
@@ -836,8 +929,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
             stamp(k, 3);
             // critic tower t on (state, action) (HIRL.py:277)
             float q1[1];
+            float *h1t = c.tcc.H1TI + (size_t)unit * H1T_FLOATS;
             k.pb = 28;
-            pass_forward<CriticL>(k, c.critic + t * CriticL::SIZE, c.tcc.img_critic + (size_t)t * IMG_FWD, 0, nullptr, slope, xh, rstd, q1);
+            pass_forward<CriticL>(k, c.critic + t * CriticL::SIZE, c.tcc.img_critic + (size_t)t * IMG_FWD, 0, nullptr, slope, h1t, true, xh, rstd, q1, own);
             k.pb = 0;
             stamp(k, 4);
             flag_wait(k, PF_TQ + r * 2 + (1 - t), fgen);
@@ -853,36 +947,35 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                 c.sc.TQ[(size_t)t * B + bg] = tq_own;
                 if (t == 0) c.sc.Y[bg] = y;
             }
-            {
-                const float ls = row_sum(k, valid ? delta * delta : 0.f, 0);
-                if (k.crank == 0 && threadIdx.x == 0) c.tcc.LPT[unit] = ls;
-            }
             float dout[1] = {valid ? (2.f / (float)B) * delta : 0.f};                                          // mse_loss backward, mean reduction
             float dz[32], dy[32], h[32];
             head_ln2_backward<CriticL>(k, xh, rstd, dout, slope, dz, dy, h);
-            __syncthreads();                                                                                   // exchange slots (D region) read by everybody
-            // second-layer small parameters of this CTA's 64 features: db2, dgamma2, dbeta2, dW3 (+ db3 by CTA 0)
+            // second-layer small parameters of this CTA's 64 features: db2, dgamma2, dbeta2, dW3 (+ db3, loss by CTA 0)
             float *part = c.tcc.PARTC + ((size_t)(unit >> 1) * CL * 2 + t) * CriticL::SMALL;                   // slot 8 r (+ tower)
             {
                 float *p2 = part + CriticL::small_index(CriticL::B2) + NSL * k.crank;
                 const float dq = dout[0];
-                column_sums<4>(k, [&](int a, int e) { return a == 0 ? dz[e] : a == 1 ? dy[e] * xh[e] : a == 2 ? dy[e] : dq * h[e]; }, p2, H2);
-                const float sdq = row_sum(k, dq, 1);
-                if (k.crank == 0 && threadIdx.x == 0) part[CriticL::small_index(CriticL::B3)] = sdq;
+                const float rv[2] = {dq, valid ? delta * delta : 0.f};
+                column_sums<4, 2>(k, [&](int a, int e) { return a == 0 ? dz[e] : a == 1 ? dy[e] * xh[e] : a == 2 ? dy[e] : dq * h[e]; }, p2, H2, rv,
+                                  k.crank == 0 ? c.tcc.RSUM + 8 * unit : nullptr);
+                if (k.crank == 0 && threadIdx.x == 0) {
+                    part[CriticL::small_index(CriticL::B3)] = c.tcc.RSUM[8 * unit];
+                    c.tcc.LPT[unit] = c.tcc.RSUM[8 * unit + 1];
+                }
             }
             stamp(k, 37);
             BwdOut bo;
             k.pb = 40;
-            pass_backward<CriticL, true>(k, c.critic + t * CriticL::SIZE, c.tcc.imgt_critic + (size_t)t * IMG_T, 0, nullptr, slope, dz,
-                                         c.tcc.DH1P + (size_t)unit * CL * RB * H1, c.tcc.GW2PC + ((size_t)t * MAX_RB + r) * H2 * H1, bo);
+            pass_backward<CriticL, true>(k, c.critic + t * CriticL::SIZE, c.tcc.imgt_critic + (size_t)t * IMG_T, slope, dz, own,
+                                         c.tcc.DH1P + (size_t)unit * CL * RB * H1, h1t, true, c.tcc.GW2PC + ((size_t)t * MAX_RB + r) * H2 * H1, bo);
             k.pb = 0;
-            ln1_param_partials<CriticL>(k, bo, 0, nullptr, c.tcc.PARTC + ((size_t)(r * CL + k.crank) * 2 + t) * CriticL::SMALL);
+            ln1_param_partials<CriticL>(k, bo, own, 0, nullptr, c.tcc.PARTC + ((size_t)(r * CL + k.crank) * 2 + t) * CriticL::SMALL);
             stamp(k, 5);
         }
         grid_sync(k);
         stamp(k, 6);
         // =============================== phase B: critic Adam ===============================
-        adam_tcc<CriticL>(grank, gsize, 2, c.critic, c.g_critic, c.tcc.GW2PC, MAX_RB, c.m_critic, c.v_critic, c.tcc.PARTC, CL * nrb, nrb,
+        adam_tcc<CriticL, MAX_RB>(k, grank, gsize, 2, c.critic, c.g_critic, c.tcc.GW2PC, c.m_critic, c.v_critic, c.tcc.PARTC, CL * nrb, nrb,
                           st.critic_neg_step, st.critic_bc2_sqrt, c.tcc.img_critic, c.tcc.imgt_critic, nullptr, nullptr, false, 0.f, 0.f);
         if (grank == gsize - 1 && threadIdx.x == 0) {
             float s0 = 0.f, s1 = 0.f;
@@ -917,11 +1010,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                 const int bg = RB * r + k.row;
                 const bool valid = bg < B;
                 float xh[32], rstd;
+                OwnRow own, own_q;
+                float *h1t = c.tcc.H1TI + (size_t)k.cid * H1T_FLOATS;
+                float *rsum = c.tcc.RSUM + 8 * k.cid;
                 if (role == 0) {
                     // ---- role A: pi = actor(s), rl_Q = Q1(s, pi) with the updated critic (HIRL.py:295-297)
                     gather_rows(k, c, st, step, r, false);
                     float out[A], pi[A];
-                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, xh, rstd, out);
+                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, h1t, false, xh, rstd, out, own);   // the Q pass' cluster barriers release the image
 #pragma unroll
                     for (int j = 0; j < A; ++j) pi[j] = tanhf(out[j]);
                     if (k.act && k.wh == 0) {
@@ -938,10 +1034,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         for (int e = 0; e < 32; e += 4) st4(xs2 + e, make_float4(xh[e], xh[e + 1], xh[e + 2], xh[e + 3]));
                     }
                     const float rstd_a = rstd;
-                    __syncthreads();
                     stamp(k, 10);
                     float q[1];
-                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, xh, rstd, q);
+                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, nullptr, false, xh, rstd, q, own_q);
                     stamp(k, 11);
                     float softq = 0.f;
                     if (soft) {
@@ -952,19 +1047,18 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         c.sc.RLQ[bg] = q[0];
                         if (soft) c.sc.SOFTQ[bg] = softq;
                     }
-                    {
-                        const float cnt = row_sum(k, (valid && soft && softq > q[0]) ? 1.f : 0.f, 0);          // HIRL.py:303
-                        const float sq = row_sum(k, valid ? q[0] : 0.f, 1);
-                        if (k.crank == 0 && threadIdx.x == 0) { c.tcc.CNT[2 * r] = cnt; c.tcc.CNT[2 * r + 1] = sq; }
-                        flag_publish(k, PF_CNT + r, fgen);
-                    }
                     // backward of rl_loss = -mean(Q1) to the action input; (1 - w) is applied where it meets the actor
                     float dout[1] = {valid ? -1.f / (float)B : 0.f};
                     float dz[32], dy[32], h[32];
                     head_ln2_backward<CriticL>(k, xh, rstd, dout, slope, dz, dy, h);
-                    __syncthreads();
+                    {
+                        const float rv[2] = {(valid && soft && softq > q[0]) ? 1.f : 0.f, valid ? q[0] : 0.f};    // HIRL.py:303, :297
+                        column_sums<0, 2>(k, [&](int, int) { return 0.f; }, nullptr, 0, rv, k.crank == 0 ? rsum : nullptr);
+                        if (k.crank == 0 && threadIdx.x == 0) { c.tcc.CNT[2 * r] = rsum[0]; c.tcc.CNT[2 * r + 1] = rsum[1]; }
+                        flag_publish(k, PF_CNT + r, fgen);
+                    }
                     BwdOut bo;
-                    pass_backward<CriticL, false>(k, c.critic, c.tcc.imgt_critic, 0, acts, slope, dz, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, nullptr, bo);
+                    pass_backward<CriticL, false>(k, c.critic, c.tcc.imgt_critic, slope, dz, own_q, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, nullptr, false, nullptr, bo);
                     {
                         float g[A];
 #pragma unroll
@@ -1002,26 +1096,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         dpre[j] = dpi * (1.f - pi[j] * pi[j]);
                     }
                     head_ln2_backward<ActorL>(k, xh, rstd_a, dpre, slope, dz, dy, h);
-                    __syncthreads();
                     float *part = c.tcc.PARTA + (size_t)(r * CL) * ActorL::SMALL;                               // branch 0, slot 8 r
                     {
                         float *p2 = part + ActorL::small_index(ActorL::B2) + NSL * k.crank;
-                        column_sums<7>(k, [&](int a, int e) { return a == 0 ? dz[e] : a == 1 ? dy[e] * xh[e] : a == 2 ? dy[e] : dpre[a - 3] * h[e]; }, p2, H2);
-#pragma unroll
-                        for (int j = 0; j < A; ++j) {
-                            const float sd = row_sum(k, dpre[j], 1);
-                            if (k.crank == 0 && threadIdx.x == 0) part[ActorL::small_index(ActorL::B3) + j] = sd;
-                        }
+                        column_sums<7, 4>(k, [&](int a, int e) { return a == 0 ? dz[e] : a == 1 ? dy[e] * xh[e] : a == 2 ? dy[e] : dpre[a - 3] * h[e]; }, p2, H2,
+                                          dpre, k.crank == 0 ? part + ActorL::small_index(ActorL::B3) : nullptr);
                     }
-                    pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, 0, nullptr, slope, dz, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1,
+                    pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, slope, dz, own, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, h1t, false,
                                                 c.tcc.GW2PA + (size_t)r * H2 * H1, bo);
-                    ln1_param_partials<ActorL>(k, bo, 0, nullptr, c.tcc.PARTA + (size_t)(r * CL + k.crank) * ActorL::SMALL);
+                    ln1_param_partials<ActorL>(k, bo, own, 0, nullptr, c.tcc.PARTA + (size_t)(r * CL + k.crank) * ActorL::SMALL);
                     stamp(k, 14);
                 } else if (role == 1) {
                     // ---- role S: a_bc = bc_actor(s), soft_Q = Q1(s, a_bc) (HIRL.py:300-302)
                     gather_rows(k, c, st, step, r, false);
                     float out[A];
-                    pass_forward<ActorL>(k, c.bc, c.tcc.img_bc, 0, nullptr, slope, xh, rstd, out);
+                    pass_forward<ActorL>(k, c.bc, c.tcc.img_bc, 0, nullptr, slope, nullptr, false, xh, rstd, out, own);
                     if (k.act && k.wh == 0) {
 #pragma unroll
                         for (int j = 0; j < A; ++j) {
@@ -1030,33 +1119,31 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                             if (k.crank == 0 && valid) c.sc.ABC[(size_t)bg * A + j] = a;
                         }
                     }
-                    __syncthreads();
                     float q[1];
-                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, xh, rstd, q);
+                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, nullptr, false, xh, rstd, q, own_q);
                     if (k.crank == 0 && k.act && k.wh == 0) c.tcc.SOFTQX[r * RB + k.row] = q[0];
                     flag_publish(k, PF_SOFTQ + r, fgen);
                 } else {
                     // ---- role AB: pi_bc = actor(s_bc), cloning loss (HIRL.py:310-319), actor backward of the BC branch
                     gather_rows(k, c, st, step, r, true);
                     float out[A], pi[A], diff[A];
-                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, xh, rstd, out);
+                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, h1t, true, xh, rstd, out, own);
                     const float *xs = reinterpret_cast<const float *>(k.sm + O_X);
-                    float sq = 0.f, fire = 0.f;
+                    float sq = 0.f;
 #pragma unroll
                     for (int j = 0; j < A; ++j) {
                         pi[j] = tanhf(out[j]);
                         diff[j] = pi[j] - xs[k.row * 32 + S + j];
                         sq = fmaf(diff[j], diff[j], sq);
                     }
-                    fire = diff[3] * diff[3];
+                    const float fire = diff[3] * diff[3];
                     if (k.crank == 0 && k.act && k.wh == 0 && valid) {
 #pragma unroll
                         for (int j = 0; j < A; ++j) c.sc.PIB[(size_t)bg * A + j] = pi[j];
                     }
                     {
-                        const float s0 = row_sum(k, valid ? sq : 0.f, 0);
-                        const float s1 = row_sum(k, valid ? fire : 0.f, 1);
-                        if (k.crank == 0 && threadIdx.x == 0) { c.tcc.LPT[8 + 2 * r] = s0; c.tcc.LPT[8 + 2 * r + 1] = s1; }
+                        const float rv[2] = {valid ? sq : 0.f, valid ? fire : 0.f};
+                        column_sums<0, 2>(k, [&](int, int) { return 0.f; }, nullptr, 0, rv, k.crank == 0 ? c.tcc.LPT + 8 + 2 * r : nullptr);
                     }
                     resolve_weight();
                     const float bc_scale = bw.w * c.loss_lambda;
@@ -1068,27 +1155,22 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                     }
                     float dz[32], dy[32], h[32];
                     head_ln2_backward<ActorL>(k, xh, rstd, dpre, slope, dz, dy, h);
-                    __syncthreads();
                     float *part = c.tcc.PARTA + (size_t)((MAX_RB + r) * CL) * ActorL::SMALL;                    // branch 1, slot 8 (4 + r)
                     {
                         float *p2 = part + ActorL::small_index(ActorL::B2) + NSL * k.crank;
-                        column_sums<7>(k, [&](int a, int e) { return a == 0 ? dz[e] : a == 1 ? dy[e] * xh[e] : a == 2 ? dy[e] : dpre[a - 3] * h[e]; }, p2, H2);
-#pragma unroll
-                        for (int j = 0; j < A; ++j) {
-                            const float sd = row_sum(k, dpre[j], 1);
-                            if (k.crank == 0 && threadIdx.x == 0) part[ActorL::small_index(ActorL::B3) + j] = sd;
-                        }
+                        column_sums<7, 4>(k, [&](int a, int e) { return a == 0 ? dz[e] : a == 1 ? dy[e] * xh[e] : a == 2 ? dy[e] : dpre[a - 3] * h[e]; }, p2, H2,
+                                          dpre, k.crank == 0 ? part + ActorL::small_index(ActorL::B3) : nullptr);
                     }
                     BwdOut bo;
-                    pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, 0, nullptr, slope, dz, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1,
+                    pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, slope, dz, own, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, h1t, true,
                                                 c.tcc.GW2PA + (size_t)(MAX_RB + r) * H2 * H1, bo);
-                    ln1_param_partials<ActorL>(k, bo, 0, nullptr, c.tcc.PARTA + (size_t)((MAX_RB + r) * CL + k.crank) * ActorL::SMALL);
+                    ln1_param_partials<ActorL>(k, bo, own, 0, nullptr, c.tcc.PARTA + (size_t)((MAX_RB + r) * CL + k.crank) * ActorL::SMALL);
                 }
             }
             grid_sync(k);
             stamp(k, 15);
             // =============================== phase D: actor Adam, Polyak, scalars ===============================
-            adam_tcc<ActorL>(grank, gsize, 1, c.actor, c.g_actor, c.tcc.GW2PA, 2 * MAX_RB, c.m_actor, c.v_actor, c.tcc.PARTA, 2 * MAX_RB * CL, 2 * MAX_RB,
+            adam_tcc<ActorL, 2 * MAX_RB>(k, grank, gsize, 1, c.actor, c.g_actor, c.tcc.GW2PA, c.m_actor, c.v_actor, c.tcc.PARTA, 2 * MAX_RB * CL, 2 * MAX_RB,
                              st.actor_neg_step, st.actor_bc2_sqrt, c.tcc.img_actor, c.tcc.imgt_actor, c.tactor, c.tcc.img_tactor, do_polyak, tau, omt);
             if (do_polyak) polyak_tcc<CriticL>(grank, gsize, 2, c.critic, c.tcritic, c.tcc.img_tcritic, tau, omt);
             if (grank == gsize - 1 && threadIdx.x == 0) {
@@ -1121,7 +1203,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
     }
     if (grank == 0 && threadIdx.x == 0) *c.tcc.gen_ctr = k.pgen + (unsigned)Lc.k_steps;
     tc::tc_fence_before();
-    __syncthreads();
+    cluster_sync();                                                    // nobody leaves while a peer may still push into its shared memory
     if (threadIdx.x < 32) tc::tmem_dealloc(k.tm);
 }
 

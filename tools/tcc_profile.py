@@ -57,6 +57,10 @@ def main():
                 continue
             print(f"  {label:66s} {us(p[i] - prev):8.2f} us   (t = {us(p[i] - p[0]):8.2f})")
             prev = p[i]
+        for base in (20, 28):
+            d = p[base + 28: base + 35]
+            if d[0]:
+                print(f"    l1_tile @{base}: W1 landed +{us(d[0] - p[base]):.2f} | grp0 fma {us(d[1] - d[0]):.2f} stats {us(d[2] - d[1]):.2f} store {us(d[3] - d[2]):.2f} | grp1 fma {us(d[4] - d[3]):.2f} stats {us(d[5] - d[4]):.2f} store {us(d[6] - d[5]):.2f}")
         for base, name, labels, start in ((20, "target actor pass", FWD, p[1]), (28, "critic forward pass", FWD, p[3]), (40, "critic backward", BWD, p[37])):
             print(f"    -- inside the {name}:")
             prev = start
