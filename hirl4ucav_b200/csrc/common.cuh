@@ -126,7 +126,10 @@ struct TccPtrs {
     float *PARTA;    // [2 branches * 4 row blocks * 8 CTAs][ActorL::SMALL]
     float *TQX;      // [4][2][64] target Q of a tower, exchanged between the two tower clusters of a row block
     float *SOFTQX;   // [4][64]
+    float *APX;      // [4][64][4] a' of a row block, published by its target-actor unit
+    float *XHP;      // [8 units][64][H2] normalised second-layer rows of the critic forward pass, parked while the target tower runs
     float *XH2S;     // [4][64][H2] normalised second-layer rows of the actor pass, parked while the Q pass runs
+    float *H1I;      // [clusters][32768] first-layer activation tile (hi | lo) of the pass a cluster is executing: written row-wise by its 8 CTAs, multicast back
     float *H1TI;     // [units][32768] transposed first-layer activation tiles (hi | lo) of back-propagated passes
     float *RSUM;     // [units][8] per-unit row sums (scratch)
     float *LPT;      // [16] per-unit loss partials: critic [r][t] at 0..7, cloning (sum sq, fire sq) at 8 + 2 r

@@ -467,7 +467,9 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     // activations on chip, but every one of its sequential sub-steps is latency-bound with 8 warps per SM: 132 us per
     // batch-256 step against 112 us for the stage-structured kernel, which therefore stays the default.
     proto.use_cluster = 0;
+#ifndef HIRL_NO_CLUSTER   // development builds (-DHIRL_NO_CLUSTER) leave the two cluster-kernel instances out: half the compile time
     if (const char *e = getenv("HIRL_CLUSTER")) proto.use_cluster = (atoi(e) != 0 && R == 1) ? 1 : 0;
+#endif
     proto.cluster_ri = 8;
     proto.Bpad = ((cfg->batch + 15) / 16) * 16;
     // Tensor-core cluster kernel (csrc/tcc_update.cuh): single HIRL agent (relu or leaky_relu), batch <= 256.  HIRL_TCC=0/1
@@ -492,6 +494,7 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
         h->tcc_ncl = ncl;
         if (proto.use_tcc) proto.use_tc = proto.tc_g1 = 0;
     }
+#ifndef HIRL_NO_CLUSTER
     if (proto.use_cluster) {
         proto.use_tc = proto.tc_g1 = 0;
         // how many clusters of 8 CTAs are co-resident on this part (B200: 15 or 16, depends on the floor plan of the die)
@@ -519,6 +522,7 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
         const int rb = 2 * proto.cluster_ri;
         proto.Bpad = ((cfg->batch + rb - 1) / rb) * rb;
     }
+#endif
     proto.BT = (cfg->batch + 31) & ~31;
     // dW2 reduces over the batch: split it so that a long reduction still spreads over the SMs (tensor-core tiles:
     // one split per 512 batch rows = one accumulation chunk; FP32 tiles: one per 1024 rows)
@@ -603,6 +607,9 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
             if ((rc = dev_alloc(h, &t.SOFTQX, (size_t)tcc::MAX_RB * tcc::RB))) return rc;
             if ((rc = dev_alloc(h, &t.XH2S, (size_t)tcc::MAX_RB * tcc::RB * H2))) return rc;
             if ((rc = dev_alloc(h, &t.H1TI, (size_t)tcc::MAX_NCL * tcc::H1T_FLOATS))) return rc;
+            if ((rc = dev_alloc(h, &t.APX, (size_t)tcc::MAX_RB * tcc::RB * 4))) return rc;
+            if ((rc = dev_alloc(h, &t.XHP, (size_t)2 * tcc::MAX_RB * tcc::RB * H2))) return rc;
+            if ((rc = dev_alloc(h, &t.H1I, (size_t)tcc::MAX_NCL * tcc::H1T_FLOATS))) return rc;
             if ((rc = dev_alloc(h, &t.RSUM, (size_t)tcc::MAX_NCL * 8))) return rc;
             if ((rc = dev_alloc(h, &t.LPT, 16))) return rc;
             if ((rc = dev_alloc(h, &t.CNT, 8))) return rc;
@@ -771,6 +778,7 @@ static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_de
             e = cudaLaunchKernelExC(&lc, (const void *)tcc::hirl_tcc_kernel, args);
         }
         if (e != cudaSuccess) return fail(HIRL_E_CUDA, std::string("tcc kernel launch: ") + cudaGetErrorString(e));
+#ifndef HIRL_NO_CLUSTER
     } else if (R == 1 && h->ctxs[0].use_cluster) {
         cl::ClusterLaunch L;
         L.agent = h->ctxs[0];
@@ -798,6 +806,7 @@ static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_de
             e = cudaLaunchKernelExC(&lc, fn, args);
         }
         if (e != cudaSuccess) return fail(HIRL_E_CUDA, std::string("cluster kernel launch: ") + cudaGetErrorString(e));
+#endif
     } else if (R == 1) {
         LaunchCtx L;
         L.agent = h->ctxs[0];

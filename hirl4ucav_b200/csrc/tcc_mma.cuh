@@ -78,6 +78,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// the same copy delivered to the same CTA-relative offsets (data and mbarrier) of every CTA in cta_mask (SASS UBLKCP ... .MULTICAST)
+__device__ __forceinline__ void bulk_g2s_mc(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
 
 // ---- cluster / DSMEM -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {

@@ -85,9 +85,9 @@ __host__ __device__ __forceinline__ size_t img_t_index(int n, int k) {       // 
 }
 
 // p2p flag words (each on its own 128-byte line)
-enum { PF_TQ = 0 /* [r][t] */, PF_SOFTQ = 8 /* [r] */, PF_CNT = 12 /* [r] */, PF_WORDS = 16 };
+enum { PF_TQ = 0 /* [r][t] */, PF_SOFTQ = 8 /* [r] */, PF_CNT = 12 /* [r] */, PF_AP = 16 /* [r] */, PF_WORDS = 20 };
 constexpr int PROF_WORDS = 96;
-enum { B_FULL = 0, B_EMPTY = NSLOT, B_ACC = 2 * NSLOT, B_W1 = 2 * NSLOT + 2, B_H1T, B_X0, B_X1, N_BARS };
+enum { B_FULL = 0, B_EMPTY = NSLOT, B_ACC = 2 * NSLOT, B_W1 = 2 * NSLOT + 2, B_H1T, B_H1, B_X0, B_X1, N_BARS };
 
 struct TccLaunch {
     AgentCtx agent;
@@ -103,13 +103,18 @@ struct Ctl {
     uint32_t tm;
     int crank, cid, ncl, warp, lane, sub, wh, row;   // row: batch row of this thread inside the block (thread-per-row epilogues)
     bool act;                                         // lane < 16: this thread owns (row, 32 columns)
-    unsigned ring_n, acc_n[2], w1_n, h1t_n, xr, gen, pgen;
+    unsigned ring_n, acc_n[2], w1_n, h1t_n, h1_n, xr, gen, pgen;
+    float *h1img;      // this cluster's H1 image in L2 (layout of the shared operand tile)
     unsigned *flags, *pflags;
-    long long *pr;
+    long long *pr, *pr2;   // pr: stamps of cluster 0 / CTA 0;  pr2: of the first online unit's cluster (phase A) / CTA 0
     int pb;   // base index of the fine-grained stamps of the current pass (0: off)
 };
 __device__ __forceinline__ void stamp(const Ctl &k, int id) { if (k.pr && threadIdx.x == 0) k.pr[id] = clock64(); }
-__device__ __forceinline__ void pstamp(const Ctl &k, int i) { if (k.pr && k.pb && threadIdx.x == 0) k.pr[k.pb + i] = clock64(); }
+__device__ __forceinline__ void stamp2(const Ctl &k, int id) { if (k.pr2 && threadIdx.x == 0) k.pr2[id] = clock64(); }
+__device__ __forceinline__ void pstamp(const Ctl &k, int i) {
+    long long *p = k.pr ? k.pr : k.pr2;
+    if (p && k.pb && threadIdx.x == 0) p[k.pb + i] = clock64();
+}
 
 // ---- synchronisation -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grid_sync(Ctl &k) {
@@ -212,102 +217,80 @@ __device__ __forceinline__ void publish_operands() {
     __syncthreads();
 }
 
-// ---- first layer + LayerNorm1 + activation into the forward operand tile ------------------------------------------------
+// ---- first layer + LayerNorm1 + activation of the CTA's OWN 8 rows -> H1 image of the row block in L2 ------------------
+// Warp w evaluates batch row 8 crank + w (lane owns n = lane + 32 j); the result goes hi/lo-split into the cluster's H1
+// image in global memory, which has exactly the layout of the shared operand tile (8 blocks of [64 rows][32] hi | lo), so
+// that after one cluster barrier every CTA multicasts one k-block of it (hi + lo, 16 KB) into the operand tile of all
+// eight CTAs: the first layer is computed once per cluster instead of once per CTA.
 // x_k of row b:  k < 13: xs[b][soff + k];  k >= 13 (critic): acts[b][k - 13]  (acts == nullptr: xs[b][k], the stored action)
-// W1T [k0 x 256] is staged in shared memory (stage_w1); b1 / g1 / be1 come from the arena.  H1[b][n] -> 8 blocks of [64 rows][32] hi | lo.
-// own_xh / own_rstd: xhat1 / rstd1 of the CTA's own row of this warp (row 8 crank + warp), kept for the backward pass.
-// h1t (may be null): global H1^T image of the row block; this warp writes the column of its own row.
+// W1T [k0 x 256] is staged in shared memory (stage_w1); b1 / g1 / be1 come from the arena.
+// own: xhat1 / rstd1 of the row, kept for the backward pass.  h1t (may be null): global H1^T image; this warp writes its column.
+struct OwnRow { float xh1[8], rstd1; };
 template <class L>
-__device__ __noinline__ void l1_tile(unsigned pad, const float *tw, uint64_t *w1bar, unsigned w1par, int soff, bool use_acts, float slope, int crank, float *h1t,
-                                     float (&own_xh)[8], float &own_rstd, long long *dbg) {
-    // pointers are derived from the shared-memory symbol itself (not passed in as generic pointers): LDS / STS instead of LD / ST
-    extern __shared__ float4 smem4[];
-    char *sm = reinterpret_cast<char *>(smem4) + pad;
-    const float *acts = use_acts ? reinterpret_cast<const float *>(sm + O_ACT) : nullptr;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float *xs = reinterpret_cast<const float *>(sm + O_X), *w1s = reinterpret_cast<const float *>(sm + O_W1);
-    float b1[8], g1[8], be1[8];
+__device__ __forceinline__ void l1_rows(Ctl &k, const float *tw, int soff, const float *acts, float slope, float *h1img, float *h1t, OwnRow &own) {
+    const float *xs = reinterpret_cast<const float *>(k.sm + O_X), *w1s = reinterpret_cast<const float *>(k.sm + O_W1);
+    const int lane = k.lane, b = 8 * k.crank + k.warp;
+    float b1[8], g1[8], be1[8], z[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {                                      // in flight while the bulk copy of W1 lands
         b1[j] = tw[L::B1 + lane + 32 * j];
         g1[j] = tw[L::G1 + lane + 32 * j];
         be1[j] = tw[L::BE1 + lane + 32 * j];
     }
-    tc::mbar_wait(w1bar, w1par, 900);
-    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
-    for (int grp = 0; grp < 2; ++grp) {
-        float z[4][8];
+    float xv = 0.f;
+    if (lane < L::k0) xv = lane < S ? xs[b * 32 + soff + lane] : (acts ? acts[b * 4 + (lane - S)] : xs[b * 32 + lane]);
+    tc::mbar_wait(k.bars + B_W1, k.w1_n & 1u, 900);
+    k.w1_n += 1u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 8; ++j) z[j] = b1[j];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) z[i][j] = b1[j];
+    for (int kk = 0; kk < L::k0; ++kk) {
+        const float x = __shfl_sync(0xffffffffu, xv, kk);
 #pragma unroll
-        for (int kk = 0; kk < L::k0; ++kk) {
-            float w[8], xv[4];
+        for (int j = 0; j < 8; ++j) z[j] = fmaf(x, w1s[kk * H1 + lane + 32 * j], z[j]);
+    }
+    float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = w1s[kk * H1 + lane + 32 * j];
+    for (int j = 0; j < 8; ++j) s += z[j];
+    s = warp_sum(s) * (1.f / H1);
+    float v = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int b = warp + 8 * (4 * grp + i);
-                xv[i] = kk < S ? xs[b * 32 + soff + kk] : (acts ? acts[b * 4 + (kk - S)] : xs[b * 32 + kk]);
-            }
+    for (int j = 0; j < 8; ++j) {
+        const float d = z[j] - s;
+        v = fmaf(d, d, v);
+    }
+    v = warp_sum(v);
+    const float rstd = 1.f / sqrtf(v * (1.f / H1) + LN_EPS);
+    own.rstd1 = rstd;
+    float *dst = h1img + sw128_words(b, lane);
+    float *tst = reinterpret_cast<float *>(k.sm + O_R);               // [8 rows][256] staging of the transposed image (the operand tile is idle here)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 8; ++j) {
+        const float xh = (z[j] - s) * rstd;
+        const float hv = act_f(fmaf(xh, g1[j], be1[j]), slope);
+        const float hi = tf32_hi(hv);
+        own.xh1[j] = xh;
+        dst[j * 2048] = hi;
+        dst[16384 + j * 2048] = hv - hi;
+        if (h1t) tst[k.warp * H1 + lane + 32 * j] = hv;
+    }
+    if (h1t) {
+        // H1^T image [256 n][64 b] (K-major along b): thread n writes this CTA's 8 batch rows = one 32-byte sector hi, one lo
+        __syncthreads();
+        const int n = threadIdx.x, b0 = 8 * k.crank;
+        float hv[8], hi[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) z[i][j] = fmaf(xv[i], w[j], z[i][j]);
+        for (int i = 0; i < 8; ++i) {
+            hv[i] = tst[i * H1 + n];
+            hi[i] = tf32_hi(hv[i]);
         }
-        if (dbg && threadIdx.x == 0) dbg[1 + 3 * grp] = clock64();
-        float s[4], v[4];
+        float *t = h1t + (size_t)(b0 >> 5) * 8192;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            s[i] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s[i] += z[i][j];
+        for (int q = 0; q < 2; ++q) {
+            float *w = t + sw128_words(n, (b0 & 31) + 4 * q);
+            st4(w, make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]));
+            st4(w + 16384, make_float4(hv[4 * q] - hi[4 * q], hv[4 * q + 1] - hi[4 * q + 1], hv[4 * q + 2] - hi[4 * q + 2], hv[4 * q + 3] - hi[4 * q + 3]));
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            s[i] *= (1.f / H1);
-            v[i] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float d = z[i][j] - s[i];
-                v[i] = fmaf(d, d, v[i]);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-        if (dbg && threadIdx.x == 0) dbg[2 + 3 * grp] = clock64();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int b = warp + 8 * (4 * grp + i);
-            const bool own = (4 * grp + i) == crank;
-            const float rstd = 1.f / sqrtf(v[i] * (1.f / H1) + LN_EPS);
-            if (own) own_rstd = rstd;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float xh = (z[i][j] - s[i]) * rstd;
-                const float hv = act_f(fmaf(xh, g1[j], be1[j]), slope);
-                const float hi = tf32_hi(hv);
-                const uint32_t off = (uint32_t)j * 8192u + sw128_off(b, lane);
-                *reinterpret_cast<float *>(sm + O_R + off) = hi;
-                *reinterpret_cast<float *>(sm + O_R + R_LO + off) = hv - hi;
-                if (own) {
-                    own_xh[j] = xh;
-                    if (h1t) {
-                        float *t = h1t + (size_t)(b >> 5) * 8192 + sw128_words(lane + 32 * j, b & 31);
-                        t[0] = hi;
-                        t[16384] = hv - hi;
-                    }
-                }
-            }
-        }
-        if (dbg && threadIdx.x == 0) dbg[3 + 3 * grp] = clock64();
     }
 }
 
@@ -335,28 +318,38 @@ __device__ __forceinline__ void stage_w1(Ctl &k, const float *tw) {
 
 // ---- forward pass: first layer, second layer on the tensor cores, LayerNorm2 + head per thread-row --------------------
 // out[o]: the head output of this thread's row (identical in every CTA); xh / rstd: this thread's 32 normalised columns.
-struct OwnRow { float xh1[8], rstd1; };
 template <class L>
 __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const float *img, int soff, const float *acts, float slope, float *h1t,
-                                             bool h1t_arrive, float (&xh)[32], float &rstd, float (&out)[L::nout], OwnRow &own) {
+                                             float (&xh)[32], float &rstd, float (&out)[L::nout], OwnRow &own) {
     char *sm = k.sm;
     const float *unit0 = img + (size_t)k.crank * 8 * 4096;            // this CTA's slice: 8 k-blocks of hi | lo
     stage_w1<L>(k, tw);
     stream_units(k, unit0, 0, NSLOT);                                  // lands while the first layer runs
+    if (threadIdx.x == PRODUCER) mbar_expect_tx(k.bars + B_H1, 131072);
     load_pc<L>(k, tw);
     pstamp(k, 0);
-    l1_tile<L>(k.pad, tw, k.bars + B_W1, k.w1_n & 1u, soff, acts != nullptr, slope, k.crank, h1t, own.xh1, own.rstd1,
-               (k.pr && k.pb) ? k.pr + k.pb + 8 + 20 : nullptr);
-    k.w1_n += 1u;
+    l1_rows<L>(k, tw, soff, acts, slope, k.h1img, h1t, own);
     pstamp(k, 1);
-    publish_operands();
-    if (h1t_arrive) cluster_arrive();                                  // releases this CTA's rows of the H1^T image; the matching wait opens pass_backward
+    // every CTA's rows of the H1 image (and of the H1^T image) are in L2, and every CTA is past its last use of the
+    // operand-tile region (it arrives here only after that): the multicast below may land everywhere
+    cluster_sync();
+    if (threadIdx.x == PRODUCER) {
+        fence_proxy_async_all();
+#ifdef TCC_H1_UNICAST
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bulk_g2s(sm + O_R + q * 32768, k.h1img + (size_t)q * 8192, 32768, k.bars + B_H1);
+#else
+        bulk_g2s_mc(sm + O_R + k.crank * 8192, k.h1img + (size_t)k.crank * 2048, 8192, k.bars + B_H1, (uint16_t)0xFF);
+        bulk_g2s_mc(sm + O_R + R_LO + k.crank * 8192, k.h1img + 16384 + (size_t)k.crank * 2048, 8192, k.bars + B_H1, (uint16_t)0xFF);
+#endif
+    }
     stream_units(k, unit0, NSLOT, 8 - NSLOT);
     if (k.lane == 0 && k.warp < ISSUERS) {
         tc::tc_fence_after();
         const int p = k.warp;
         const uint32_t id = idesc(RB, NSL, 0, 0), r = smem_u32(sm + O_R) + (p == 1 ? R_LO : 0), ring = smem_u32(sm + O_RING) + (p == 2 ? 8192 : 0);
         const uint32_t acc = k.tm + 64 * p;
+        tc::mbar_wait(k.bars + B_H1, k.h1_n & 1u, 960);                  // the H1 tile has landed (async proxy: no generic-proxy fence needed)
         for (int c = 0; c < 8; ++c) {
             const unsigned n = k.ring_n + (unsigned)c;
             ring_wait_full(k, n);
@@ -369,6 +362,7 @@ __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const floa
     }
     __syncwarp();
     k.ring_n += 8u;
+    k.h1_n += 1u;
     pstamp(k, 2);
     acc_wait(k, 0);
     pstamp(k, 3);
@@ -512,10 +506,9 @@ __device__ __forceinline__ void column_sums(Ctl &k, F val, float *dst, int dst_s
 struct BwdOut { float dz1[8], dy1[8]; int b; };   // own row (warp w <-> row 8 crank + w), lane owns n = lane + 32 j
 template <class L, bool WITH_DW>
 __device__ __forceinline__ void pass_backward(Ctl &k, const float *tw, const float *imgt, float slope, const float (&dz)[32], const OwnRow &own,
-                                              float *dh1p_unit, const float *h1t, bool h1t_wait, float *gw2p_slot, BwdOut &o) {
+                                              float *dh1p_unit, const float *h1t, float *gw2p_slot, BwdOut &o) {
     char *sm = k.sm;
     const float *units = imgt + (size_t)k.crank * 8 * 4096;          // 8 sub-units: (mb, cc, hi | lo)
-    if (WITH_DW && h1t_wait) cluster_wait();                          // every CTA's rows of the H1^T image are visible (arrive: pass_forward)
     stream_units(k, units, 0, NSLOT);
     if (WITH_DW && threadIdx.x == PRODUCER) {                         // H1^T image of the row block -> the (dead) H1 region
         fence_proxy_async_all();
@@ -861,10 +854,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
     k.crank = (int)cluster_ctarank(); k.cid = (int)cluster_id_x(); k.ncl = Lc.ncl;
     k.warp = threadIdx.x >> 5; k.lane = threadIdx.x & 31; k.sub = k.warp & 3; k.wh = k.warp >> 2;
     k.act = k.lane < 16; k.row = 16 * k.sub + (k.lane & 15);
-    k.ring_n = 0u; k.acc_n[0] = k.acc_n[1] = 0u; k.w1_n = k.h1t_n = 0u; k.xr = 0u;
+    k.ring_n = 0u; k.acc_n[0] = k.acc_n[1] = 0u; k.w1_n = k.h1t_n = k.h1_n = 0u; k.xr = 0u;
     k.flags = Lc.bar_flags;
     k.gen = ld_relaxed_u32(k.flags + k.cid * FLAG_STRIDE);
-    k.pr = nullptr; k.pb = 0;
+    k.pr = k.pr2 = nullptr; k.pb = 0;
     if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot);
     if (threadIdx.x == 32) {
         for (int i = 0; i < N_BARS; ++i) tc::mbar_init(bars + i, (i >= B_EMPTY && i < B_ACC + 2) ? ISSUERS : 1);
@@ -877,6 +870,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
     const AgentCtx &c = ctx;
     k.pflags = c.tcc.pflags;
     k.pgen = ld_relaxed_u32(c.tcc.gen_ctr);
+    k.h1img = c.tcc.H1I + (size_t)k.cid * H1T_FLOATS;
     cluster_sync();                                                    // peers' shared memory and barriers are live before anybody pushes
     const float slope = slope_of(c);
     const int B = c.B, nrb = (B + RB - 1) / RB;
@@ -892,50 +886,83 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
         const bool do_actor = st.do_actor != 0, soft = st.bc_weight_now == 100.f, do_polyak = st.do_polyak != 0;
         const unsigned fgen = k.pgen + (unsigned)step + 1u;
         k.pr = (Lc.prof && step < PROF_STEPS && k.cid == 0 && k.crank == 0) ? Lc.prof + (size_t)step * PROF_WORDS : nullptr;
+        k.pr2 = (Lc.prof && step < PROF_STEPS && k.cid == nrb % k.ncl && k.crank == 0) ? Lc.prof + (size_t)step * PROF_WORDS : nullptr;
         stamp(k, 0);
+        stamp2(k, 18);
+        if (k.pr && threadIdx.x == 0) k.pr[19] = k.ncl;
         // =============================== phase A: critic forward / backward ===============================
-        if (k.cid < 2 * nrb) {
-            const int r = k.cid >> 1, t = k.cid & 1, unit = k.cid;
-            const int bg = RB * r + k.row;                             // global batch row of this thread
-            const bool valid = bg < B;
-            gather_rows(k, c, st, step, r, false);
-            stamp(k, 1);
+        // units 0 .. nrb - 1: target actor of row block r -> a' published through L2;
+        // units nrb .. 3 nrb - 1: critic tower (r, t): forward on (s, a) while the target actor runs, then the target tower on
+        // (s', a'), the TD target with the partner tower's target Q, loss and the backward pass.
+        // 3 nrb <= 12 clusters carry the phase (B200 co-schedules 15 clusters of 8 CTAs).
+#pragma unroll 1
+        for (int ua = k.cid; ua < 3 * nrb; ua += k.ncl) {
             float xh[32], rstd;
             OwnRow own;
-            // target actor on next_state (HIRL.py:264) -> a' (HIRL.py:265-267)
-            {
+            if (ua < nrb) {
+                const int r = ua;
+                gather_rows(k, c, st, step, r, false);
+                stamp(k, 1);
+                // target actor on next_state (HIRL.py:264) -> a' (HIRL.py:265-267)
                 float out[A];
                 k.pb = 20;
-                pass_forward<ActorL>(k, c.tactor, c.tcc.img_tactor, SA, nullptr, slope, nullptr, false, xh, rstd, out, own);
+                pass_forward<ActorL>(k, c.tactor, c.tcc.img_tactor, SA, nullptr, slope, nullptr, xh, rstd, out, own);
                 k.pb = 0;
-                if (k.act && k.wh == 0) {
+                if (k.crank == 0 && k.act && k.wh == 0) {
+                    float ap[A];
 #pragma unroll
                     for (int j = 0; j < A; ++j) {
                         const float nz = fminf(fmaxf(st.noise[j], -c.noise_clamp), c.noise_clamp);
-                        acts[k.row * 4 + j] = fminf(fmaxf(tanhf(out[j]) + nz, -1.f), 1.f);
+                        ap[j] = fminf(fmaxf(tanhf(out[j]) + nz, -1.f), 1.f);
                     }
+                    st4(c.tcc.APX + (r * RB + k.row) * 4, make_float4(ap[0], ap[1], ap[2], ap[3]));
                 }
+                flag_publish(k, PF_AP + r, fgen);
+                stamp(k, 2);
+                continue;
             }
-            stamp(k, 2);
-            // target critic tower t on (next_state, a') (HIRL.py:270)
-            float tq_own;
-            {
-                float out[1];
-                pass_forward<CriticL>(k, c.tcritic + t * CriticL::SIZE, c.tcc.img_tcritic + (size_t)t * IMG_FWD, SA, acts, slope, nullptr, false, xh, rstd, out, own);
-                tq_own = out[0];
-                if (k.crank == 0 && k.act && k.wh == 0) c.tcc.TQX[(r * 2 + t) * RB + k.row] = tq_own;
-                flag_publish(k, PF_TQ + r * 2 + t, fgen);
-            }
-            stamp(k, 3);
+            const int unit = ua - nrb, r = unit >> 1, t = unit & 1;
+            const int bg = RB * r + k.row;                             // global batch row of this thread
+            const bool valid = bg < B;
+            gather_rows(k, c, st, step, r, false);
+            stamp2(k, 17);
             // critic tower t on (state, action) (HIRL.py:277)
             float q1[1];
             float *h1t = c.tcc.H1TI + (size_t)unit * H1T_FLOATS;
             k.pb = 28;
-            pass_forward<CriticL>(k, c.critic + t * CriticL::SIZE, c.tcc.img_critic + (size_t)t * IMG_FWD, 0, nullptr, slope, h1t, true, xh, rstd, q1, own);
+            pass_forward<CriticL>(k, c.critic + t * CriticL::SIZE, c.tcc.img_critic + (size_t)t * IMG_FWD, 0, nullptr, slope, h1t, xh, rstd, q1, own);
             k.pb = 0;
-            stamp(k, 4);
+            stamp2(k, 4);
+            float *xpark = c.tcc.XHP + ((size_t)unit * RB + k.row) * H2 + NSL * k.crank + 32 * k.wh;   // the pass' state waits in L2 while the target tower uses the registers
+            if (k.act) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) st4(xpark + e, make_float4(xh[e], xh[e + 1], xh[e + 2], xh[e + 3]));
+            }
+            const float rstd_c = rstd;
+            // target critic tower t on (next_state, a') (HIRL.py:270)
+            flag_wait(k, PF_AP + r, fgen);
+            if (k.act && k.wh == 0) *reinterpret_cast<float4 *>(acts + k.row * 4) = __ldcg(reinterpret_cast<const float4 *>(c.tcc.APX + (r * RB + k.row) * 4));
+            stamp2(k, 38);
+            float tq_own;
+            {
+                float out[1];
+                OwnRow own_t;
+                pass_forward<CriticL>(k, c.tcritic + t * CriticL::SIZE, c.tcc.img_tcritic + (size_t)t * IMG_FWD, SA, acts, slope, nullptr, xh, rstd, out, own_t);
+                tq_own = out[0];
+                if (k.crank == 0 && k.act && k.wh == 0) c.tcc.TQX[(r * 2 + t) * RB + k.row] = tq_own;
+                flag_publish(k, PF_TQ + r * 2 + t, fgen);
+            }
+            stamp2(k, 39);
+            if (k.act) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    const float4 v4 = __ldcg(reinterpret_cast<const float4 *>(xpark + e));
+                    xh[e] = v4.x; xh[e + 1] = v4.y; xh[e + 2] = v4.z; xh[e + 3] = v4.w;
+                }
+            }
+            rstd = rstd_c;
             flag_wait(k, PF_TQ + r * 2 + (1 - t), fgen);
-            stamp(k, 36);
+            stamp2(k, 36);
             const float tq_other = __ldcg(c.tcc.TQX + (r * 2 + (1 - t)) * RB + k.row);
             const float *xs = reinterpret_cast<const float *>(k.sm + O_X);
             const float rew = xs[k.row * 32 + 30], dn = xs[k.row * 32 + 31];
@@ -949,9 +976,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
             }
             float dout[1] = {valid ? (2.f / (float)B) * delta : 0.f};                                          // mse_loss backward, mean reduction
             float dz[32], dy[32], h[32];
+            load_pc<CriticL>(k, c.critic + t * CriticL::SIZE);         // the parameter cache held the target tower's
+            __syncthreads();
             head_ln2_backward<CriticL>(k, xh, rstd, dout, slope, dz, dy, h);
             // second-layer small parameters of this CTA's 64 features: db2, dgamma2, dbeta2, dW3 (+ db3, loss by CTA 0)
-            float *part = c.tcc.PARTC + ((size_t)(unit >> 1) * CL * 2 + t) * CriticL::SMALL;                   // slot 8 r (+ tower)
+            float *part = c.tcc.PARTC + ((size_t)r * CL * 2 + t) * CriticL::SMALL;                             // slot 8 r (+ tower)
             {
                 float *p2 = part + CriticL::small_index(CriticL::B2) + NSL * k.crank;
                 const float dq = dout[0];
@@ -963,14 +992,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                     c.tcc.LPT[unit] = c.tcc.RSUM[8 * unit + 1];
                 }
             }
-            stamp(k, 37);
+            stamp2(k, 37);
             BwdOut bo;
             k.pb = 40;
             pass_backward<CriticL, true>(k, c.critic + t * CriticL::SIZE, c.tcc.imgt_critic + (size_t)t * IMG_T, slope, dz, own,
-                                         c.tcc.DH1P + (size_t)unit * CL * RB * H1, h1t, true, c.tcc.GW2PC + ((size_t)t * MAX_RB + r) * H2 * H1, bo);
+                                         c.tcc.DH1P + (size_t)unit * CL * RB * H1, h1t, c.tcc.GW2PC + ((size_t)t * MAX_RB + r) * H2 * H1, bo);
             k.pb = 0;
             ln1_param_partials<CriticL>(k, bo, own, 0, nullptr, c.tcc.PARTC + ((size_t)(r * CL + k.crank) * 2 + t) * CriticL::SMALL);
-            stamp(k, 5);
+            stamp2(k, 5);
         }
         grid_sync(k);
         stamp(k, 6);
@@ -1017,7 +1046,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                     // ---- role A: pi = actor(s), rl_Q = Q1(s, pi) with the updated critic (HIRL.py:295-297)
                     gather_rows(k, c, st, step, r, false);
                     float out[A], pi[A];
-                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, h1t, false, xh, rstd, out, own);   // the Q pass' cluster barriers release the image
+                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, h1t, xh, rstd, out, own);
 #pragma unroll
                     for (int j = 0; j < A; ++j) pi[j] = tanhf(out[j]);
                     if (k.act && k.wh == 0) {
@@ -1036,7 +1065,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                     const float rstd_a = rstd;
                     stamp(k, 10);
                     float q[1];
-                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, nullptr, false, xh, rstd, q, own_q);
+                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, nullptr, xh, rstd, q, own_q);
                     stamp(k, 11);
                     float softq = 0.f;
                     if (soft) {
@@ -1058,7 +1087,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         flag_publish(k, PF_CNT + r, fgen);
                     }
                     BwdOut bo;
-                    pass_backward<CriticL, false>(k, c.critic, c.tcc.imgt_critic, slope, dz, own_q, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, nullptr, false, nullptr, bo);
+                    pass_backward<CriticL, false>(k, c.critic, c.tcc.imgt_critic, slope, dz, own_q, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, nullptr, nullptr, bo);
                     {
                         float g[A];
 #pragma unroll
@@ -1102,7 +1131,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         column_sums<7, 4>(k, [&](int a, int e) { return a == 0 ? dz[e] : a == 1 ? dy[e] * xh[e] : a == 2 ? dy[e] : dpre[a - 3] * h[e]; }, p2, H2,
                                           dpre, k.crank == 0 ? part + ActorL::small_index(ActorL::B3) : nullptr);
                     }
-                    pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, slope, dz, own, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, h1t, false,
+                    pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, slope, dz, own, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, h1t,
                                                 c.tcc.GW2PA + (size_t)r * H2 * H1, bo);
                     ln1_param_partials<ActorL>(k, bo, own, 0, nullptr, c.tcc.PARTA + (size_t)(r * CL + k.crank) * ActorL::SMALL);
                     stamp(k, 14);
@@ -1110,7 +1139,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                     // ---- role S: a_bc = bc_actor(s), soft_Q = Q1(s, a_bc) (HIRL.py:300-302)
                     gather_rows(k, c, st, step, r, false);
                     float out[A];
-                    pass_forward<ActorL>(k, c.bc, c.tcc.img_bc, 0, nullptr, slope, nullptr, false, xh, rstd, out, own);
+                    pass_forward<ActorL>(k, c.bc, c.tcc.img_bc, 0, nullptr, slope, nullptr, xh, rstd, out, own);
                     if (k.act && k.wh == 0) {
 #pragma unroll
                         for (int j = 0; j < A; ++j) {
@@ -1120,14 +1149,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         }
                     }
                     float q[1];
-                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, nullptr, false, xh, rstd, q, own_q);
+                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, nullptr, xh, rstd, q, own_q);
                     if (k.crank == 0 && k.act && k.wh == 0) c.tcc.SOFTQX[r * RB + k.row] = q[0];
                     flag_publish(k, PF_SOFTQ + r, fgen);
                 } else {
                     // ---- role AB: pi_bc = actor(s_bc), cloning loss (HIRL.py:310-319), actor backward of the BC branch
                     gather_rows(k, c, st, step, r, true);
                     float out[A], pi[A], diff[A];
-                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, h1t, true, xh, rstd, out, own);
+                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, h1t, xh, rstd, out, own);
                     const float *xs = reinterpret_cast<const float *>(k.sm + O_X);
                     float sq = 0.f;
 #pragma unroll
@@ -1162,7 +1191,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                                           dpre, k.crank == 0 ? part + ActorL::small_index(ActorL::B3) : nullptr);
                     }
                     BwdOut bo;
-                    pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, slope, dz, own, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, h1t, true,
+                    pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, slope, dz, own, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, h1t,
                                                 c.tcc.GW2PA + (size_t)(MAX_RB + r) * H2 * H1, bo);
                     ln1_param_partials<ActorL>(k, bo, own, 0, nullptr, c.tcc.PARTA + (size_t)((MAX_RB + r) * CL + k.crank) * ActorL::SMALL);
                 }

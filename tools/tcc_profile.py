@@ -15,12 +15,14 @@ from hirl4ucav_b200 import _lib, synth  # noqa: E402
 from hirl4ucav_b200.agents.HIRL import Agent  # noqa: E402
 from hirl4ucav_b200.utils.seed import set_seed  # noqa: E402
 
-MAIN = [(1, "A: gather"), (2, "A: target actor pass -> a'"), (3, "A: target critic pass -> tq published"), (4, "A: critic forward pass"),
-        (36, "A: wait for the partner tower's tq"), (37, "A: TD target, loss, head/LN2 backward, small-param column sums"), (5, "A: backward GEMMs, LN1 backward, partials"),
-        (6, "grid barrier"), (7, "B: critic Adam + images"), (8, "grid barrier"),
+ONLINE = [(17, "A/tower unit: gather"), (4, "A/tower unit: critic forward pass"), (38, "A/tower unit: park state, wait for a'"),
+          (39, "A/tower unit: target critic pass -> tq published"), (36, "A/tower unit: wait for the partner tower's tq"),
+          (37, "A/tower unit: TD target, loss, head/LN2 backward, small-param column sums"), (5, "A/tower unit: backward GEMMs, LN1 backward, partials")]
+MAIN = [(1, "A/target-actor unit: gather"), (2, "A/target-actor unit: target actor pass -> a' published"),
+        (6, "grid barrier (after the slower chain)"), (7, "B: critic Adam + images"), (8, "grid barrier"),
         (10, "C: gather, actor pass -> pi"), (11, "C: Q1(s,pi) pass"), (12, "C: soft count, Q backward -> d pi"), (13, "C: wait for every row block's count"),
         (14, "C: actor backward (RL branch)"), (15, "grid barrier"), (16, "D: actor Adam, Polyak, images + grid barrier")]
-FWD = ["stream begin + param cache", "first layer (FP32 FMA) -> H1 tile", "publish + MMA issue", "wait for the accumulator", "TMEM -> registers, local LN stats",
+FWD = ["stream begin + param cache", "first layer of the own 8 rows -> H1 image in L2", "cluster barrier, multicast, MMA issue", "wait for the accumulator", "TMEM -> registers, local LN stats",
        "exchange 1 (LN statistics)", "normalise, head partial, exchange 2"]
 BWD = ["dz2 tile", "publish + dH1 MMA issue", "H1^T recompute", "wait dH1, dz2^T tile, dW2 issue", "dH1 partial -> L2", "cluster barrier", "own rows: 8 partials, LN1 backward",
        "wait dW2, partial -> L2"]
@@ -48,20 +50,25 @@ def main():
     _lib.check(lib.hirl_debug_profile(ag._h, 0, buf.ctypes.data_as(C.c_void_p), n))
     prof = buf[:12 * 96].reshape(12, 96)
     us = lambda d: d / a.mhz
+    tot = [us(prof[i + 1][0] - prof[i][0]) for i in range(4, 10)]
+    print("whole calls 4..9 (start to start, cluster 0): " + " ".join(f"{t:.1f}" for t in tot) + f" us   mean {sum(tot) / len(tot):.1f} us")
     for step in (6, 7):
         p = prof[step]
         print(f"step {step} ({'actor' if p[10] else 'critic-only'} call), cluster 0 / CTA 0:")
+        print(f"  clusters: {p[19]}")
+        prev = p[18]
+        for i, label in ONLINE:      # stamped by the cluster of the first online unit (SM clocks of different SMs: offsets of a few hundred ns)
+            if p[i] == 0:
+                continue
+            print(f"  {label:66s} {us(p[i] - prev):8.2f} us   (t = {us(p[i] - p[18]):8.2f})")
+            prev = p[i]
         prev = p[0]
         for i, label in MAIN:
             if p[i] == 0:
                 continue
             print(f"  {label:66s} {us(p[i] - prev):8.2f} us   (t = {us(p[i] - p[0]):8.2f})")
             prev = p[i]
-        for base in (20, 28):
-            d = p[base + 28: base + 35]
-            if d[0]:
-                print(f"    l1_tile @{base}: W1 landed +{us(d[0] - p[base]):.2f} | grp0 fma {us(d[1] - d[0]):.2f} stats {us(d[2] - d[1]):.2f} store {us(d[3] - d[2]):.2f} | grp1 fma {us(d[4] - d[3]):.2f} stats {us(d[5] - d[4]):.2f} store {us(d[6] - d[5]):.2f}")
-        for base, name, labels, start in ((20, "target actor pass", FWD, p[1]), (28, "critic forward pass", FWD, p[3]), (40, "critic backward", BWD, p[37])):
+        for base, name, labels, start in ((20, "target actor pass", FWD, p[1]), (28, "critic forward pass", FWD, p[17]), (40, "critic backward", BWD, p[37])):
             print(f"    -- inside the {name}:")
             prev = start
             for j, label in enumerate(labels):
