@@ -472,10 +472,10 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
 #endif
     proto.cluster_ri = 8;
     proto.Bpad = ((cfg->batch + 15) / 16) * 16;
-    // Tensor-core cluster kernel (csrc/tcc_update.cuh): single HIRL agent (relu or leaky_relu), batch <= 256.  HIRL_TCC=0/1
-    // overrides; TD3 / BC step modes are not implemented there, the wrapper classes of those agents pass HIRL_TCC=0 semantics
-    // through cfg->activation == leaky (TD3.py, BC.py) -> stage kernel.
-    proto.use_tcc = 0;   // opt-in until validated: (R == 1 && cfg->batch <= 4 * tcc::RB && cfg->activation == HIRL_ACT_RELU && !proto.use_cluster)
+    // Tensor-core cluster kernel (csrc/tcc_update.cuh): the default for a single HIRL agent (relu towers) at batch <= 256.
+    // HIRL_TCC=0/1 overrides.  TD3 / BC step modes are not implemented there; those agents (leaky_relu towers, TD3.py / BC.py)
+    // and larger batches / ensembles run on the stage kernel.
+    proto.use_tcc = (R == 1 && cfg->batch <= 4 * tcc::RB && cfg->activation == HIRL_ACT_RELU && !proto.use_cluster) ? 1 : 0;
     if (const char *e = getenv("HIRL_TCC")) proto.use_tcc = (atoi(e) != 0 && R == 1 && cfg->batch <= 4 * tcc::RB && !proto.use_cluster) ? 1 : 0;
     if (proto.use_tcc && (getenv("HIRL_TC") || getenv("HIRL_NSPLIT") || getenv("HIRL_DW_SPLIT")) && !getenv("HIRL_TCC")) proto.use_tcc = 0;   // explicit stage-kernel knobs select the stage kernel
     if (proto.use_tcc) {

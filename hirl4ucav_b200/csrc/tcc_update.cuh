@@ -3,31 +3,36 @@
 // whole networks (forward AND backward) with every 256<->512 contraction on tcgen05 (3xTF32), and grid-wide barriers
 // remain only where a weight gradient has to be complete.
 //
-//   phase A  unit (row block r, critic tower t) -> one cluster:
-//              gather rows -> target actor (redundantly in both tower clusters) -> a' -> target critic tower t -> tq_t
-//              -> published to the partner cluster through a flag in global memory
-//              -> critic tower t forward -> TD target y -> loss -> backward: dz2, dH1 (K-split over the cluster, summed
-//              through L2), LayerNorm1 / first-layer backward, dW2 (per row block) -> partial gradients in global memory
+//   phase A  units, one cluster each (12 at batch 256; B200 co-schedules 15 clusters of 8 CTAs):
+//              target-actor unit r : gather rows -> target actor on s' -> a' published through L2 (flag)
+//              tower unit (r, t)   : gather rows -> critic tower t forward on (s, a) [overlaps the target actor]
+//                                    -> target tower t on (s', a') -> tq_t published to the partner tower's unit (flag)
+//                                    -> TD target y -> loss -> backward: dz2, dH1 (K-split over the cluster, summed
+//                                    through L2), LayerNorm1 / first-layer backward, dW2 (per row block) -> partials
 //   ---- grid barrier ----
 //   phase B  critic Adam over the whole grid (fixed-order sums of the partials); refreshes the tensor-core operand
 //            images of the weights it changed
 //   ---- grid barrier ----                                                                  (critic-only calls end here)
-//   phase C  units (r, role): role A : actor(s) -> pi -> Q1(s,pi) [updated critic] -> backward to d pi
+//   phase C  units (r, role): role A : actor(s) -> pi -> Q1(s,pi) [updated critic] -> backward to d pi -> actor backward
 //                             role S : bc_actor(s) -> a_bc -> Q1(s,a_bc) -> soft Q published to role A (flag)
-//                             role AB: actor(s_bc) -> pi_bc -> cloning loss
-//            role A counts soft_Q > rl_Q per row block and publishes the count (flag); once every block's count is there
-//            the Q-filter weight w (HIRL.py:303-308) is known and roles A / AB run their actor backward passes
+//                             role AB: actor(s_bc) -> pi_bc -> cloning loss -> actor backward
+//            Both actor branches are linear in their loss scale, so they are back-propagated UNSCALED and the Q-filter
+//            weight w (HIRL.py:303-308; needs every row block's count of soft_Q > rl_Q) is applied to the summed partial
+//            gradients of a branch in phase D: (1 - w) resp. w * lambda.  Nobody waits for the count.
 //   ---- grid barrier ----
 //   phase D  actor Adam, Polyak every 3rd actor update (HIRL.py:327-330), operand images, returned scalars
-//   ---- grid barrier ----
+//   ---- grid barrier, only if the targets moved (the next call's phase A reads nothing else that phase D writes) ----
 //
 // CTA j of a cluster owns the output features 64 j .. 64 j + 63 of the 512-wide layers.  Per pass:
-//   * first layer (K = 13 / 17) + LayerNorm1 + activation in FP32 FMAs from weights staged in shared memory (one bulk
-//     copy), 4 rows register-blocked per warp, written hi/lo-split straight into the SWIZZLE_128B K-major operand tile
-//     H1[64][256] (128 KB of shared memory); for back-propagated passes the CTA also writes its own 8 rows of the
-//     TRANSPOSED tile image to L2 (tf32 has no MN-major twin of this layout, tools/tcc_probe.cu);
+//   * first layer (K = 13 / 17) + LayerNorm1 + activation ONCE PER CLUSTER: warp w of CTA j evaluates batch row 8 j + w in
+//     FP32 FMAs (weights staged in shared memory by one bulk copy) and writes it hi/lo-split into the cluster's H1 image
+//     in L2, which has the layout of the SWIZZLE_128B K-major operand tile H1[64][256] (128 KB); after one cluster
+//     barrier every CTA multicasts one k-block (hi + lo, 16 KB) of the image into the operand tile of all 8 CTAs
+//     (cp.async.bulk ... .multicast::cluster).  For back-propagated passes the CTA also writes its 8 rows of the
+//     TRANSPOSED tile image (tf32 has no MN-major twin of this layout, tools/tcc_probe.cu);
 //   * second layer: tcgen05.mma M=64 N=64, A = H1 tile, B = this CTA's slice of a pre-split, pre-swizzled image of W2
-//     streamed by cp.async.bulk through a 3-slot ring; the three products of the 3xTF32 split are issued by three threads
+//     streamed by cp.async.bulk through a 3-slot ring (the first three units are requested at the end of the PREVIOUS
+//     pass, as soon as its MMAs have released the ring); the three products of the 3xTF32 split are issued by three threads
 //     into three TMEM accumulators (a single issuing thread costs ~90 cycles per MMA and was the critical path);
 //   * LayerNorm2 / head from the accumulators with ONE THREAD PER ROW (tcgen05.ld): row statistics and head dot products
 //     are completed across the 8 CTAs by st.async pushes into every CTA's shared memory, each signalling the receiver's
@@ -105,6 +110,7 @@ struct Ctl {
     bool act;                                         // lane < 16: this thread owns (row, 32 columns)
     unsigned ring_n, acc_n[2], w1_n, h1t_n, h1_n, xr, gen, pgen;
     float *h1img;      // this cluster's H1 image in L2 (layout of the shared operand tile)
+    const float *pre;  // weight stream whose first NSLOT units are already on their way into the ring (issued at the end of the previous pass)
     unsigned *flags, *pflags;
     long long *pr, *pr2;   // pr: stamps of cluster 0 / CTA 0;  pr2: of the first online unit's cluster (phase A) / CTA 0
     int pb;   // base index of the fine-grained stamps of the current pass (0: off)
@@ -201,6 +207,18 @@ __device__ __forceinline__ void stream_units(Ctl &k, const float *src, int first
         }
     }
 }
+// first units of a pass: skipped if the previous pass already requested exactly this stream
+__device__ __forceinline__ void stream_begin(Ctl &k, const float *units) {
+    if (k.pre != units) stream_units(k, units, 0, NSLOT);
+    k.pre = nullptr;
+}
+// the ring is idle (every MMA that read it has completed): request the next pass' first units now, so that their L2 round
+// trip overlaps this pass' epilogue and the next pass' prologue
+__device__ __forceinline__ void stream_prefetch(Ctl &k, const float *next_units) {
+    if (next_units) stream_units(k, next_units, 0, NSLOT);
+    k.pre = next_units;
+}
+__device__ __forceinline__ const float *slice_of(const Ctl &k, const float *img) { return img + (size_t)k.crank * 8 * 4096; }
 __device__ __forceinline__ void ring_wait_full(Ctl &k, unsigned n) {   // issuer threads
     tc::mbar_wait(k.bars + B_FULL + (n % NSLOT), (n / NSLOT) & 1u, 600);
     tc::tc_fence_after();
@@ -320,11 +338,11 @@ __device__ __forceinline__ void stage_w1(Ctl &k, const float *tw) {
 // out[o]: the head output of this thread's row (identical in every CTA); xh / rstd: this thread's 32 normalised columns.
 template <class L>
 __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const float *img, int soff, const float *acts, float slope, float *h1t,
-                                             float (&xh)[32], float &rstd, float (&out)[L::nout], OwnRow &own) {
+                                             float (&xh)[32], float &rstd, float (&out)[L::nout], OwnRow &own, const float *next_units) {
     char *sm = k.sm;
-    const float *unit0 = img + (size_t)k.crank * 8 * 4096;            // this CTA's slice: 8 k-blocks of hi | lo
+    const float *unit0 = slice_of(k, img);                             // this CTA's slice: 8 k-blocks of hi | lo
     stage_w1<L>(k, tw);
-    stream_units(k, unit0, 0, NSLOT);                                  // lands while the first layer runs
+    stream_begin(k, unit0);                                            // lands while the first layer runs
     if (threadIdx.x == PRODUCER) mbar_expect_tx(k.bars + B_H1, 131072);
     load_pc<L>(k, tw);
     pstamp(k, 0);
@@ -333,6 +351,7 @@ __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const floa
     // every CTA's rows of the H1 image (and of the H1^T image) are in L2, and every CTA is past its last use of the
     // operand-tile region (it arrives here only after that): the multicast below may land everywhere
     cluster_sync();
+    if (k.pr && k.pb == 20 && threadIdx.x == 0) k.pr[55] = clock64();
     if (threadIdx.x == PRODUCER) {
         fence_proxy_async_all();
 #ifdef TCC_H1_UNICAST
@@ -350,9 +369,11 @@ __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const floa
         const uint32_t id = idesc(RB, NSL, 0, 0), r = smem_u32(sm + O_R) + (p == 1 ? R_LO : 0), ring = smem_u32(sm + O_RING) + (p == 2 ? 8192 : 0);
         const uint32_t acc = k.tm + 64 * p;
         tc::mbar_wait(k.bars + B_H1, k.h1_n & 1u, 960);                  // the H1 tile has landed (async proxy: no generic-proxy fence needed)
+        if (k.pr && k.pb == 20 && p == 0) k.pr[56] = clock64();
         for (int c = 0; c < 8; ++c) {
             const unsigned n = k.ring_n + (unsigned)c;
             ring_wait_full(k, n);
+            if (k.pr && k.pb == 20 && p == 0) k.pr[57 + c] = clock64();
             const uint64_t a = desc_k(r + c * 8192), b = desc_k(ring + (n % NSLOT) * SLOT_BYTES);
 #pragma unroll
             for (int s = 0; s < 4; ++s) mma_ss(acc, a + 2 * s, b + 2 * s, id, (c == 0 && s == 0) ? 0u : 1u);
@@ -365,6 +386,7 @@ __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const floa
     k.h1_n += 1u;
     pstamp(k, 2);
     acc_wait(k, 0);
+    stream_prefetch(k, next_units);
     pstamp(k, 3);
     const float *pc = reinterpret_cast<const float *>(sm + O_PC) + 32 * k.wh;
     const uint32_t lane_addr = k.tm + ((uint32_t)(k.sub * 32) << 16) + 32 * k.wh;
@@ -506,10 +528,10 @@ __device__ __forceinline__ void column_sums(Ctl &k, F val, float *dst, int dst_s
 struct BwdOut { float dz1[8], dy1[8]; int b; };   // own row (warp w <-> row 8 crank + w), lane owns n = lane + 32 j
 template <class L, bool WITH_DW>
 __device__ __forceinline__ void pass_backward(Ctl &k, const float *tw, const float *imgt, float slope, const float (&dz)[32], const OwnRow &own,
-                                              float *dh1p_unit, const float *h1t, float *gw2p_slot, BwdOut &o) {
+                                              float *dh1p_unit, const float *h1t, float *gw2p_slot, BwdOut &o, const float *next_units) {
     char *sm = k.sm;
-    const float *units = imgt + (size_t)k.crank * 8 * 4096;          // 8 sub-units: (mb, cc, hi | lo)
-    stream_units(k, units, 0, NSLOT);
+    const float *units = slice_of(k, imgt);                           // 8 sub-units: (mb, cc, hi | lo)
+    stream_begin(k, units);
     if (WITH_DW && threadIdx.x == PRODUCER) {                         // H1^T image of the row block -> the (dead) H1 region
         fence_proxy_async_all();
         mbar_expect_tx(k.bars + B_H1T, 131072);
@@ -559,6 +581,7 @@ __device__ __forceinline__ void pass_backward(Ctl &k, const float *tw, const flo
     k.ring_n += 8u;
     pstamp(k, 1);
     acc_wait(k, 0);                                                   // dH1^T complete: the ring and the dz2 tile are idle
+    if (!WITH_DW) stream_prefetch(k, next_units);
     pstamp(k, 2);
     // (3) dH1^T partial -> global [64 rows][256], coalesced along the 256 (lane = feature of H1)
     {
@@ -637,6 +660,7 @@ __device__ __forceinline__ void pass_backward(Ctl &k, const float *tw, const flo
     if (WITH_DW) {
         // (7) dW2^T partial of this row block -> global [512][256] slot, rows 64 crank .. + 63
         acc_wait(k, 1);
+        stream_prefetch(k, next_units);                               // the ring held the dz2^T tile until now
         const uint32_t lane_addr = k.tm + ((uint32_t)(k.sub * 32) << 16) + 32 * k.wh;
         float *dst = gw2p_slot + (size_t)NSL * k.crank * H1;
 #pragma unroll
@@ -718,10 +742,11 @@ __device__ __forceinline__ void gather_rows(Ctl &k, const AgentCtx &c, const hir
 //   first-layer entries are summed over slots 0 .. n1-1, second-layer small entries over slots 0, 8, 16, .. (nq of them).
 //   W2 is processed in tiles of [32 features][16 k]: reads / arena writes / forward image coalesced along k, the
 //   input-gradient image (features contiguous) through a shared-memory transpose.
-template <class L, int NPARTS>
+template <class L, int NPARTS, bool BRANCHES>
 __device__ __forceinline__ void adam_tcc(Ctl &k, int rank, int size, int ntowers, float *w, float *gw, const float *w2parts, float *m, float *v,
                                          const float *part, int n1, int nq, float neg_step, float bc2_sqrt, float *img, float *imgt,
-                                         float *target, float *timg, bool polyak, float tau, float omt) {
+                                         float *target, float *timg, bool polyak, float tau, float omt, float sc0 = 1.f, float sc1 = 1.f) {
+    // BRANCHES: the partial slots are two halves (RL branch | cloning branch) whose sums are scaled by sc0 / sc1
     // (a) everything but W2
     const int nsmall = ntowers * L::SMALL;
     for (int i = rank * TTHREADS + threadIdx.x; i < nsmall; i += size * TTHREADS) {
@@ -732,8 +757,18 @@ __device__ __forceinline__ void adam_tcc(Ctl &k, int rank, int size, int ntowers
         const float *p0 = part + (size_t)tower * L::SMALL + si;
         const size_t ps = (size_t)stride * ntowers * L::SMALL;
         float g = 0.f;
+        if (BRANCHES) {
+            float g1 = 0.f;
 #pragma unroll 8
-        for (int s = 0; s < ns; ++s) g += __ldcg(p0 + s * ps);
+            for (int s = 0; s < ns / 2; ++s) {
+                g += __ldcg(p0 + s * ps);
+                g1 += __ldcg(p0 + (s + ns / 2) * ps);
+            }
+            g = fmaf(sc0, g, sc1 * g1);
+        } else {
+#pragma unroll 8
+            for (int s = 0; s < ns; ++s) g += __ldcg(p0 + s * ps);
+        }
         gw[e] = g;
         float wv = w[e], mv = m[e], vv = v[e];
         adam_elem(g, wv, mv, vv, neg_step, bc2_sqrt);
@@ -756,8 +791,18 @@ __device__ __forceinline__ void adam_tcc(Ctl &k, int rank, int size, int ntowers
                     const int n = 32 * nb + tn + 16 * it, kk = 16 * kb + tk, i = n * H1 + kk, e = tower * L::SIZE + L::W2 + i;
                     const float *p0 = w2parts + (size_t)tower * NPARTS * H2 * H1 + i;
                     float s = __ldcg(p0);
+                    if (BRANCHES) {
+                        float s1 = __ldcg(p0 + (size_t)(NPARTS / 2) * H2 * H1);
 #pragma unroll
-                    for (int q = 1; q < NPARTS; ++q) s += __ldcg(p0 + (size_t)q * H2 * H1);
+                        for (int q = 1; q < NPARTS / 2; ++q) {
+                            s += __ldcg(p0 + (size_t)q * H2 * H1);
+                            s1 += __ldcg(p0 + (size_t)(q + NPARTS / 2) * H2 * H1);
+                        }
+                        s = fmaf(sc0, s, sc1 * s1);
+                    } else {
+#pragma unroll
+                        for (int q = 1; q < NPARTS; ++q) s += __ldcg(p0 + (size_t)q * H2 * H1);
+                    }
                     g[u][it] = s;
                     wv[u][it] = w[e]; mv[u][it] = m[e]; vv[u][it] = v[e];
                     tv[u][it] = polyak ? target[e] : 0.f;
@@ -857,7 +902,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
     k.ring_n = 0u; k.acc_n[0] = k.acc_n[1] = 0u; k.w1_n = k.h1t_n = k.h1_n = 0u; k.xr = 0u;
     k.flags = Lc.bar_flags;
     k.gen = ld_relaxed_u32(k.flags + k.cid * FLAG_STRIDE);
-    k.pr = k.pr2 = nullptr; k.pb = 0;
+    k.pr = k.pr2 = nullptr; k.pb = 0; k.pre = nullptr;
     if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot);
     if (threadIdx.x == 32) {
         for (int i = 0; i < N_BARS; ++i) tc::mbar_init(bars + i, (i >= B_EMPTY && i < B_ACC + 2) ? ISSUERS : 1);
@@ -906,7 +951,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                 // target actor on next_state (HIRL.py:264) -> a' (HIRL.py:265-267)
                 float out[A];
                 k.pb = 20;
-                pass_forward<ActorL>(k, c.tactor, c.tcc.img_tactor, SA, nullptr, slope, nullptr, xh, rstd, out, own);
+                pass_forward<ActorL>(k, c.tactor, c.tcc.img_tactor, SA, nullptr, slope, nullptr, xh, rstd, out, own, nullptr);
                 k.pb = 0;
                 if (k.crank == 0 && k.act && k.wh == 0) {
                     float ap[A];
@@ -930,7 +975,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
             float q1[1];
             float *h1t = c.tcc.H1TI + (size_t)unit * H1T_FLOATS;
             k.pb = 28;
-            pass_forward<CriticL>(k, c.critic + t * CriticL::SIZE, c.tcc.img_critic + (size_t)t * IMG_FWD, 0, nullptr, slope, h1t, xh, rstd, q1, own);
+            pass_forward<CriticL>(k, c.critic + t * CriticL::SIZE, c.tcc.img_critic + (size_t)t * IMG_FWD, 0, nullptr, slope, h1t, xh, rstd, q1, own,
+                                  slice_of(k, c.tcc.img_tcritic + (size_t)t * IMG_FWD));
             k.pb = 0;
             stamp2(k, 4);
             float *xpark = c.tcc.XHP + ((size_t)unit * RB + k.row) * H2 + NSL * k.crank + 32 * k.wh;   // the pass' state waits in L2 while the target tower uses the registers
@@ -947,7 +993,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
             {
                 float out[1];
                 OwnRow own_t;
-                pass_forward<CriticL>(k, c.tcritic + t * CriticL::SIZE, c.tcc.img_tcritic + (size_t)t * IMG_FWD, SA, acts, slope, nullptr, xh, rstd, out, own_t);
+                pass_forward<CriticL>(k, c.tcritic + t * CriticL::SIZE, c.tcc.img_tcritic + (size_t)t * IMG_FWD, SA, acts, slope, nullptr, xh, rstd, out, own_t,
+                                      slice_of(k, c.tcc.imgt_critic + (size_t)t * IMG_T));
                 tq_own = out[0];
                 if (k.crank == 0 && k.act && k.wh == 0) c.tcc.TQX[(r * 2 + t) * RB + k.row] = tq_own;
                 flag_publish(k, PF_TQ + r * 2 + t, fgen);
@@ -996,7 +1043,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
             BwdOut bo;
             k.pb = 40;
             pass_backward<CriticL, true>(k, c.critic + t * CriticL::SIZE, c.tcc.imgt_critic + (size_t)t * IMG_T, slope, dz, own,
-                                         c.tcc.DH1P + (size_t)unit * CL * RB * H1, h1t, c.tcc.GW2PC + ((size_t)t * MAX_RB + r) * H2 * H1, bo);
+                                         c.tcc.DH1P + (size_t)unit * CL * RB * H1, h1t, c.tcc.GW2PC + ((size_t)t * MAX_RB + r) * H2 * H1, bo, nullptr);
             k.pb = 0;
             ln1_param_partials<CriticL>(k, bo, own, 0, nullptr, c.tcc.PARTC + ((size_t)(r * CL + k.crank) * 2 + t) * CriticL::SMALL);
             stamp2(k, 5);
@@ -1004,7 +1051,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
         grid_sync(k);
         stamp(k, 6);
         // =============================== phase B: critic Adam ===============================
-        adam_tcc<CriticL, MAX_RB>(k, grank, gsize, 2, c.critic, c.g_critic, c.tcc.GW2PC, c.m_critic, c.v_critic, c.tcc.PARTC, CL * nrb, nrb,
+        adam_tcc<CriticL, MAX_RB, false>(k, grank, gsize, 2, c.critic, c.g_critic, c.tcc.GW2PC, c.m_critic, c.v_critic, c.tcc.PARTC, CL * nrb, nrb,
                           st.critic_neg_step, st.critic_bc2_sqrt, c.tcc.img_critic, c.tcc.imgt_critic, nullptr, nullptr, false, 0.f, 0.f);
         if (grank == gsize - 1 && threadIdx.x == 0) {
             float s0 = 0.f, s1 = 0.f;
@@ -1016,24 +1063,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
         stamp(k, 8);
         if (do_actor) {
             // =============================== phase C: actor forward / backward ===============================
-            BcWeight bw;
-            bw.w = 0.f; bw.one_minus_w = 1.f; bw.count = 0.f;
-            auto resolve_weight = [&]() {                               // HIRL.py:292-308, identical in every CTA
-                double w = (double)st.bc_weight_now;
-                if (soft) {
-                    float cnt = 0.f;
-                    for (int r = 0; r < nrb; ++r) {
-                        flag_wait(k, PF_CNT + r, fgen);
-                        cnt += __ldcg(c.tcc.CNT + 2 * r);
-                    }
-                    bw.count = cnt;
-                    const float mean = st.force_soft_weight >= 0.f ? st.force_soft_weight : cnt / (float)B;
-                    w = (double)mean + (double)st.bc_warm_up;
-                }
-                if (w > 1.0) w = 1.0;
-                bw.w = (float)w;
-                bw.one_minus_w = (float)(1.0 - w);
-            };
+            // The Q-filter weight w (HIRL.py:292-308) needs every row block's count, but both actor branches are LINEAR in their
+            // loss scale: the RL branch is back-propagated with scale 1 and the cloning branch with 2 / (A B), and phase D
+            // multiplies the summed partial gradients of a branch by (1 - w) resp. w * lambda -- nobody waits for the count.
             const int role = k.cid % 3, r = k.cid / 3;
             if (k.cid < 3 * nrb && (role != 1 || soft)) {
                 const int bg = RB * r + k.row;
@@ -1046,7 +1078,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                     // ---- role A: pi = actor(s), rl_Q = Q1(s, pi) with the updated critic (HIRL.py:295-297)
                     gather_rows(k, c, st, step, r, false);
                     float out[A], pi[A];
-                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, h1t, xh, rstd, out, own);
+                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, h1t, xh, rstd, out, own, slice_of(k, c.tcc.img_critic));
 #pragma unroll
                     for (int j = 0; j < A; ++j) pi[j] = tanhf(out[j]);
                     if (k.act && k.wh == 0) {
@@ -1065,7 +1097,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                     const float rstd_a = rstd;
                     stamp(k, 10);
                     float q[1];
-                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, nullptr, xh, rstd, q, own_q);
+                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, nullptr, xh, rstd, q, own_q, slice_of(k, c.tcc.imgt_critic));
                     stamp(k, 11);
                     float softq = 0.f;
                     if (soft) {
@@ -1084,10 +1116,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         const float rv[2] = {(valid && soft && softq > q[0]) ? 1.f : 0.f, valid ? q[0] : 0.f};    // HIRL.py:303, :297
                         column_sums<0, 2>(k, [&](int, int) { return 0.f; }, nullptr, 0, rv, k.crank == 0 ? rsum : nullptr);
                         if (k.crank == 0 && threadIdx.x == 0) { c.tcc.CNT[2 * r] = rsum[0]; c.tcc.CNT[2 * r + 1] = rsum[1]; }
-                        flag_publish(k, PF_CNT + r, fgen);
                     }
                     BwdOut bo;
-                    pass_backward<CriticL, false>(k, c.critic, c.tcc.imgt_critic, slope, dz, own_q, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, nullptr, nullptr, bo);
+                    pass_backward<CriticL, false>(k, c.critic, c.tcc.imgt_critic, slope, dz, own_q, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, nullptr, nullptr, bo,
+                                                  slice_of(k, c.tcc.imgt_actor));
                     {
                         float g[A];
 #pragma unroll
@@ -1105,8 +1137,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         cluster_sync();
                     }
                     stamp(k, 12);
-                    resolve_weight();
-                    stamp(k, 13);
                     // actor backward, RL branch
                     load_pc<ActorL>(k, c.actor);
                     if (k.act) {
@@ -1121,7 +1151,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                     float dpre[A];
 #pragma unroll
                     for (int j = 0; j < A; ++j) {
-                        const float dpi = valid ? bw.one_minus_w * gpi[k.row * 4 + j] : 0.f;
+                        const float dpi = valid ? gpi[k.row * 4 + j] : 0.f;
                         dpre[j] = dpi * (1.f - pi[j] * pi[j]);
                     }
                     head_ln2_backward<ActorL>(k, xh, rstd_a, dpre, slope, dz, dy, h);
@@ -1132,14 +1162,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                                           dpre, k.crank == 0 ? part + ActorL::small_index(ActorL::B3) : nullptr);
                     }
                     pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, slope, dz, own, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, h1t,
-                                                c.tcc.GW2PA + (size_t)r * H2 * H1, bo);
+                                                c.tcc.GW2PA + (size_t)r * H2 * H1, bo, nullptr);
                     ln1_param_partials<ActorL>(k, bo, own, 0, nullptr, c.tcc.PARTA + (size_t)(r * CL + k.crank) * ActorL::SMALL);
                     stamp(k, 14);
                 } else if (role == 1) {
                     // ---- role S: a_bc = bc_actor(s), soft_Q = Q1(s, a_bc) (HIRL.py:300-302)
                     gather_rows(k, c, st, step, r, false);
                     float out[A];
-                    pass_forward<ActorL>(k, c.bc, c.tcc.img_bc, 0, nullptr, slope, nullptr, xh, rstd, out, own);
+                    pass_forward<ActorL>(k, c.bc, c.tcc.img_bc, 0, nullptr, slope, nullptr, xh, rstd, out, own, slice_of(k, c.tcc.img_critic));
                     if (k.act && k.wh == 0) {
 #pragma unroll
                         for (int j = 0; j < A; ++j) {
@@ -1149,14 +1179,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         }
                     }
                     float q[1];
-                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, nullptr, xh, rstd, q, own_q);
+                    pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, nullptr, xh, rstd, q, own_q, nullptr);
                     if (k.crank == 0 && k.act && k.wh == 0) c.tcc.SOFTQX[r * RB + k.row] = q[0];
                     flag_publish(k, PF_SOFTQ + r, fgen);
                 } else {
                     // ---- role AB: pi_bc = actor(s_bc), cloning loss (HIRL.py:310-319), actor backward of the BC branch
                     gather_rows(k, c, st, step, r, true);
                     float out[A], pi[A], diff[A];
-                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, h1t, xh, rstd, out, own);
+                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, h1t, xh, rstd, out, own, slice_of(k, c.tcc.imgt_actor));
                     const float *xs = reinterpret_cast<const float *>(k.sm + O_X);
                     float sq = 0.f;
 #pragma unroll
@@ -1174,12 +1204,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         const float rv[2] = {valid ? sq : 0.f, valid ? fire : 0.f};
                         column_sums<0, 2>(k, [&](int, int) { return 0.f; }, nullptr, 0, rv, k.crank == 0 ? c.tcc.LPT + 8 + 2 * r : nullptr);
                     }
-                    resolve_weight();
-                    const float bc_scale = bw.w * c.loss_lambda;
                     float dpre[A];
 #pragma unroll
                     for (int j = 0; j < A; ++j) {
-                        const float dpi = valid ? ((2.f / (float)(A * B)) * diff[j]) * bc_scale : 0.f;
+                        const float dpi = valid ? (2.f / (float)(A * B)) * diff[j] : 0.f;
                         dpre[j] = dpi * (1.f - pi[j] * pi[j]);
                     }
                     float dz[32], dy[32], h[32];
@@ -1192,30 +1220,36 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                     }
                     BwdOut bo;
                     pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, slope, dz, own, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, h1t,
-                                                c.tcc.GW2PA + (size_t)(MAX_RB + r) * H2 * H1, bo);
+                                                c.tcc.GW2PA + (size_t)(MAX_RB + r) * H2 * H1, bo, nullptr);
                     ln1_param_partials<ActorL>(k, bo, own, 0, nullptr, c.tcc.PARTA + (size_t)((MAX_RB + r) * CL + k.crank) * ActorL::SMALL);
                 }
             }
             grid_sync(k);
             stamp(k, 15);
             // =============================== phase D: actor Adam, Polyak, scalars ===============================
-            adam_tcc<ActorL, 2 * MAX_RB>(k, grank, gsize, 1, c.actor, c.g_actor, c.tcc.GW2PA, c.m_actor, c.v_actor, c.tcc.PARTA, 2 * MAX_RB * CL, 2 * MAX_RB,
-                             st.actor_neg_step, st.actor_bc2_sqrt, c.tcc.img_actor, c.tcc.imgt_actor, c.tactor, c.tcc.img_tactor, do_polyak, tau, omt);
-            if (do_polyak) polyak_tcc<CriticL>(grank, gsize, 2, c.critic, c.tcritic, c.tcc.img_tcritic, tau, omt);
-            if (grank == gsize - 1 && threadIdx.x == 0) {
-                // the weight once more, from the published counts (every flag has been passed by now)
+            // the Q-filter weight from the published counts (HIRL.py:292-308), identical in every thread
+            float wf, omw, cnt = 0.f;
+            {
                 double w = (double)st.bc_weight_now;
-                float cnt = 0.f, sumq = 0.f, bsq = 0.f, fsq = 0.f;
-                for (int r = 0; r < nrb; ++r) {
-                    cnt += __ldcg(c.tcc.CNT + 2 * r); sumq += __ldcg(c.tcc.CNT + 2 * r + 1);
-                    bsq += __ldcg(c.tcc.LPT + 8 + 2 * r); fsq += __ldcg(c.tcc.LPT + 8 + 2 * r + 1);
-                }
                 if (soft) {
+                    for (int r = 0; r < nrb; ++r) cnt += __ldcg(c.tcc.CNT + 2 * r);
                     const float mean = st.force_soft_weight >= 0.f ? st.force_soft_weight : cnt / (float)B;
                     w = (double)mean + (double)st.bc_warm_up;
-                } else cnt = 0.f;
+                }
                 if (w > 1.0) w = 1.0;
-                const float wf = (float)w, omw = (float)(1.0 - w);
+                wf = (float)w;
+                omw = (float)(1.0 - w);
+            }
+            adam_tcc<ActorL, 2 * MAX_RB, true>(k, grank, gsize, 1, c.actor, c.g_actor, c.tcc.GW2PA, c.m_actor, c.v_actor, c.tcc.PARTA, 2 * MAX_RB * CL, 2 * MAX_RB,
+                             st.actor_neg_step, st.actor_bc2_sqrt, c.tcc.img_actor, c.tcc.imgt_actor, c.tactor, c.tcc.img_tactor, do_polyak, tau, omt,
+                             omw, wf * c.loss_lambda);
+            if (do_polyak) polyak_tcc<CriticL>(grank, gsize, 2, c.critic, c.tcritic, c.tcc.img_tcritic, tau, omt);
+            if (grank == gsize - 1 && threadIdx.x == 0) {
+                float sumq = 0.f, bsq = 0.f, fsq = 0.f;
+                for (int r = 0; r < nrb; ++r) {
+                    sumq += __ldcg(c.tcc.CNT + 2 * r + 1);
+                    bsq += __ldcg(c.tcc.LPT + 8 + 2 * r); fsq += __ldcg(c.tcc.LPT + 8 + 2 * r + 1);
+                }
                 const float rl_loss = -(sumq / (float)B);                                                     // HIRL.py:297
                 const float bc_loss = __fmul_rn(bsq / (float)(A * B), c.loss_lambda);                          // HIRL.py:311
                 c.carry[1] = __fadd_rn(__fmul_rn(bc_loss, wf), __fmul_rn(rl_loss, omw));                       // HIRL.py:321
@@ -1223,9 +1257,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                 c.carry[3] = rl_loss;
                 c.carry[4] = fsq / (float)B;                                                                   // HIRL.py:319 (x lambda on the host)
                 c.carry[5] = wf;
-                c.carry[6] = cnt;
+                c.carry[6] = soft ? cnt : 0.f;
             }
-            grid_sync(k);
+            // the next call's phase A reads nothing that phase D writes unless the targets moved (Polyak): no grid barrier then
+            if (do_polyak || step + 1 == Lc.k_steps) grid_sync(k);
+            else __syncthreads();
             stamp(k, 16);
         }
         if (grank == gsize - 1 && threadIdx.x < HIRL_OUT_SCALARS) c.out_scalars[(size_t)step * HIRL_OUT_SCALARS + threadIdx.x] = c.carry[threadIdx.x];

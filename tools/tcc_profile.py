@@ -20,7 +20,7 @@ ONLINE = [(17, "A/tower unit: gather"), (4, "A/tower unit: critic forward pass")
           (37, "A/tower unit: TD target, loss, head/LN2 backward, small-param column sums"), (5, "A/tower unit: backward GEMMs, LN1 backward, partials")]
 MAIN = [(1, "A/target-actor unit: gather"), (2, "A/target-actor unit: target actor pass -> a' published"),
         (6, "grid barrier (after the slower chain)"), (7, "B: critic Adam + images"), (8, "grid barrier"),
-        (10, "C: gather, actor pass -> pi"), (11, "C: Q1(s,pi) pass"), (12, "C: soft count, Q backward -> d pi"), (13, "C: wait for every row block's count"),
+        (10, "C: gather, actor pass -> pi"), (11, "C: Q1(s,pi) pass"), (12, "C: soft count, Q backward -> d pi"),
         (14, "C: actor backward (RL branch)"), (15, "grid barrier"), (16, "D: actor Adam, Polyak, images + grid barrier")]
 FWD = ["stream begin + param cache", "first layer of the own 8 rows -> H1 image in L2", "cluster barrier, multicast, MMA issue", "wait for the accumulator", "TMEM -> registers, local LN stats",
        "exchange 1 (LN statistics)", "normalise, head partial, exchange 2"]
@@ -68,6 +68,10 @@ def main():
                 continue
             print(f"  {label:66s} {us(p[i] - prev):8.2f} us   (t = {us(p[i] - p[0]):8.2f})")
             prev = p[i]
+        if p[55]:
+            t0 = p[21]
+            print("    target actor pass, after the first layer: cluster barrier +%.2f | H1 tile landed +%.2f | W2 unit c landed (issuer 0 past its wait): %s us" % (
+                us(p[55] - t0), us(p[56] - t0), " ".join(f"+{us(p[57 + c] - t0):.2f}" for c in range(8))))
         for base, name, labels, start in ((20, "target actor pass", FWD, p[1]), (28, "critic forward pass", FWD, p[17]), (40, "critic backward", BWD, p[37])):
             print(f"    -- inside the {name}:")
             prev = start
