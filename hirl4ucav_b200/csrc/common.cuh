@@ -125,7 +125,10 @@ struct TccPtrs {
     float *PARTC;    // [4 row blocks * 8 CTAs][2 towers][CriticL::SMALL] small-parameter partials
     float *PARTA;    // [2 branches * 4 row blocks * 8 CTAs][ActorL::SMALL]
     float *TQX;      // [4][2][64] target Q of a tower, exchanged between the two tower clusters of a row block
-    float *SOFTQX;   // [4][64]
+    float *RLQX;     // [4][64] Q1(s, pi) of a row block, published by role A for role S' count
+    float *PIX;      // [4][64][4] pi = actor(s), evaluated by phase A's actor units
+    float *RSA;      // [4][64] rstd of LayerNorm2 of that pass
+    float *OWNP;     // [4][64][H1 + 32] xhat1 (+ rstd1) of that pass
     float *APX;      // [4][64][4] a' of a row block, published by its target-actor unit
     float *XHP;      // [8 units][64][H2] normalised second-layer rows of the critic forward pass, parked while the target tower runs
     float *XH2S;     // [4][64][H2] normalised second-layer rows of the actor pass, parked while the Q pass runs

@@ -604,7 +604,10 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
             if ((rc = dev_alloc(h, &t.PARTC, (size_t)tcc::MAX_RB * tcc::CL * 2 * CriticL::SMALL))) return rc;
             if ((rc = dev_alloc(h, &t.PARTA, (size_t)2 * tcc::MAX_RB * tcc::CL * ActorL::SMALL))) return rc;
             if ((rc = dev_alloc(h, &t.TQX, (size_t)tcc::MAX_RB * 2 * tcc::RB))) return rc;
-            if ((rc = dev_alloc(h, &t.SOFTQX, (size_t)tcc::MAX_RB * tcc::RB))) return rc;
+            if ((rc = dev_alloc(h, &t.RLQX, (size_t)tcc::MAX_RB * tcc::RB))) return rc;
+            if ((rc = dev_alloc(h, &t.PIX, (size_t)tcc::MAX_RB * tcc::RB * 4))) return rc;
+            if ((rc = dev_alloc(h, &t.RSA, (size_t)tcc::MAX_RB * tcc::RB))) return rc;
+            if ((rc = dev_alloc(h, &t.OWNP, (size_t)tcc::MAX_RB * tcc::RB * (H1 + 32)))) return rc;
             if ((rc = dev_alloc(h, &t.XH2S, (size_t)tcc::MAX_RB * tcc::RB * H2))) return rc;
             if ((rc = dev_alloc(h, &t.H1TI, (size_t)tcc::MAX_NCL * tcc::H1T_FLOATS))) return rc;
             if ((rc = dev_alloc(h, &t.APX, (size_t)tcc::MAX_RB * tcc::RB * 4))) return rc;

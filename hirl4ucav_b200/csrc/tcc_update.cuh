@@ -21,7 +21,8 @@
 //            gradients of a branch in phase D: (1 - w) resp. w * lambda.  Nobody waits for the count.
 //   ---- grid barrier ----
 //   phase D  actor Adam, Polyak every 3rd actor update (HIRL.py:327-330), operand images, returned scalars
-//   ---- grid barrier, only if the targets moved (the next call's phase A reads nothing else that phase D writes) ----
+//   ---- grid barrier, only if the targets moved or the next call is an actor call (phase A of a critic-only call reads
+//        nothing else that phase D writes) ----
 //
 // CTA j of a cluster owns the output features 64 j .. 64 j + 63 of the 512-wide layers.  Per pass:
 //   * first layer (K = 13 / 17) + LayerNorm1 + activation ONCE PER CLUSTER: warp w of CTA j evaluates batch row 8 j + w in
@@ -90,7 +91,7 @@ __host__ __device__ __forceinline__ size_t img_t_index(int n, int k) {       // 
 }
 
 // p2p flag words (each on its own 128-byte line)
-enum { PF_TQ = 0 /* [r][t] */, PF_SOFTQ = 8 /* [r] */, PF_CNT = 12 /* [r] */, PF_AP = 16 /* [r] */, PF_WORDS = 20 };
+enum { PF_TQ = 0 /* [r][t] */, PF_RLQ = 8 /* [r] */, PF_CNT = 12 /* [r] */, PF_AP = 16 /* [r] */, PF_WORDS = 20 };
 constexpr int PROF_WORDS = 96;
 enum { B_FULL = 0, B_EMPTY = NSLOT, B_ACC = 2 * NSLOT, B_W1 = 2 * NSLOT + 2, B_H1T, B_H1, B_X0, B_X1, N_BARS };
 
@@ -323,6 +324,29 @@ __device__ __forceinline__ void load_pc(const Ctl &k, const float *tw) {
     }
     if (threadIdx.x < L::nout) pc[448 + threadIdx.x] = tw[L::B3 + threadIdx.x];
 }
+// the same in two halves: the loads are issued at the top of a pass, the shared-memory stores follow the first layer (whose own
+// parameter loads are then in flight at the same time: one exposed L2 round trip instead of two)
+template <class L>
+__device__ __forceinline__ void pc_fetch(const Ctl &k, const float *tw, float (&v)[2], float &b3v) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int i = threadIdx.x + q * TTHREADS;
+        const int a = i >> 6, c = i & 63;
+        const int off = a == 0 ? L::B2 : a == 1 ? L::G2 : a == 2 ? L::BE2 : L::W3 + (a - 3) * H2;
+        v[q] = i < (3 + L::nout) * NSL ? tw[off + NSL * k.crank + c] : 0.f;
+    }
+    b3v = threadIdx.x < L::nout ? tw[L::B3 + threadIdx.x] : 0.f;
+}
+template <class L>
+__device__ __forceinline__ void pc_store(const Ctl &k, const float (&v)[2], float b3v) {
+    float *pc = reinterpret_cast<float *>(k.sm + O_PC);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int i = threadIdx.x + q * TTHREADS;
+        if (i < (3 + L::nout) * NSL) pc[i] = v[q];
+    }
+    if (threadIdx.x < L::nout) pc[448 + threadIdx.x] = b3v;
+}
 // first-layer weight matrix of the pass into shared memory (one bulk copy)
 template <class L>
 __device__ __forceinline__ void stage_w1(Ctl &k, const float *tw) {
@@ -341,12 +365,14 @@ __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const floa
                                              float (&xh)[32], float &rstd, float (&out)[L::nout], OwnRow &own, const float *next_units) {
     char *sm = k.sm;
     const float *unit0 = slice_of(k, img);                             // this CTA's slice: 8 k-blocks of hi | lo
+    float pcv[2], b3v;
+    pc_fetch<L>(k, tw, pcv, b3v);
     stage_w1<L>(k, tw);
     stream_begin(k, unit0);                                            // lands while the first layer runs
     if (threadIdx.x == PRODUCER) mbar_expect_tx(k.bars + B_H1, 131072);
-    load_pc<L>(k, tw);
     pstamp(k, 0);
     l1_rows<L>(k, tw, soff, acts, slope, k.h1img, h1t, own);
+    pc_store<L>(k, pcv, b3v);                                          // read after the cluster barrier below
     pstamp(k, 1);
     // every CTA's rows of the H1 image (and of the H1^T image) are in L2, and every CTA is past its last use of the
     // operand-tile region (it arrives here only after that): the multicast below may land everywhere
@@ -742,7 +768,7 @@ __device__ __forceinline__ void gather_rows(Ctl &k, const AgentCtx &c, const hir
 //   first-layer entries are summed over slots 0 .. n1-1, second-layer small entries over slots 0, 8, 16, .. (nq of them).
 //   W2 is processed in tiles of [32 features][16 k]: reads / arena writes / forward image coalesced along k, the
 //   input-gradient image (features contiguous) through a shared-memory transpose.
-template <class L, int NPARTS, bool BRANCHES>
+template <class L, int NPARTS, bool BRANCHES, int UB>
 __device__ __forceinline__ void adam_tcc(Ctl &k, int rank, int size, int ntowers, float *w, float *gw, const float *w2parts, float *m, float *v,
                                          const float *part, int n1, int nq, float neg_step, float bc2_sqrt, float *img, float *imgt,
                                          float *target, float *timg, bool polyak, float tau, float omt, float sc0 = 1.f, float sc1 = 1.f) {
@@ -778,7 +804,6 @@ __device__ __forceinline__ void adam_tcc(Ctl &k, int rank, int size, int ntowers
     // (b) W2 tiles, up to 3 tiles' loads in flight per CTA (the loop is bound by L2 round trips, not by arithmetic)
     float *ts = reinterpret_cast<float *>(k.sm + O_R);                 // [32 features][17]
     const int tiles = ntowers * 16 * 16, tk = threadIdx.x & 15, tn = threadIdx.x >> 4;
-    constexpr int UB = 3;
     for (int t0 = rank; t0 < tiles; t0 += UB * size) {
         float g[UB][2], wv[UB][2], mv[UB][2], vv[UB][2], tv[UB][2];
 #pragma unroll
@@ -940,10 +965,39 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
         // units nrb .. 3 nrb - 1: critic tower (r, t): forward on (s, a) while the target actor runs, then the target tower on
         // (s', a'), the TD target with the partner tower's target Q, loss and the backward pass.
         // 3 nrb <= 12 clusters carry the phase (B200 co-schedules 15 clusters of 8 CTAs).
+        //   on actor calls, units 3 nrb .. 4 nrb - 1: ACTOR forward unit r: pi = actor(s) (HIRL.py:295) depends on nothing phase A or B
+        //   changes, so it runs here on clusters that would idle (its state is parked in L2 for phase C's role A)
+        const int nunits_a = 3 * nrb + (do_actor ? nrb : 0);
 #pragma unroll 1
-        for (int ua = k.cid; ua < 3 * nrb; ua += k.ncl) {
+        for (int ua = k.cid; ua < nunits_a; ua += k.ncl) {
             float xh[32], rstd;
             OwnRow own;
+            if (ua >= 3 * nrb) {
+                const int r = ua - 3 * nrb;
+                const int bg = RB * r + k.row;
+                gather_rows(k, c, st, step, r, false);
+                float out[A];
+                pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, c.tcc.H1TI + (size_t)(12 + r) * H1T_FLOATS, xh, rstd, out, own, nullptr);
+                if (k.crank == 0 && k.act && k.wh == 0) {
+                    const float4 pi = make_float4(tanhf(out[0]), tanhf(out[1]), tanhf(out[2]), tanhf(out[3]));
+                    st4(c.tcc.PIX + (r * RB + k.row) * 4, pi);
+                    c.tcc.RSA[r * RB + k.row] = rstd;
+                    if (bg < B) st4(c.sc.PI + (size_t)bg * A, pi);
+                }
+                if (k.act) {
+                    float *xs2 = c.tcc.XH2S + ((size_t)r * RB + k.row) * H2 + NSL * k.crank + 32 * k.wh;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) st4(xs2 + e, make_float4(xh[e], xh[e + 1], xh[e + 2], xh[e + 3]));
+                }
+                {
+                    const int b = 8 * k.crank + k.warp;                 // the row this warp owns
+                    float *op = c.tcc.OWNP + ((size_t)r * RB + b) * (H1 + 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) op[k.lane + 32 * j] = own.xh1[j];
+                    if (k.lane == 0) op[H1] = own.rstd1;
+                }
+                continue;
+            }
             if (ua < nrb) {
                 const int r = ua;
                 gather_rows(k, c, st, step, r, false);
@@ -1051,7 +1105,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
         grid_sync(k);
         stamp(k, 6);
         // =============================== phase B: critic Adam ===============================
-        adam_tcc<CriticL, MAX_RB, false>(k, grank, gsize, 2, c.critic, c.g_critic, c.tcc.GW2PC, c.m_critic, c.v_critic, c.tcc.PARTC, CL * nrb, nrb,
+        adam_tcc<CriticL, MAX_RB, false, 5>(k, grank, gsize, 2, c.critic, c.g_critic, c.tcc.GW2PC, c.m_critic, c.v_critic, c.tcc.PARTC, CL * nrb, nrb,
                           st.critic_neg_step, st.critic_bc2_sqrt, c.tcc.img_critic, c.tcc.imgt_critic, nullptr, nullptr, false, 0.f, 0.f);
         if (grank == gsize - 1 && threadIdx.x == 0) {
             float s0 = 0.f, s1 = 0.f;
@@ -1072,50 +1126,35 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                 const bool valid = bg < B;
                 float xh[32], rstd;
                 OwnRow own, own_q;
-                float *h1t = c.tcc.H1TI + (size_t)k.cid * H1T_FLOATS;
+                float *h1t = c.tcc.H1TI + (size_t)(role == 0 ? 12 + r : k.cid) * H1T_FLOATS;   // role A: written by phase A's actor unit
                 float *rsum = c.tcc.RSUM + 8 * k.cid;
                 if (role == 0) {
-                    // ---- role A: pi = actor(s), rl_Q = Q1(s, pi) with the updated critic (HIRL.py:295-297)
+                    // ---- role A: rl_Q = Q1(s, pi) with the updated critic (HIRL.py:296-297); pi = actor(s) was evaluated in phase A
                     gather_rows(k, c, st, step, r, false);
-                    float out[A], pi[A];
-                    pass_forward<ActorL>(k, c.actor, c.tcc.img_actor, 0, nullptr, slope, h1t, xh, rstd, out, own, slice_of(k, c.tcc.img_critic));
-#pragma unroll
-                    for (int j = 0; j < A; ++j) pi[j] = tanhf(out[j]);
-                    if (k.act && k.wh == 0) {
-#pragma unroll
-                        for (int j = 0; j < A; ++j) acts[k.row * 4 + j] = pi[j];
-                        if (k.crank == 0 && valid) {
-#pragma unroll
-                            for (int j = 0; j < A; ++j) c.sc.PI[(size_t)bg * A + j] = pi[j];
-                        }
+                    float pi[A];
+                    {
+                        const float4 p4 = __ldcg(reinterpret_cast<const float4 *>(c.tcc.PIX + (r * RB + k.row) * 4));
+                        pi[0] = p4.x; pi[1] = p4.y; pi[2] = p4.z; pi[3] = p4.w;
+                        if (k.act && k.wh == 0) *reinterpret_cast<float4 *>(acts + k.row * 4) = p4;
                     }
-                    if (k.act) {                                        // the actor pass' state is parked in L2 while the Q pass uses the registers
-                        float *xs2 = c.tcc.XH2S + ((size_t)r * RB + k.row) * H2 + NSL * k.crank + 32 * k.wh;
-#pragma unroll
-                        for (int e = 0; e < 32; e += 4) st4(xs2 + e, make_float4(xh[e], xh[e + 1], xh[e + 2], xh[e + 3]));
-                    }
-                    const float rstd_a = rstd;
+                    const float rstd_a = __ldcg(c.tcc.RSA + r * RB + k.row);
                     stamp(k, 10);
                     float q[1];
                     pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, nullptr, xh, rstd, q, own_q, slice_of(k, c.tcc.imgt_critic));
                     stamp(k, 11);
-                    float softq = 0.f;
-                    if (soft) {
-                        flag_wait(k, PF_SOFTQ + r, fgen);
-                        softq = __ldcg(c.tcc.SOFTQX + r * RB + k.row);
+                    if (k.crank == 0 && k.act && k.wh == 0) {
+                        c.tcc.RLQX[r * RB + k.row] = q[0];
+                        if (valid) c.sc.RLQ[bg] = q[0];
                     }
-                    if (k.crank == 0 && k.act && k.wh == 0 && valid) {
-                        c.sc.RLQ[bg] = q[0];
-                        if (soft) c.sc.SOFTQ[bg] = softq;
-                    }
+                    if (soft) flag_publish(k, PF_RLQ + r, fgen);        // role S compares its soft Q with it (HIRL.py:303)
                     // backward of rl_loss = -mean(Q1) to the action input; (1 - w) is applied where it meets the actor
                     float dout[1] = {valid ? -1.f / (float)B : 0.f};
                     float dz[32], dy[32], h[32];
                     head_ln2_backward<CriticL>(k, xh, rstd, dout, slope, dz, dy, h);
                     {
-                        const float rv[2] = {(valid && soft && softq > q[0]) ? 1.f : 0.f, valid ? q[0] : 0.f};    // HIRL.py:303, :297
+                        const float rv[2] = {0.f, valid ? q[0] : 0.f};                                           // HIRL.py:297
                         column_sums<0, 2>(k, [&](int, int) { return 0.f; }, nullptr, 0, rv, k.crank == 0 ? rsum : nullptr);
-                        if (k.crank == 0 && threadIdx.x == 0) { c.tcc.CNT[2 * r] = rsum[0]; c.tcc.CNT[2 * r + 1] = rsum[1]; }
+                        if (k.crank == 0 && threadIdx.x == 0) c.tcc.CNT[2 * r + 1] = rsum[1];
                     }
                     BwdOut bo;
                     pass_backward<CriticL, false>(k, c.critic, c.tcc.imgt_critic, slope, dz, own_q, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, nullptr, nullptr, bo,
@@ -1137,8 +1176,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         cluster_sync();
                     }
                     stamp(k, 12);
-                    // actor backward, RL branch
+                    // actor backward, RL branch (state of the actor pass: parked by phase A's actor unit)
                     load_pc<ActorL>(k, c.actor);
+                    {
+                        const float *op = c.tcc.OWNP + ((size_t)r * RB + 8 * k.crank + k.warp) * (H1 + 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) own.xh1[j] = __ldcg(op + k.lane + 32 * j);
+                        own.rstd1 = __ldcg(op + H1);
+                    }
                     if (k.act) {
                         const float *xs2 = c.tcc.XH2S + ((size_t)r * RB + k.row) * H2 + NSL * k.crank + 32 * k.wh;
 #pragma unroll
@@ -1180,8 +1225,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                     }
                     float q[1];
                     pass_forward<CriticL>(k, c.critic, c.tcc.img_critic, 0, acts, slope, nullptr, xh, rstd, q, own_q, nullptr);
-                    if (k.crank == 0 && k.act && k.wh == 0) c.tcc.SOFTQX[r * RB + k.row] = q[0];
-                    flag_publish(k, PF_SOFTQ + r, fgen);
+                    // the count of soft_Q > rl_Q over the row block (HIRL.py:303); rl_Q comes from role A's unit
+                    flag_wait(k, PF_RLQ + r, fgen);
+                    const float rlq = __ldcg(c.tcc.RLQX + r * RB + k.row);
+                    if (k.crank == 0 && k.act && k.wh == 0 && valid) c.sc.SOFTQ[bg] = q[0];
+                    const float rv[2] = {(valid && q[0] > rlq) ? 1.f : 0.f, 0.f};
+                    column_sums<0, 2>(k, [&](int, int) { return 0.f; }, nullptr, 0, rv, k.crank == 0 ? rsum : nullptr);
+                    if (k.crank == 0 && threadIdx.x == 0) c.tcc.CNT[2 * r] = rsum[0];
                 } else {
                     // ---- role AB: pi_bc = actor(s_bc), cloning loss (HIRL.py:310-319), actor backward of the BC branch
                     gather_rows(k, c, st, step, r, true);
@@ -1240,7 +1290,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                 wf = (float)w;
                 omw = (float)(1.0 - w);
             }
-            adam_tcc<ActorL, 2 * MAX_RB, true>(k, grank, gsize, 1, c.actor, c.g_actor, c.tcc.GW2PA, c.m_actor, c.v_actor, c.tcc.PARTA, 2 * MAX_RB * CL, 2 * MAX_RB,
+            adam_tcc<ActorL, 2 * MAX_RB, true, 3>(k, grank, gsize, 1, c.actor, c.g_actor, c.tcc.GW2PA, c.m_actor, c.v_actor, c.tcc.PARTA, 2 * MAX_RB * CL, 2 * MAX_RB,
                              st.actor_neg_step, st.actor_bc2_sqrt, c.tcc.img_actor, c.tcc.imgt_actor, c.tactor, c.tcc.img_tactor, do_polyak, tau, omt,
                              omw, wf * c.loss_lambda);
             if (do_polyak) polyak_tcc<CriticL>(grank, gsize, 2, c.critic, c.tcritic, c.tcc.img_tcritic, tau, omt);
@@ -1260,7 +1310,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                 c.carry[6] = soft ? cnt : 0.f;
             }
             // the next call's phase A reads nothing that phase D writes unless the targets moved (Polyak): no grid barrier then
-            if (do_polyak || step + 1 == Lc.k_steps) grid_sync(k);
+            if (do_polyak || step + 1 == Lc.k_steps || c.steps[step + 1].do_actor != 0) grid_sync(k);
             else __syncthreads();
             stamp(k, 16);
         }

@@ -20,7 +20,7 @@ ONLINE = [(17, "A/tower unit: gather"), (4, "A/tower unit: critic forward pass")
           (37, "A/tower unit: TD target, loss, head/LN2 backward, small-param column sums"), (5, "A/tower unit: backward GEMMs, LN1 backward, partials")]
 MAIN = [(1, "A/target-actor unit: gather"), (2, "A/target-actor unit: target actor pass -> a' published"),
         (6, "grid barrier (after the slower chain)"), (7, "B: critic Adam + images"), (8, "grid barrier"),
-        (10, "C: gather, actor pass -> pi"), (11, "C: Q1(s,pi) pass"), (12, "C: soft count, Q backward -> d pi"),
+        (10, "C: gather, parked pi of the phase-A actor unit"), (11, "C: Q1(s,pi) pass"), (12, "C: soft count, Q backward -> d pi"),
         (14, "C: actor backward (RL branch)"), (15, "grid barrier"), (16, "D: actor Adam, Polyak, images + grid barrier")]
 FWD = ["stream begin + param cache", "first layer of the own 8 rows -> H1 image in L2", "cluster barrier, multicast, MMA issue", "wait for the accumulator", "TMEM -> registers, local LN stats",
        "exchange 1 (LN statistics)", "normalise, head partial, exchange 2"]
