@@ -246,7 +246,7 @@ __device__ __forceinline__ void publish_operands() {
 // own: xhat1 / rstd1 of the row, kept for the backward pass.  h1t (may be null): global H1^T image; this warp writes its column.
 struct OwnRow { float xh1[8], rstd1; };
 template <class L>
-__device__ __forceinline__ void l1_rows(Ctl &k, const float *tw, int soff, const float *acts, float slope, float *h1img, float *h1t, OwnRow &own) {
+__device__ __forceinline__ void l1_rows(Ctl &k, const float *tw, int soff, const float *acts, float slope, float *h1img, float (&hrow)[8], OwnRow &own) {
     const float *xs = reinterpret_cast<const float *>(k.sm + O_X), *w1s = reinterpret_cast<const float *>(k.sm + O_W1);
     const int lane = k.lane, b = 8 * k.crank + k.warp;
     float b1[8], g1[8], be1[8], z[8];
@@ -282,7 +282,6 @@ __device__ __forceinline__ void l1_rows(Ctl &k, const float *tw, int soff, const
     const float rstd = 1.f / sqrtf(v * (1.f / H1) + LN_EPS);
     own.rstd1 = rstd;
     float *dst = h1img + sw128_words(b, lane);
-    float *tst = reinterpret_cast<float *>(k.sm + O_R);               // [8 rows][256] staging of the transposed image (the operand tile is idle here)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float xh = (z[j] - s) * rstd;
@@ -291,19 +290,34 @@ __device__ __forceinline__ void l1_rows(Ctl &k, const float *tw, int soff, const
         own.xh1[j] = xh;
         dst[j * 2048] = hi;
         dst[16384 + j * 2048] = hv - hi;
-        if (h1t) tst[k.warp * H1 + lane + 32 * j] = hv;
+        hrow[j] = hv;
     }
-    if (h1t) {
-        // H1^T image [256 n][64 b] (K-major along b): thread n writes this CTA's 8 batch rows = one 32-byte sector hi, one lo
-        __syncthreads();
-        const int n = threadIdx.x, b0 = 8 * k.crank;
+}
+// H1^T image [256 n][64 b] (K-major along b) of a back-propagated pass: written AFTER the multicast of the forward tile has
+// been issued and WHILE the MMAs are issued (warps 0-2 issue, warp 3 streams the weights, warps 4-7 write the image): off the
+// critical path.  Staged through the W1 region, which is dead once every warp has left the first layer (the cluster barrier
+// in between).  A writer thread handles two columns n: this CTA's 8 batch rows = one 32-byte sector hi, one lo each.
+// Visibility for the bulk load in pass_backward: the next cluster barrier / grid barrier of the unit (see the call sites).
+__device__ __forceinline__ void h1t_stage(Ctl &k, const float (&hrow)[8]) {   // all warps
+    float *tst = reinterpret_cast<float *>(k.sm + O_W1);               // [8 rows][256]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tst[k.warp * H1 + k.lane + 32 * j] = hrow[j];
+    if (k.warp < 4) asm volatile("bar.arrive 1, 256;" ::: "memory");
+    else asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+__device__ __forceinline__ void h1t_write(Ctl &k, float *h1t) {               // warps 4-7
+    const float *tst = reinterpret_cast<const float *>(k.sm + O_W1);
+    const int b0 = 8 * k.crank;
+    float *t = h1t + (size_t)(b0 >> 5) * 8192;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int n = (int)threadIdx.x - 128 + 128 * half;
         float hv[8], hi[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             hv[i] = tst[i * H1 + n];
             hi[i] = tf32_hi(hv[i]);
         }
-        float *t = h1t + (size_t)(b0 >> 5) * 8192;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             float *w = t + sw128_words(n, (b0 & 31) + 4 * q);
@@ -371,7 +385,8 @@ __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const floa
     stream_begin(k, unit0);                                            // lands while the first layer runs
     if (threadIdx.x == PRODUCER) mbar_expect_tx(k.bars + B_H1, 131072);
     pstamp(k, 0);
-    l1_rows<L>(k, tw, soff, acts, slope, k.h1img, h1t, own);
+    float hrow[8];
+    l1_rows<L>(k, tw, soff, acts, slope, k.h1img, hrow, own);
     pc_store<L>(k, pcv, b3v);                                          // read after the cluster barrier below
     pstamp(k, 1);
     // every CTA's rows of the H1 image (and of the H1^T image) are in L2, and every CTA is past its last use of the
@@ -388,7 +403,9 @@ __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const floa
         bulk_g2s_mc(sm + O_R + R_LO + k.crank * 8192, k.h1img + 16384 + (size_t)k.crank * 2048, 8192, k.bars + B_H1, (uint16_t)0xFF);
 #endif
     }
+    if (h1t) h1t_stage(k, hrow);
     stream_units(k, unit0, NSLOT, 8 - NSLOT);
+    if (h1t && k.warp >= 4) h1t_write(k, h1t);                          // while warps 0-2 issue the MMAs
     if (k.lane == 0 && k.warp < ISSUERS) {
         tc::tc_fence_after();
         const int p = k.warp;
@@ -533,16 +550,20 @@ __device__ __forceinline__ void column_sums(Ctl &k, F val, float *dst, int dst_s
         if (i < NA * NSL) {
             const int a = i >> 6, c = i & 63;
             const float *col = st + a * RB * CS_LD + c;
-            float s = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < RB; ++r) s += col[r * CS_LD];
-            dst[a * dst_stride + c] = s;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;               // four independent chains (fixed order): the loop is latency-bound
+#pragma unroll 4
+            for (int r = 0; r < RB; r += 4) {
+                s0 += col[r * CS_LD]; s1 += col[(r + 1) * CS_LD]; s2 += col[(r + 2) * CS_LD]; s3 += col[(r + 3) * CS_LD];
+            }
+            dst[a * dst_stride + c] = (s0 + s1) + (s2 + s3);
         } else if (rdst) {
             const int j = i - NA * NSL;
-            float s = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < RB; ++r) s += rs[j * RB + r];
-            rdst[j] = s;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+            for (int r = 0; r < RB; r += 4) {
+                s0 += rs[j * RB + r]; s1 += rs[j * RB + r + 1]; s2 += rs[j * RB + r + 2]; s3 += rs[j * RB + r + 3];
+            }
+            rdst[j] = (s0 + s1) + (s2 + s3);
         }
     }
     __syncthreads();
@@ -1269,6 +1290,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                                           dpre, k.crank == 0 ? part + ActorL::small_index(ActorL::B3) : nullptr);
                     }
                     BwdOut bo;
+                    cluster_sync();                                     // every CTA's rows of the H1^T image (written during this unit's forward MMAs) are visible
                     pass_backward<ActorL, true>(k, c.actor, c.tcc.imgt_actor, slope, dz, own, c.tcc.DH1P + (size_t)k.cid * CL * RB * H1, h1t,
                                                 c.tcc.GW2PA + (size_t)(MAX_RB + r) * H2 * H1, bo, nullptr);
                     ln1_param_partials<ActorL>(k, bo, own, 0, nullptr, c.tcc.PARTA + (size_t)((MAX_RB + r) * CL + k.crank) * ActorL::SMALL);
