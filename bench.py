@@ -49,13 +49,14 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures
-# (profiles/r1_ncu_full_update_kernel_v10_raw.csv, r1_ncu_full_env_step_kernel_v8_raw.csv), per unit of work so that
-# it scales to the launch this run times:
-# update kernel, soft256: 10.72 MB read + 53.91 MB written in a 12-call launch -> 5.39 MB per call (the agent state
-# and its replay tables are L2-resident; the writes are scratch buffers draining from L2);
+# (profiles/r2_ncu_full_tcc_kernel_raw.csv, r1_ncu_full_update_kernel_v10_raw.csv, r1_ncu_full_env_step_kernel_v8_raw.csv),
+# per unit of work so that it scales to the launch this run times:
+# tensor-core cluster kernel (round 2 default at batch <= 256), soft256: 18.58 MB read + 4.37 MB written in a 12-call launch
+#   -> 1.91 MB per call (activations stay on the SMs; what is left are the per-row-block gradient partials and operand images);
+# stage kernel (round 1), soft256: 10.72 MB read + 53.91 MB written in a 12-call launch -> 5.39 MB per call;
 # env kernel: 640.1 MB read + 557.7 MB written for 10 M states -> 119.8 B per state (algorithmic 124 B).
-NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_full_update_kernel_v10_raw.csv / r1_ncu_full_env_step_kernel_v8_raw.csv, scaled to this launch"
-NCU_UPDATE_DRAM_BYTES_PER_STEP = {"soft256": (10.721024e6 + 53.908480e6) / 12}
+NCU_TRAFFIC_SOURCE = "profiles/r2_ncu_full_tcc_kernel_raw.csv (tcc) / r1_ncu_full_update_kernel_v10_raw.csv (stage) / r1_ncu_full_env_step_kernel_v8_raw.csv, scaled to this launch"
+NCU_UPDATE_DRAM_BYTES_PER_STEP = {("soft256", "tcc"): (18.580480e6 + 4.370688e6) / 12, ("soft256", "stage"): (10.721024e6 + 53.908480e6) / 12}
 NCU_ENV_DRAM_BYTES_PER_STATE = (640.081664e6 + 557.742080e6) / 10_000_000
 
 
@@ -326,6 +327,7 @@ def time_single_agent(name, K, W, local, rank, world, fp32_peak, tf32_peak, peak
     wl = WORKLOADS[name]
     dev = torch.device("cuda", local)
     ag = build_agent(wl, local, seed=rank, max_steps=max(K, W, 64))
+    backend = ag.backend
     B = wl["batch"]
     guess = 0.12 if B <= 256 else 0.5
     # ---- value: device-resident streams, one persistent launch for the K timed steps
@@ -386,13 +388,59 @@ def time_single_agent(name, K, W, local, rank, world, fp32_peak, tf32_peak, peak
                                           "product costs three TF32 MMAs; achieved = algorithmic fp32 FLOP/s per GPU",
                            "frac_of_fp32_fma_peak": achieved / fp32_peak, "frac_of_bf16_tensor_burst": achieved / peaks.get("bf16_tflops", 1660.5)}
     else:
-        rec["roofline"] = {"kernel": "hirl_update_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+        kname = {"tcc": "hirl_tcc_kernel (cluster-resident: first layers FP32 FMA, 256<->512 contractions tcgen05 3xTF32)",
+                 "stage": "hirl_update_kernel"}.get(backend, backend)
+        rec["roofline"] = {"kernel": kname, "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                            "frac": achieved / fp32_peak if fp32_peak else None,
-                           "traffic": NCU_UPDATE_DRAM_BYTES_PER_STEP[name] * K if name in NCU_UPDATE_DRAM_BYTES_PER_STEP else None,
+                           "traffic": NCU_UPDATE_DRAM_BYTES_PER_STEP[(name, backend)] * K if (name, backend) in NCU_UPDATE_DRAM_BYTES_PER_STEP else None,
                            "traffic_source": NCU_TRAFFIC_SOURCE,
+                           "frac_of_tf32_over_3": achieved / (tf32_peak / 3.0) if tf32_peak else None,
                            "peak_source": "in-run register-resident FFMA loop (hirl_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                            "flop_per_step": flops_per_step, "frac_of_bf16_tensor_burst": achieved / peaks.get("bf16_tflops", 1660.5),
                            "tensor_peak_source": peak_src}
+    rec["backend"] = backend
+    del ag
+    return rec
+
+
+def time_data_parallel(K, W, local, rank, world):
+    """BASELINE config fixed4096 as ONE agent whose global batch of 4096 rows is cut over the N GPUs: strong
+    scaling.  Every rank builds the same agent (same seed, same replay rows); per call the shard gradients are all-reduced with
+    NCCL at the reference's two optimizer steps (include/hirl_b200.h).  Timed end to end through Agent.learn_many (host RNG
+    draws over the global batch, sharding, H2D, 2-5 launches + 2-4 NCCL calls per call, D2H), wall clock with a device sync,
+    max over ranks."""
+    from hirl4ucav_b200 import synth
+    from hirl4ucav_b200.agents.HIRL import Agent
+    from hirl4ucav_b200.utils.seed import set_seed
+    import contextlib, io
+    wl = WORKLOADS["fixed4096"]
+    es, ea = synth.expert_table(N_EXPERT)
+    set_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ag = Agent(HP["actorLR"], HP["criticLR"], 13, 4, 256, 512, HP["tau"], HP["gamma"], HP["bufferSize"], wl["batch"], True,
+                   "Harfang_GYM", es, ea, 0.5, True, device=local, max_fused_steps=64, data_parallel=(rank, world))
+    synth.fill_agent(ag, N_ONLINE, expert_states=es, expert_actions=ea)
+    ag.buffer.flush(); ag.expert_buffer.flush()
+    set_seed(1)
+    chunk = [(wl["bcw"], wl["expert_num"], 0)] * K
+    ag.learn_many([(wl["bcw"], wl["expert_num"], 0)] * W)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(5):
+        sync_all(world)
+        t0 = time.perf_counter()
+        out = ag.learn_many(chunk)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        sync_all(world)
+    assert np.isfinite([float(v) for v in out[-1][:4]]).all()
+    sec = median_over_repeats(times, torch.device("cuda", local), world)
+    rec = {"workload": "dp4096: ONE HIRL agent (fixed BC weight), global batch 4096 cut into %d shard(s) of %d rows, gradients all-reduced over NVLink" % (world, wl["batch"] // world),
+           "value": K / sec, "unit": "updates/s", "ms_per_step": sec / K * 1e3, "steps": K, "scaling": "strong", "global_batch": wl["batch"],
+           "rows_per_gpu": wl["batch"] // world, "backend": ag.backend,
+           "collectives_per_call": "critic-only call: 1 grouped NCCL all-reduce (276 482 fp32 gradient + loss); actor call: + filter count + 1 grouped all-reduce (138 756 fp32 + 4 scalars)",
+           "launches_per_call": "2 (critic-only) / 5 (actor call) stage-range launches of hirl_update_kernel",
+           "timing": "end to end through Agent.learn_many (host draws + sharding + H2D + launches + NCCL + D2H), median of 5, max over ranks"}
     del ag
     return rec
 
@@ -491,6 +539,8 @@ def run_ours(args):
             if name != "ensemble128":
                 subs["ensemble128"] = dict(time_ensemble("ensemble128", 6, 6, WORKLOADS["ensemble128"]["replicas"], local, rank, world, fp32.value, tf32),
                                            workload=WORKLOADS["ensemble128"]["desc"])
+            if name != "fixed4096":
+                subs["dp4096"] = time_data_parallel(24, 6, local, rank, world)
         roof_env = env_roofline(dev, peaks, rank, world)
     if rank != 0:
         if world > 1:

@@ -46,6 +46,10 @@ SYMBOLS = {
     "hirl_agent_create": (_i, [C.POINTER(Config), C.POINTER(_vp)]),
     "hirl_agent_destroy": (_i, [_vp]),
     "hirl_agent_sm_count": (_i, [_vp]),
+    "hirl_agent_backend": (_i, [_vp]),
+    "hirl_nccl_unique_id": (_i, [_vp]),
+    "hirl_allreduce_init": (_i, [_vp, _vp, _i, _i, _i]),
+    "hirl_allreduce_attach": (_i, [_vp, _vp, _i, _i, _i]),
     "hirl_params_import": (_i, [_vp, _i, _i, _vp, _sz]),
     "hirl_params_export": (_i, [_vp, _i, _i, _vp, _sz]),
     "hirl_adam_import": (_i, [_vp, _i, _i, _vp, _vp, _sz]),

@@ -56,7 +56,12 @@ class Agent(object):
 
     def __init__(self, actorLR, criticLR, stateDim, actionDim, full1Dim, full2Dim, tau, gamma, bufferSize, batchSize,
                  layerNorm, name, expert_states, expert_actions, bc_weight, expert_warm_up, device=None,
-                 max_fused_steps=64, buffer_upsample=None, expert_upsample=None):
+                 max_fused_steps=64, buffer_upsample=None, expert_upsample=None, data_parallel=None):
+        """``data_parallel=(rank, world)``: data-parallel large-batch mode (include/hirl_b200.h).  Every rank
+        constructs the same agent under the same seeds and stores the same transitions; ``batchSize`` is the GLOBAL batch,
+        this process executes ``batchSize // world`` of every call's rows and the gradients are all-reduced (NCCL) at the
+        reference's two optimizer steps (HIRL.py:286-288, 323-325).  Needs an initialised torch.distributed group for
+        world > 1 (only to broadcast the 128-byte NCCL id)."""
         if (stateDim, actionDim, full1Dim, full2Dim) != (13, 4, 256, 512):
             raise NotImplementedError("the fused kernel is specialised for the reference driver's geometry "
                                       "13/4/256/512 (hirl/train_all.py:200-203)")
@@ -65,6 +70,10 @@ class Agent(object):
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
         self.tau, self.gamma = tau, gamma
         self.bufferSize, self.batchSize = int(bufferSize), int(batchSize)
+        self._dp = None if data_parallel is None else (int(data_parallel[0]), int(data_parallel[1]))
+        if self._dp is not None and (self.batchSize % self._dp[1] or not 0 <= self._dp[0] < self._dp[1]):
+            raise ValueError("data_parallel=(rank, world): batchSize must be a multiple of world and 0 <= rank < world")
+        self._dev_batch = self.batchSize if self._dp is None else self.batchSize // self._dp[1]   # rows this process executes per call
         self.actorLR, self.criticLR = actorLR, criticLR
         self.actorTrainable = True
         self.actionDim = actionDim
@@ -97,7 +106,7 @@ class Agent(object):
                   f"loss lambda is {self.loss_lambda}")
 
         n_exp = len(expert_states) if has_expert else 0
-        cfg = _lib.Config(device=self.device.index, batch=self.batchSize, online_capacity=self.bufferSize,
+        cfg = _lib.Config(device=self.device.index, batch=self._dev_batch, online_capacity=self.bufferSize,
                           expert_capacity=n_exp + 10, bc_rows=n_exp, max_steps=self._max_steps, activation=self._ACT,
                           replicas=1, gamma=gamma, tau=tau, noise_clamp=self.TD3LearningNoiseClamp,
                           loss_lambda=float(self.loss_lambda))
@@ -136,6 +145,54 @@ class Agent(object):
         self._noise_mean = torch.zeros(self.actionDim)
         self._noise_std = torch.ones(self.actionDim) * self.TD3LearningNoise
         self.last_draws = {}
+        if self._dp is not None:
+            Bl = self._dev_batch
+            self._sh_steps_t = mk((K * _lib.STEP_DTYPE.itemsize,), torch.uint8)
+            self._sh_steps = self._sh_steps_t.numpy().view(_lib.STEP_DTYPE)
+            self._sh_on_t, self._sh_ex_t, self._sh_bc_t = mk((K, Bl), torch.int32), mk((K, Bl), torch.int32), mk((K, Bl), torch.int32)
+            self._sh_on, self._sh_ex, self._sh_bc = self._sh_on_t.numpy(), self._sh_ex_t.numpy(), self._sh_bc_t.numpy()
+            self._sh_addr = tuple(a.ctypes.data for a in (self._sh_steps, self._sh_on, self._sh_ex, self._sh_bc))
+            self._attach_data_parallel()
+
+    def _attach_data_parallel(self):
+        rank, world = self._dp
+        uid = np.zeros(128, np.uint8)
+        if rank == 0:
+            _lib.check(self._lib.hirl_nccl_unique_id(_lib.ptr(uid)))
+        if world > 1:
+            import torch.distributed as dist
+            box = [uid.tobytes()]
+            dist.broadcast_object_list(box, src=0)
+            uid = np.frombuffer(box[0], np.uint8).copy()
+        _lib.check(self._lib.hirl_allreduce_init(self._h, _lib.ptr(uid), rank, world, self.batchSize))
+
+    @property
+    def backend(self):
+        """Name of the update kernel this agent launches."""
+        return ("stage", "tcc", "cluster", "ensemble")[self._lib.hirl_agent_backend(self._h)]
+
+    def _submit(self, lo, n):
+        """Enqueues staging slots lo .. lo+n-1.  Data-parallel agents first cut every slot's index streams (drawn over the
+        global batch, identically on every rank) down to this rank's rows (parallel.shard_step)."""
+        if self._dp is None:
+            _lib.check(self._lib.hirl_learn_async(self._h, n, *(self._st_ptrs if lo == 0 else self._slot_ptrs(lo))))
+            return
+        from .. import parallel
+        rank, world = self._dp
+        Bl = self._dev_batch
+        for k in range(lo, lo + n):
+            st = self._st_steps[k]
+            n_on, n_ex, on, ex, bc = parallel.shard_step(int(st["n_online"]), int(st["n_expert"]), self._st_on[k], self._st_ex[k],
+                                                         self._st_bc[k], rank, world)
+            self._sh_steps[k] = st
+            self._sh_steps[k]["n_online"], self._sh_steps[k]["n_expert"] = n_on, n_ex
+            self._sh_on[k, :n_on] = on
+            self._sh_ex[k, :n_ex] = ex
+            self._sh_bc[k, :] = bc
+        a = self._sh_addr
+        _lib.check(self._lib.hirl_learn_async(self._h, n, C.c_void_p(a[0] + lo * _lib.STEP_DTYPE.itemsize), C.c_void_p(a[1] + lo * Bl * 4),
+                                              C.c_void_p(a[2] + lo * Bl * 4), C.c_void_p(a[3] + lo * Bl * 4),
+                                              C.c_void_p(self._st_addr[4] + lo * _lib.OUT_SCALARS * 4)))
 
     def _make_nets(self, stateDim, actionDim, full1Dim, full2Dim, name):
         mk_a = lambda tag: nets.make_actor(stateDim, actionDim, full1Dim, full2Dim, tag + name, self._GAIN)
@@ -387,7 +444,7 @@ class Agent(object):
 
     def _launch(self, k_steps, predraw_for=None):
         self._pre_launch()
-        _lib.check(self._lib.hirl_learn_async(self._h, k_steps, *self._st_ptrs))
+        self._submit(0, k_steps)
         try:
             if predraw_for is not None:
                 self._predraw_next(predraw_for)
@@ -438,7 +495,7 @@ class Agent(object):
                         for k in range(lo, hi):
                             self._st_bc[k, :] = ready[k - lo]
                         self.last_draws["bc"] = self._st_bc[hi - 1].copy()
-                    _lib.check(self._lib.hirl_learn_async(self._h, hi - lo, *self._slot_ptrs(lo)))
+                    self._submit(lo, hi - lo)
             finally:
                 _lib.check(self._lib.hirl_learn_wait(self._h))
             self._host_stale = True

@@ -162,6 +162,8 @@ struct AgentCtx {
     float *out_scalars;    // [k][8]
     float *carry;          // [8] scalars carried between calls (stale-value semantics, HIRL.py:334)
     int B;
+    int Bg;                // batch the loss means run over: B, or the global batch in the data-parallel mode (this agent holds B of its rows)
+    float *dp_count;       // data-parallel mode: soft-count word, written by the launch that ends with stage G6, all-reduced, read by stage R6 (else null)
     int zsplit;            // allocated split-K slots per Z2 / DH1 buffer (max of ns[])
     int ns[NS_COUNT];      // split-K factor per GEMM group
     int activation;
@@ -181,6 +183,8 @@ struct LaunchCtx {
     unsigned *bar_flags;   // [MAX_CTAS][32] barrier flags: generations keep counting up across launches (never reset)
     int k_steps;
     int stop_after;        // debug: leave after this stage of step 0 (0 = never)
+    int step0;             // first step record of this launch
+    int first_stage, last_stage, adam_phase;   // stage range of a data-parallel launch (1, ST_END, 0: whole calls)
     long long *prof;       // debug: [PROF_STEPS][ST_END][MAX_CTAS][2] SM-clock stamps (work done, barrier released)
 };
 constexpr int PROF_STEPS = 12;

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(THREADS, 1) hirl_update_kernel(const __grid_co
     tm.tc_smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
     tm.tc_bars = &tc_bars;
     for (int step = 0; step < L.k_steps; ++step)
-        if (learn_step(ctx, step, tm, smem, step == 0 ? L.stop_after : 0, L.prof)) break;
+        if (learn_step(ctx, L.step0 + step, tm, smem, step == 0 ? L.stop_after : 0, L.prof, L.first_stage, L.last_stage, L.adam_phase)) break;
     if (any_tc) {
         __syncthreads();
         if (threadIdx.x < 32) tc::tmem_dealloc(tm.tmem_base);
@@ -207,6 +207,52 @@ static int fail(int code, const std::string &msg) {
         if (e_ != cudaSuccess) return fail(HIRL_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+// ---- NCCL, resolved at run time (data-parallel mode, see launch_update_dp) ------------------------------------------------
+#include <dlfcn.h>
+namespace {
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_uid_fn)(void *);
+typedef int (*nccl_init_fn)(void **, int, const void *, int);   // ncclCommInitRank(comm*, nranks, ncclUniqueId BY VALUE, rank): see nccl_init_rank below
+typedef int (*nccl_destroy_fn)(void *);
+typedef const char *(*nccl_errstr_fn)(int);
+typedef int (*nccl_group_fn)(void);
+struct NcclUid { char internal[128]; };
+typedef int (*nccl_init_byval_fn)(void **, int, NcclUid, int);
+struct NcclApi {
+    void *lib = nullptr;
+    nccl_allreduce_fn allreduce = nullptr;
+    nccl_uid_fn unique_id = nullptr;
+    nccl_init_byval_fn init_rank = nullptr;
+    nccl_destroy_fn destroy = nullptr;
+    nccl_errstr_fn errstr = nullptr;
+    nccl_group_fn group_start = nullptr, group_end = nullptr;
+} g_nccl;
+int nccl_load() {
+    if (g_nccl.lib) return 0;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(HIRL_E_UNSUPPORTED, std::string("libnccl.so.2 not found: ") + dlerror());
+    g_nccl.allreduce = (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce");
+    g_nccl.unique_id = (nccl_uid_fn)dlsym(lib, "ncclGetUniqueId");
+    g_nccl.init_rank = (nccl_init_byval_fn)dlsym(lib, "ncclCommInitRank");
+    g_nccl.destroy = (nccl_destroy_fn)dlsym(lib, "ncclCommDestroy");
+    g_nccl.errstr = (nccl_errstr_fn)dlsym(lib, "ncclGetErrorString");
+    g_nccl.group_start = (nccl_group_fn)dlsym(lib, "ncclGroupStart");
+    g_nccl.group_end = (nccl_group_fn)dlsym(lib, "ncclGroupEnd");
+    if (!g_nccl.allreduce || !g_nccl.unique_id || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.errstr || !g_nccl.group_start || !g_nccl.group_end)
+        return fail(HIRL_E_UNSUPPORTED, "libnccl.so.2 lacks an expected symbol");
+    g_nccl.lib = lib;
+    return 0;
+}
+constexpr int NCCL_FLOAT32 = 7, NCCL_SUM = 0;   // ncclDataType_t / ncclRedOp_t values of nccl.h (stable since NCCL 2.0)
+}  // namespace
+#define NC(call)                                                                                                    \
+    do {                                                                                                            \
+        int r_ = (call);                                                                                            \
+        if (r_ != 0) return fail(HIRL_E_CUDA, std::string(#call) + ": " + (g_nccl.errstr ? g_nccl.errstr(r_) : "nccl error")); \
+    } while (0)
+
 struct hirl_agent {
     hirl_config_t cfg;
     int sm_count = 0, grid = 0;
@@ -236,6 +282,12 @@ struct hirl_agent {
     bool coop_ok = true;         // cooperative attribute accepted for cluster launches
     int ncl = 0;                 // cluster kernel: co-resident clusters of 8 CTAs used per launch
     int tcc_ncl = 0;             // tensor-core cluster kernel: clusters per launch
+    // data-parallel large-batch mode (hirl_allreduce_init / hirl_allreduce_attach)
+    void *nccl_comm = nullptr;
+    bool dp_own_comm = false;
+    int dp_world = 0, dp_rank = 0;
+    float *d_dp_count = nullptr;
+    std::vector<int> dp_do_actor, dp_mode;   // host copy of the step records' control words of the launch being enqueued
 };
 
 template <class T>
@@ -435,6 +487,8 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     AgentCtx proto;
     std::memset(&proto, 0, sizeof(proto));
     proto.B = cfg->batch;
+    proto.Bg = cfg->batch;
+    proto.dp_count = nullptr;
     proto.activation = cfg->activation;
     proto.gamma = cfg->gamma; proto.tau = cfg->tau; proto.noise_clamp = cfg->noise_clamp; proto.loss_lambda = cfg->loss_lambda;
     // split-K factors (unit = one 64x64 output tile over the layer's full K)
@@ -649,11 +703,59 @@ int hirl_agent_destroy(hirl_agent_t *h) {
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->d_act_s) cudaFree(h->d_act_s);
     if (h->d_act_a) cudaFree(h->d_act_a);
+    if (h->nccl_comm && h->dp_own_comm && g_nccl.destroy) g_nccl.destroy(h->nccl_comm);
     for (void *p : h->allocs) cudaFree(p);
     delete h;
     return 0;
 }
 int hirl_agent_sm_count(hirl_agent_t *h) { return h ? h->grid : 0; }
+int hirl_agent_backend(hirl_agent_t *h) {
+    if (!h) return fail(HIRL_E_INVALID, "null handle");
+    if (h->ctxs.size() > 1) return 3;
+    return h->ctxs[0].use_tcc ? 1 : h->ctxs[0].use_cluster ? 2 : 0;
+}
+
+// ---- data-parallel mode: communicator ---------------------------------------------------------------------------------
+static int dp_enable(hirl_agent *h, void *comm, bool own, int rank, int world, int global_batch) {
+    if (h->ctxs.size() != 1) return fail(HIRL_E_UNSUPPORTED, "data-parallel mode is for a single agent per handle");
+    if (world < 1 || rank < 0 || rank >= world) return fail(HIRL_E_INVALID, "bad rank / world");
+    if (global_batch != h->cfg.batch * world) return fail(HIRL_E_INVALID, "global_batch must be world * cfg.batch (equal shards)");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (!h->d_dp_count) { if (int rc = dev_alloc(h, &h->d_dp_count, 1)) return rc; }
+    AgentCtx &c = h->ctxs[0];
+    // the stage kernel carries the mode (its stages keep their state in global memory, so a call can be cut at the two
+    // optimizer boundaries); an agent that was created on the cluster kernels moves over: parameters, moments, replay
+    // tables and the stage scratch are shared by all back-ends
+    c.use_tcc = 0; c.use_cluster = 0;   // (created with use_tc = tc_g1 = 0: the FP32 tiles, which need no derived weight images)
+    c.Bg = global_batch;
+    c.dp_count = h->d_dp_count;
+    h->nccl_comm = comm; h->dp_own_comm = own; h->dp_rank = rank; h->dp_world = world;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    return 0;
+}
+int hirl_nccl_unique_id(void *id128) {
+    if (!id128) return fail(HIRL_E_INVALID, "null argument");
+    if (int rc = nccl_load()) return rc;
+    NC(g_nccl.unique_id(id128));
+    return 0;
+}
+int hirl_allreduce_init(hirl_agent_t *h, const void *id128, int rank, int world, int global_batch) {
+    if (!h || !id128) return fail(HIRL_E_INVALID, "null argument");
+    if (int rc = nccl_load()) return rc;
+    CU(cudaSetDevice(h->cfg.device));
+    NcclUid uid;
+    std::memcpy(&uid, id128, sizeof(uid));
+    void *comm = nullptr;
+    NC(g_nccl.init_rank(&comm, world, uid, rank));
+    if (int rc = dp_enable(h, comm, true, rank, world, global_batch)) { g_nccl.destroy(comm); return rc; }
+    return 0;
+}
+int hirl_allreduce_attach(hirl_agent_t *h, void *nccl_comm, int rank, int world, int global_batch) {
+    if (!h || !nccl_comm) return fail(HIRL_E_INVALID, "null argument");
+    if (int rc = nccl_load()) return rc;
+    return dp_enable(h, nccl_comm, false, rank, world, global_batch);
+}
 
 int hirl_params_import(hirl_agent_t *h, int replica, int net, const float *src, size_t n) {
     if (!h || !src) return fail(HIRL_E_INVALID, "null argument");
@@ -752,6 +854,53 @@ int hirl_gather_bc(hirl_agent_t *h, const int32_t *idx_bc, int n, float *out_sta
 }
 
 // steps/idx/out are device arrays with a leading [replicas] dimension of stride max(k_steps)
+
+// ---- data-parallel large-batch mode ----------------------------------------------------------------------------------
+// One process per GPU, every process a full replica of the agent and of its replay tables; a call's batch of Bg rows is cut
+// into world shards of B rows (the host mirror slices the index streams it drew once, hirl4ucav_b200/parallel.py).  The
+// stage kernel runs the call as launches over stage ranges and the per-shard gradients meet in NCCL all-reduces over
+// NVLink exactly where the reference calls optimizer.step() (HIRL.py:286-288 critic, :323-325 actor):
+//   [R0 .. G4 phase 1]  critic forward / backward, shard gradient -> g_critic      all-reduce g_critic (276 482 + pad), loss
+//   [G4 phase 2]        critic Adam on the summed gradient (identical on every rank)
+//   [R4 .. G6]          Q1(s, pi), Q1(s, a_bc), shard count of soft_Q > rl_Q        all-reduce the count (HIRL.py:303 is a batch mean)
+//   [R6 .. G8 phase 1]  actor backward with the global weight w -> g_actor          all-reduce g_actor (138 756 + pad), 4 loss scalars
+//   [G8 phase 2]        actor Adam, Polyak, returned scalars
+// Loss means are taken over Bg in every shard, so sums over ranks are the global means.  libnccl is resolved at run time
+// (the copy torch already loaded, else libnccl.so.2): the library has no link-time dependency on it.
+static int launch_update_dp(hirl_agent *h, LaunchCtx &L, int k_steps, cudaStream_t stream) {
+    if ((int)h->dp_do_actor.size() < k_steps) return fail(HIRL_E_INVALID, "data-parallel mode needs host step records (hirl_learn / hirl_learn_async)");
+    AgentCtx &c = L.agent;
+    int launches = 0;
+    auto seg = [&](int step, int first, int last, int phase) -> int {
+        L.step0 = step; L.k_steps = 1; L.first_stage = first; L.last_stage = last; L.adam_phase = phase; L.stop_after = 0;
+        void *args[] = {&L};
+        CU(cudaLaunchCooperativeKernel((void *)hirl_update_kernel, dim3(h->grid), dim3(THREADS), args, SMEM_BYTES, stream));
+        ++launches;
+        return 0;
+    };
+    for (int step = 0; step < k_steps; ++step) {
+        const bool do_actor = h->dp_do_actor[step] != 0;
+        if (h->dp_mode[step] != 0) return fail(HIRL_E_UNSUPPORTED, "data-parallel mode implements the HIRL step (mode 0)");
+        if (int rc = seg(step, ST_R0, ST_G4, 1)) return rc;
+        NC(g_nccl.group_start());
+        NC(g_nccl.allreduce(c.g_critic, c.g_critic, (size_t)CRITIC_SIZE, NCCL_FLOAT32, NCCL_SUM, h->nccl_comm, stream));
+        NC(g_nccl.allreduce(c.carry, c.carry, 1, NCCL_FLOAT32, NCCL_SUM, h->nccl_comm, stream));
+        NC(g_nccl.group_end());
+        if (int rc = seg(step, ST_G4, ST_G4, 2)) return rc;
+        if (!do_actor) continue;
+        if (int rc = seg(step, ST_R4, ST_G6, 0)) return rc;
+        NC(g_nccl.allreduce(h->d_dp_count, h->d_dp_count, 1, NCCL_FLOAT32, NCCL_SUM, h->nccl_comm, stream));
+        if (int rc = seg(step, ST_R6, ST_G8, 1)) return rc;
+        NC(g_nccl.group_start());
+        NC(g_nccl.allreduce(c.g_actor, c.g_actor, (size_t)ACTOR_SIZE, NCCL_FLOAT32, NCCL_SUM, h->nccl_comm, stream));
+        NC(g_nccl.allreduce(c.carry + 1, c.carry + 1, 4, NCCL_FLOAT32, NCCL_SUM, h->nccl_comm, stream));
+        NC(g_nccl.group_end());
+        if (int rc = seg(step, ST_G8, ST_G8, 2)) return rc;
+    }
+    h->last_launches = launches;
+    return 0;
+}
+
 static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_dev, const int32_t *ion, const int32_t *iex, const int32_t *ibc,
                          float *out_dev, cudaStream_t stream) {
     const int R = (int)h->ctxs.size();
@@ -817,6 +966,8 @@ static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_de
         c.steps = steps_dev; c.idx_online = ion; c.idx_expert = iex; c.idx_bc = ibc; c.out_scalars = out_dev;
         L.bar_flags = h->d_bar; L.k_steps = k_steps; L.stop_after = h->stop_after;
         L.prof = h->prof_on ? h->d_prof : nullptr;
+        L.step0 = 0; L.first_stage = 1; L.last_stage = ST_END; L.adam_phase = 0;
+        if (h->dp_world > 0) return launch_update_dp(h, L, k_steps, stream);
         void *args[] = {&L};
         CU(cudaLaunchCooperativeKernel((void *)hirl_update_kernel, dim3(h->grid), dim3(THREADS), args, SMEM_BYTES, stream));
     } else {
@@ -855,6 +1006,10 @@ int hirl_learn(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, const int
                const int32_t *idx_bc, float *out_scalars) {
     if (!h || !steps || !idx_online || !out_scalars) return fail(HIRL_E_INVALID, "null argument");
     if (int rc = check_steps(h, k_steps, steps)) return rc;
+    if (h->dp_world > 0) {   // the data-parallel launcher cuts every call into stage ranges on the host: it needs the control words
+        h->dp_do_actor.assign(k_steps, 0); h->dp_mode.assign(k_steps, 0);
+        for (int k = 0; k < k_steps; ++k) { h->dp_do_actor[k] = steps[k].do_actor; h->dp_mode[k] = steps[k].mode; }
+    }
     const size_t B = h->cfg.batch, K = (size_t)k_steps * h->ctxs.size();
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaMemcpyAsync(h->d_steps, steps, K * sizeof(hirl_step_t), cudaMemcpyHostToDevice, h->stream));
@@ -880,6 +1035,10 @@ int hirl_learn_async(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, con
                      const int32_t *idx_bc, float *out_scalars) {
     if (!h || !steps || !idx_online || !out_scalars) return fail(HIRL_E_INVALID, "null argument");
     if (int rc = check_steps(h, k_steps, steps)) return rc;
+    if (h->dp_world > 0) {   // the data-parallel launcher cuts every call into stage ranges on the host: it needs the control words
+        h->dp_do_actor.assign(k_steps, 0); h->dp_mode.assign(k_steps, 0);
+        for (int k = 0; k < k_steps; ++k) { h->dp_do_actor[k] = steps[k].do_actor; h->dp_mode[k] = steps[k].mode; }
+    }
     const size_t B = h->cfg.batch, K = (size_t)k_steps * h->ctxs.size();
     CU(cudaSetDevice(h->cfg.device));
     // Optional zero-copy (off by default): with every stream in pinned host memory the kernel can read the step
@@ -887,7 +1046,7 @@ int hirl_learn_async(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, con
     // cudaMemcpyAsync calls per learn().  Measured on B200: the PCIe round trips on the kernel's critical path cost
     // more than the copies (e2e 5 075 vs 5 257 updates/s, learn_many 6 340 vs 7 076), so the staged copies stay.
     const void *d_st, *d_on, *d_ex = nullptr, *d_bc = nullptr, *d_out;
-    if (h->zero_copy && device_addressable_host(steps, &d_st) && device_addressable_host(idx_online, &d_on) &&
+    if (h->zero_copy && h->dp_world == 0 && device_addressable_host(steps, &d_st) && device_addressable_host(idx_online, &d_on) &&
         (!idx_expert || device_addressable_host(idx_expert, &d_ex)) && (!idx_bc || device_addressable_host(idx_bc, &d_bc)) &&
         device_addressable_host(out_scalars, &d_out)) {
         return launch_update(h, k_steps, (const hirl_step_t *)d_st, (const int32_t *)d_on, d_ex ? (const int32_t *)d_ex : h->d_iex,
@@ -902,7 +1061,7 @@ int hirl_learn_async(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, con
         CU(cudaMemcpyAsync(out_scalars, h->d_out, K * HIRL_OUT_SCALARS * 4, cudaMemcpyDeviceToHost, h->stream));
         return 0;
     };
-    const bool graphable = h->use_graph && k_steps == 1 && h->ctxs.size() == 1 && !h->prof_on && h->stop_after == 0;
+    const bool graphable = h->use_graph && k_steps == 1 && h->ctxs.size() == 1 && !h->prof_on && h->stop_after == 0 && h->dp_world == 0;
     if (graphable) {
         const void *key[5] = {steps, idx_online, idx_expert, idx_bc, out_scalars};
         if (!h->graph_exec && !h->graph_key[0]) {   // built once, for the first set of staging pointers seen
@@ -941,6 +1100,7 @@ int hirl_learn_dev(hirl_agent_t *h, int k_steps, const hirl_step_t *steps_dev, c
                    const int32_t *idx_bc_dev, float *out_scalars_dev, void *stream) {
     if (!h || !steps_dev || !idx_online_dev || !out_scalars_dev) return fail(HIRL_E_INVALID, "null argument");
     if (k_steps < 1) return fail(HIRL_E_INVALID, "k_steps must be >= 1");
+    if (h->dp_world > 0) return fail(HIRL_E_UNSUPPORTED, "data-parallel agents take host step records (hirl_learn / hirl_learn_async)");
     CU(cudaSetDevice(h->cfg.device));
     return launch_update(h, k_steps, steps_dev, idx_online_dev, idx_expert_dev ? idx_expert_dev : h->d_iex, idx_bc_dev ? idx_bc_dev : h->d_ibc,
                          out_scalars_dev, (cudaStream_t)stream);

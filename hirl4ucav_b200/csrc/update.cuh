@@ -821,7 +821,7 @@ __device__ __noinline__ void stage_r2(const AgentCtx &c, const hirl_step_t &st, 
                     c.sc.TQ[(size_t)tower * B + b] = tower ? o2[0] : o1[0];
                     if (tower == 0) c.sc.Y[b] = y;
                 }
-                dq = (2.f / (float)B) * delta;  // mse_loss backward, mean reduction
+                dq = (2.f / (float)c.Bg) * delta;  // mse_loss backward, mean reduction (over the global batch)
                 float dout[1] = {dq}, dy[16];
                 head_backward<CriticL>(tw, xh, rstd, dout, slope, lane, dz, dy);
                 store_row512(Z2p(c, pass) + (size_t)b * H2, lane, dz);
@@ -1006,13 +1006,17 @@ __device__ __forceinline__ float polyak_elem(float t, float p, float tau, float 
 template <class L>
 __device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w, float *gw, const float *w2parts, int nparts, float *m, float *v, const float *part,
                                            int part_towers, int nslots, float neg_step, float bc2_sqrt, float *target, bool polyak,
-                                           float tau, float one_minus_tau, float *w2t) {
+                                           float tau, float one_minus_tau, float *w2t, int phase = 0) {
+    // phase (data-parallel mode): 0 whole stage; 1 only the fixed-order sums of the partials -> gw (the gradient of this
+    // shard, all-reduced between the two launches); 2 only Adam (+ Polyak) from gw
     const int total = ntowers * L::SIZE;
     for (int e = tm.rank * THREADS + threadIdx.x; e < total; e += tm.size * THREADS) {
         const int tower = e / L::SIZE, off = e - tower * L::SIZE;
         float g;
         const bool in_w2 = off >= L::W2 && off < L::B2;
-        if (in_w2) {
+        if (phase == 2) {
+            g = __ldcg(gw + e);
+        } else if (in_w2) {
             if (nparts > 0) {   // fixed-order sum of the split-K / per-branch partial buffers
                 const float *p0 = w2parts + (size_t)tower * nparts * H2 * H1 + (off - L::W2);
                 g = __ldcg(p0);
@@ -1027,6 +1031,7 @@ __device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w
             for (int s = 0; s < nslots; ++s) g += __ldcg(part + ((size_t)s * part_towers + tower) * L::SMALL + si);
             gw[e] = g;
         }
+        if (phase == 1) continue;
         float wv = w[e], mv = m[e], vv = v[e];
         adam_elem(g, wv, mv, vv, neg_step, bc2_sqrt);
         w[e] = wv; m[e] = mv; v[e] = vv;
@@ -1053,17 +1058,17 @@ __device__ __forceinline__ Team arena_team(const Team &tm) {
     return t;
 }
 
-__device__ __noinline__ void stage_g4(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+__device__ __noinline__ void stage_g4(const AgentCtx &c, const hirl_step_t &st, const Team &tm, int phase) {
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
     const int P = gsize < nchunks ? gsize : nchunks;
     const Team at = arena_team(tm);
     if (tm.rank < at.size)
         adam_arena<CriticL>(at, 2, c.critic, c.g_critic, c.sc.GW2P, c.dw_split > 1 ? c.dw_split : 0, c.m_critic, c.v_critic, c.sc.PART_C, 2, P,
-                            st.critic_neg_step, st.critic_bc2_sqrt, nullptr, false, 0.f, 0.f, c.use_tc ? c.w2t_critic : nullptr);
-    if (tm.rank == tm.size - 1 && threadIdx.x < 32) {
+                            st.critic_neg_step, st.critic_bc2_sqrt, nullptr, false, 0.f, 0.f, c.use_tc ? c.w2t_critic : nullptr, phase);
+    if (phase != 2 && tm.rank == tm.size - 1 && threadIdx.x < 32) {
         // critic_loss = mse(Q1,y) + mse(Q2,y): even ranks hold tower 0, odd ranks tower 1
         const float s0 = lp_sum(c, tm, 0, 0), s1 = lp_sum(c, tm, 0, 1);
-        if (threadIdx.x == 0) c.carry[0] = __fadd_rn(s0 / (float)c.B, s1 / (float)c.B);
+        if (threadIdx.x == 0) c.carry[0] = __fadd_rn(s0 / (float)c.Bg, s1 / (float)c.Bg);
     }
 }
 
@@ -1131,7 +1136,7 @@ __device__ __noinline__ void stage_r5(const AgentCtx &c, const hirl_step_t &st, 
                 cnt += softq > q[0] ? 1.f : 0.f;
             }
         }
-        float dout[1] = {-1.f / (float)B}, dz[16], dy[16];
+        float dout[1] = {-1.f / (float)c.Bg}, dz[16], dy[16];
         head_backward<CriticL>(c.critic, xh, rstd, dout, slope, lane, dz, dy);
         store_row512(Z2p(c, P_QP) + (size_t)b * H2, lane, dz);
     }
@@ -1161,8 +1166,8 @@ __device__ __forceinline__ BcWeight bc_weight_of(const AgentCtx &c, const hirl_s
     if (st.mode == 2) w = 1.0;       // BC: the loss IS the cloning term
     else if (st.mode != 0) w = 0.0;
     else if (st.bc_weight_now == 100.f) {
-        r.count = lp_sum(c, tm, 1);
-        const float mean = st.force_soft_weight >= 0.f ? st.force_soft_weight : r.count / (float)c.B;  // .float().mean()
+        r.count = c.dp_count ? __ldcg(c.dp_count) : lp_sum(c, tm, 1);   // data-parallel: the all-reduced count of every shard
+        const float mean = st.force_soft_weight >= 0.f ? st.force_soft_weight : r.count / (float)c.Bg;  // .float().mean()
         w = (double)mean + (double)st.bc_warm_up;
     }
     if (w > 1.0) w = 1.0;
@@ -1219,7 +1224,7 @@ __device__ __noinline__ void stage_r6(const AgentCtx &c, const hirl_step_t &st, 
                             bc_sq = fmaf(diff, diff, bc_sq);
                             if (j == 3) fire_sq = fmaf(diff, diff, fire_sq);
                         }
-                        dpi = ((2.f / (float)(A * B)) * diff) * bc_scale;
+                        dpi = ((2.f / (float)(A * c.Bg)) * diff) * bc_scale;
                     }
                     dpre[j] = dpi * (1.f - pi * pi);   // tanh backward
                 }
@@ -1309,9 +1314,9 @@ __device__ __noinline__ void stage_r7(const AgentCtx &c, const hirl_step_t &st, 
 #define HIRL_G8_NOINLINE 0   // 1: build stage_g8 as a separate function again (tools/sanitize_all.sh re-tests the round-1 fault)
 #endif
 #if HIRL_G8_NOINLINE
-__device__ __noinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+__device__ __noinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm, int phase) {
 #else
-__device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+__device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm, int phase) {
 #endif
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
     const int P = gsize < nchunks ? gsize : nchunks;
@@ -1324,17 +1329,17 @@ __device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &s
     const Team at = arena_team(tm);
     if (tm.rank < at.size)
         adam_arena<ActorL>(at, 1, c.actor, c.g_actor, w2parts, (st.mode == 0 ? 2 : 1) * c.dw_split, c.m_actor, c.v_actor, part_a, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
-                       c.tactor, st.do_polyak != 0, tau, omt, c.use_tc ? c.w2t_actor : nullptr);
-    if (st.do_polyak && tm.rank < at.size) polyak_arena<CriticL>(at, 2, c.critic, c.tcritic, tau, omt);
-    if (tm.rank == tm.size - 1 && threadIdx.x < 32) {
+                       c.tactor, st.do_polyak != 0, tau, omt, c.use_tc ? c.w2t_actor : nullptr, phase);
+    if (phase != 1 && st.do_polyak && tm.rank < at.size) polyak_arena<CriticL>(at, 2, c.critic, c.tcritic, tau, omt);
+    if (phase != 2 && tm.rank == tm.size - 1 && threadIdx.x < 32) {
         const BcWeight bw = bc_weight_of(c, st, tm);
-        const float rl_loss = st.mode == 2 ? 0.f : -(lp_sum(c, tm, 2) / (float)c.B);      // HIRL.py:297
+        const float rl_loss = st.mode == 2 ? 0.f : -(lp_sum(c, tm, 2) / (float)c.Bg);     // HIRL.py:297
         float bc_loss = 0.f, fire = 0.f;
         if (st.mode == 0) {
-            bc_loss = __fmul_rn(lp_sum(c, tm, 3) / (float)(A * c.B), c.loss_lambda);       // HIRL.py:311
-            fire = lp_sum(c, tm, 4) / (float)c.B;                                          // HIRL.py:319 (x lambda on the host, in double)
+            bc_loss = __fmul_rn(lp_sum(c, tm, 3) / (float)(A * c.Bg), c.loss_lambda);      // HIRL.py:311
+            fire = lp_sum(c, tm, 4) / (float)c.Bg;                                         // HIRL.py:319 (x lambda on the host, in double)
         } else if (st.mode == 2) {
-            bc_loss = lp_sum(c, tm, 3) / (float)(A * c.B);                                 // BC.py:179
+            bc_loss = lp_sum(c, tm, 3) / (float)(A * c.Bg);                                // BC.py:179
         }
         if (threadIdx.x == 0) {
         c.carry[1] = __fadd_rn(__fmul_rn(bc_loss, bw.w), __fmul_rn(rl_loss, bw.one_minus_w));  // HIRL.py:321
@@ -1348,7 +1353,11 @@ __device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &s
 }
 
 // one full learn() call for one agent; returns true when the debug stop point was reached
-__device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm, float *smem, int stop_after, long long *prof) {
+// first / last / adam_phase: the data-parallel mode (hirl_allreduce_init) runs ONE call as several launches over stage
+// ranges [first, last] with the gradient all-reduces between them; every stage keeps its state in global memory, so a
+// range simply resumes where the previous launch stopped.  Defaults: whole call (first = 1, last = ST_END, phase 0).
+__device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm, float *smem, int stop_after, long long *prof,
+                                           int first = 1, int last = ST_END, int adam_phase = 0) {
     __shared__ hirl_step_t st;
     if (threadIdx.x < (int)(sizeof(hirl_step_t) / sizeof(int)))
         reinterpret_cast<int *>(&st)[threadIdx.x] = reinterpret_cast<const int *>(c.steps + step)[threadIdx.x];
@@ -1359,11 +1368,23 @@ __device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm
         if (threadIdx.x == 0) prof[1] = clock64();   // stage 0 slot: step start
     }
 #define HIRL_STAGE(id, call)                                                            \
+    if ((id) >= first) {                                                                \
     call;                                                                               \
     if (prof && threadIdx.x == 0) prof[(size_t)(id) * MAX_CTAS * 2] = clock64();        \
     team_sync(tm);                                                                      \
     if (prof && threadIdx.x == 0) prof[(size_t)(id) * MAX_CTAS * 2 + 1] = clock64();    \
-    if (stop_after == (id)) return true;
+    if (stop_after == (id)) return true;                                                \
+    if (last == (id)) {                                                                 \
+        if ((id) == ST_G6 && c.dp_count && tm.rank == tm.size - 1 && threadIdx.x < 32) { \
+            const float cnt_ = lp_sum(c, tm, 1);   /* this shard's count of soft_Q > rl_Q, all-reduced before stage R6 */ \
+            if (threadIdx.x == 0) *c.dp_count = cnt_;                                   \
+        }                                                                               \
+        const bool end_ = adam_phase != 1 && ((id) == ST_G8 || ((id) == ST_G4 && !do_actor)); \
+        if (end_ && tm.rank == tm.size - 1 && threadIdx.x < HIRL_OUT_SCALARS)          \
+            c.out_scalars[(size_t)step * HIRL_OUT_SCALARS + threadIdx.x] = c.carry[threadIdx.x]; \
+        return true;                                                                    \
+    }                                                                                   \
+    }
     // NOTE: every stage function has exactly ONE call site.  ptxas specialises these non-inlined functions per
     // kernel and lets them read caller registers directly; with a second call site (a separate BC sequence) the
     // actor Adam received a corrupted pointer in some threads.  One call site each keeps that analysis trivially
@@ -1380,7 +1401,7 @@ __device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm
         HIRL_STAGE(ST_R2, stage_r2(c, st, tm, smem))
         HIRL_STAGE(ST_G3, stage_g3(c, tm, smem))
         HIRL_STAGE(ST_R3, stage_r3(c, tm, smem))
-        HIRL_STAGE(ST_G4, stage_g4(c, st, tm))
+        HIRL_STAGE(ST_G4, stage_g4(c, st, tm, adam_phase))
     }
     if (bc_only || do_actor) {
         if (!bc_only) {
@@ -1392,7 +1413,7 @@ __device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm
         HIRL_STAGE(ST_R6, stage_r6(c, st, tm, smem))
         HIRL_STAGE(ST_G7, stage_g7(c, st, tm, smem))
         HIRL_STAGE(ST_R7, stage_r7(c, st, tm, smem))
-        HIRL_STAGE(ST_G8, stage_g8(c, st, tm))
+        HIRL_STAGE(ST_G8, stage_g8(c, st, tm, adam_phase))
     }
 #undef HIRL_STAGE
     if (tm.rank == tm.size - 1 && threadIdx.x < HIRL_OUT_SCALARS) c.out_scalars[(size_t)step * HIRL_OUT_SCALARS + threadIdx.x] = c.carry[threadIdx.x];

@@ -2,7 +2,9 @@
 
 The hot path shards only where it is naturally independent:
   * agent updates: independent replicas / seeds, R/k per GPU, NO data-path collective;
-  * env pass: contiguous chunks of N/k states per GPU, no exchange.
+  * env pass: contiguous chunks of N/k states per GPU, no exchange;
+  * data-parallel large-batch mode (one agent, global batch cut into equal row shards): every rank draws the same index
+    streams and keeps its rows (shard_step); the gradient all-reduces live in the C library (hirl_allreduce_init).
 torch.distributed (NCCL on GPUs, gloo in the CPU tests) is used for the timing barrier, the
 max-over-ranks reduction and gathering small result records -- plumbing, not the product.
 """
@@ -26,6 +28,22 @@ def shard_range(n: int, world: int, rank: int):
     base, extra = divmod(n, world)
     start = rank * base + min(rank, extra)
     return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_step(n_online: int, n_expert: int, idx_online, idx_expert, idx_bc, rank: int, world: int):
+    """Rows [rank * B/world, (rank + 1) * B/world) of one learn() call's batch of B = n_online + n_expert rows.
+
+    The batch is the reference's torch.cat((online batch, expert batch)) (HIRL.py:229-233): row b < n_online is
+    online[idx_online[b]], the others expert[idx_expert[b - n_online]]; the cloning batch (HIRL.py:249-251) is row-aligned
+    with it.  Returns (n_online_loc, n_expert_loc, idx_online_loc, idx_expert_loc, idx_bc_loc): concatenating the shards
+    of all ranks in rank order gives back the global batch row for row."""
+    B = int(n_online) + int(n_expert)
+    if B % world:
+        raise ValueError("the global batch must be a multiple of the world size")
+    lo, hi = shard_range(B, world, rank)
+    on_lo, on_hi = min(lo, n_online), min(hi, n_online)
+    ex_lo, ex_hi = max(lo, n_online) - n_online, max(hi, n_online) - n_online
+    return on_hi - on_lo, ex_hi - ex_lo, idx_online[on_lo:on_hi], idx_expert[ex_lo:ex_hi], idx_bc[lo:hi]
 
 
 def replica_seeds(base_seed: int, n_replicas: int, world: int, rank: int):

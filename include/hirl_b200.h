@@ -103,6 +103,25 @@ const char *hirl_last_error(void);
 int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out);
 int hirl_agent_destroy(hirl_agent_t *h);
 int hirl_agent_sm_count(hirl_agent_t *h);
+/* which update kernel this handle launches: 0 stage kernel, 1 tensor-core cluster kernel (single relu agent, batch <= 256),
+ * 2 FP32 cluster kernel (HIRL_CLUSTER=1), 3 ensemble kernel (replicas > 1) */
+int hirl_agent_backend(hirl_agent_t *h);
+
+/* ---- data-parallel large-batch mode --------------------------------------
+ * No reference counterpart (the reference is one process); it sits exactly at the reference's two
+ * optimizer boundaries: critic_optimizer.step() (HIRL.py:286-288) and actor_optimizer.step()
+ * (HIRL.py:323-325), plus the batch mean of the soft Q-filter (HIRL.py:303).  One process per GPU,
+ * each a full replica of the agent holding cfg.batch = global_batch / world rows of every call's batch;
+ * the per-shard gradients (276 482 + 138 756 fp32), the filter count and the loss scalars are summed
+ * with NCCL all-reduces over NVLink between stage ranges of the update kernel, so every rank applies the
+ * same Adam step.  Loss means run over global_batch.  The caller cuts the index streams it drew once
+ * into shards (hirl4ucav_b200/parallel.py: shard_step).
+ *   hirl_nccl_unique_id: rank 0 fills a 128-byte ncclUniqueId, the caller broadcasts it by any side channel;
+ *   hirl_allreduce_init: collective; creates this handle's own communicator from the id;
+ *   hirl_allreduce_attach: use an existing ncclComm_t instead (not destroyed with the handle). */
+int hirl_nccl_unique_id(void *id128);
+int hirl_allreduce_init(hirl_agent_t *h, const void *id128, int rank, int world, int global_batch);
+int hirl_allreduce_attach(hirl_agent_t *h, void *nccl_comm, int rank, int world, int global_batch);
 
 /* ---- parameters: state_dict import/export (HIRL.py:99-103,142-146,336-350) -------------
  * flat fp32 vector = concatenation of the module's parameters in state_dict order, each

@@ -26,6 +26,22 @@ def test_replica_seeds_do_not_depend_on_world_size():
         assert many == one
 
 
+def test_shard_step_reassembles_the_global_batch():
+    rng = np.random.default_rng(3)
+    for B, n_ex in ((8, 3), (256, 64), (4096, 1024), (64, 0), (64, 63)):
+        n_on = B - n_ex
+        on, ex, bc = rng.integers(0, 10 ** 5, n_on), rng.integers(0, 10 ** 4, n_ex), rng.permutation(20000)[:B]
+        for world in (1, 2, 4, 8):
+            rows, bcs = [], []
+            for r in range(world):
+                a, b, o, e, c = parallel.shard_step(n_on, n_ex, on, ex, bc, r, world)
+                assert a + b == B // world == len(c) and len(o) == a and len(e) == b
+                rows += [("on", int(i)) for i in o] + [("ex", int(i)) for i in e]
+                bcs += list(c)
+            assert rows == [("on", int(i)) for i in on] + [("ex", int(i)) for i in ex]     # the reference's torch.cat order (HIRL.py:229-233)
+            assert bcs == list(bc)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -41,6 +57,14 @@ def _worker(rank, world, port, q):
         x = np.arange(1001, dtype=np.int64)
         a, b = parallel.shard_range(x.size, world, rank)
         chk = parallel.sum_over_ranks(float(x[a:b].sum()))
+        # data-parallel mode: every rank draws the same streams (same seed) and keeps its rows; the union is the global batch
+        g = np.random.default_rng(11)
+        on, ex, bc = g.integers(0, 1000, 48), g.integers(0, 100, 16), g.permutation(500)[:64]
+        n_on, n_ex, o, e, c = parallel.shard_step(48, 16, on, ex, bc, rank, world)
+        shards = parallel.gather_records((n_on, n_ex, [int(i) for i in o], [int(i) for i in e], [int(i) for i in c]))
+        assert sum(s_[0] for s_ in shards) == 48 and sum(s_[1] for s_ in shards) == 16
+        assert sum((s_[2] for s_ in shards), []) == [int(i) for i in on] and sum((s_[3] for s_ in shards), []) == [int(i) for i in ex]
+        assert sum((s_[4] for s_ in shards), []) == [int(i) for i in bc]
         q.put((rank, [r["seed"] for r in allr], [r["value"] for r in allr], t_max, total, chk))
     finally:
         dist.destroy_process_group()
