@@ -70,6 +70,8 @@ SYMBOLS = {
     "hirl_agent_stream": (_i, [_vp, C.POINTER(_vp)]),
     "hirl_host_sample_indices": (_i, [_vp, _i, _i, _vp]),
     "hirl_host_choice_noreplace": (_i, [_vp, _i, _i, _vp]),
+    "hirl_host_choice_noreplace_async": (_i, [_vp, _i, _i, _vp]),
+    "hirl_host_async_wait": (_i, []),
     "hirl_debug_stop_after": (_i, [_vp, _i]),
     "hirl_debug_profile": (_i, [_vp, _i, _vp, _sz]),
     "hirl_debug_export": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_sz)]),

@@ -134,6 +134,9 @@ class Agent(object):
         mk = lambda shape, dt: torch.zeros(shape, dtype=dt, pin_memory=pin)
         self._st_steps_t = mk((K * _lib.STEP_DTYPE.itemsize,), torch.uint8)
         self._st_steps = self._st_steps_t.numpy().view(_lib.STEP_DTYPE)
+        self._st_i32 = self._st_steps_t.numpy().view(np.int32).reshape(K, 16)      # the same records, word by word (hirl_step_t)
+        self._st_f32 = self._st_steps_t.numpy().view(np.float32).reshape(K, 16)
+        self._ld = self._ld_cache = None
         self._st_on_t, self._st_ex_t, self._st_bc_t = mk((K, B), torch.int32), mk((K, B), torch.int32), mk((K, B), torch.int32)
         self._st_on, self._st_ex, self._st_bc = self._st_on_t.numpy(), self._st_ex_t.numpy(), self._st_bc_t.numpy()
         self._st_out_t = mk((K, _lib.OUT_SCALARS), torch.float32)
@@ -361,6 +364,10 @@ class Agent(object):
             else:
                 pre = self._pre_np.take([(n_bc, B)]) if k == 0 and not self.buffer.upsample else None
                 idx_bc = pre[0] if pre is not None else fast_rng.choice_noreplace(n_bc, B)   # == np.random.choice(n_bc, B, replace=False)
+                if self.PREDRAW and k == 0 and not forced and not self.buffer.upsample and not self.expert_upsample:
+                    # the NEXT call's cloning batch starts now, on the library's worker thread (a full 20 000-element
+                    # shuffle, ~60 us: longer than the kernel); it has this whole call to finish
+                    self._pre_np.prepare([(n_bc, B)])
             self._st_bc[k, :] = idx_bc
             if self.expert_upsample and "bc" not in forced:
                 # HIRL.py:253-257: one random row of the cloning batch is replaced by a firing expert row
@@ -385,11 +392,27 @@ class Agent(object):
             do_polyak = self.update_count % self.target_update_freq == 0
         self.actorTrainable = not self.actorTrainable
         # one record assignment (field order = hirl_step_t)
-        self._st_steps[k] = (n_on, n_ex, int(do_actor), int(do_polyak), bc_weight_now, bc_warm_up_weight,
-                             forced.get("soft_weight", -1.0), noise, c_neg, c_bs, a_neg, a_bs, self._MODE)
-        self.last_draws = {"online": self._st_on[k, :n_on].copy(), "expert": self._st_ex[k, :n_ex].copy(),
-                           "bc": None if idx_bc is None else self._st_bc[k].copy(), "noise": noise.copy()}
+        wi, wf = self._st_i32[k], self._st_f32[k]
+        wi[0:4] = (n_on, n_ex, do_actor, do_polyak)
+        wf[4:7] = (bc_weight_now, bc_warm_up_weight, forced.get("soft_weight", -1.0))
+        wf[7:11] = noise
+        wf[11:15] = (c_neg, c_bs, a_neg, a_bs)
+        wi[15] = self._MODE
+        self._ld, self._ld_cache = (k, n_on, n_ex, idx_bc is not None, noise), None
         return do_actor
+
+    @property
+    def last_draws(self):
+        """The index / noise streams of the last drawn call (copies, built on first access)."""
+        if self._ld_cache is None and self._ld is not None:
+            k, n_on, n_ex, has_bc, noise = self._ld
+            self._ld_cache = {"online": self._st_on[k, :n_on].copy(), "expert": self._st_ex[k, :n_ex].copy(),
+                              "bc": self._st_bc[k].copy() if has_bc else None, "noise": np.array(noise, np.float32)}
+        return self._ld_cache
+
+    @last_draws.setter
+    def last_draws(self, value):
+        self._ld, self._ld_cache = None, value
 
     def _finish(self, k, do_actor, bc_weight_now, bc_warm_up_weight):
         """Builds the reference's return tuple (HIRL.py:334) from the kernel's scalars."""
@@ -430,7 +453,7 @@ class Agent(object):
         n_ex = int(expert_num_now) if (self.expert_warm_up and expert_num_now) else 0
         if not self.buffer.upsample:
             self._pre_py.prepare(self._py_requests(n_next, n_ex))
-            if self._MODE != 1:
+            if self._MODE != 1 and not self._pre_np.ready():     # (HIRL: already started at the top of this call, see _draw)
                 self._pre_np.prepare([(len(self.expert_states), self.batchSize)])
 
     def _pre_launch(self):

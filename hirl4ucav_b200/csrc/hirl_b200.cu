@@ -11,6 +11,9 @@
 #include "env.cuh"
 #include "update.cuh"
 #include "cluster_update.cuh"
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include "tcc_update.cuh"
 #include "host_rng.h"
 
@@ -1171,9 +1174,10 @@ int hirl_agent_stream(hirl_agent_t *h, void **stream_out) {
     return 0;
 }
 
-int hirl_host_choice_noreplace(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t *out) {
-    if (!st || !out || population < 1 || size < 0 || size > population || st->pos < 0 || st->pos > 624)
-        return fail(HIRL_E_INVALID, "bad argument");
+static bool choice_args_ok(const hirl_mt19937_t *st, int32_t population, int32_t size, const int32_t *out) {
+    return st && out && population >= 1 && size >= 0 && size <= population && st->pos >= 0 && st->pos <= 624;
+}
+static void choice_noreplace_impl(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t *out) {
     hirl_host::MT19937 g{st->key, st->pos};
     static thread_local std::vector<int32_t> perm;
     perm.resize((size_t)population);
@@ -1217,6 +1221,61 @@ int hirl_host_choice_noreplace(hirl_mt19937_t *st, int32_t population, int32_t s
     if (avail) g.pos = 624 - (avail - q);   // hand the unconsumed outputs back (no block drawn: position untouched)
     for (int32_t i = 0; i < size; ++i) out[i] = perm[i];
     st->pos = g.pos;
+}
+int hirl_host_choice_noreplace(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t *out) {
+    if (!choice_args_ok(st, population, size, out)) return fail(HIRL_E_INVALID, "bad argument");
+    choice_noreplace_impl(st, population, size, out);
+    return 0;
+}
+
+// The same draw on a library-owned worker thread: np.random.choice(20000, 256, replace=False) is a full 20 000-element shuffle
+// (~60 us), longer than everything else the host does for one learn() call.  The caller hands over a private COPY of the
+// generator state (speculative pre-draw, utils/fast_rng.Predraw) and collects the result at the next call; one job at a time.
+namespace {
+struct HostWorker {
+    std::mutex m;
+    std::condition_variable cv;
+    bool has_job = false, done = true;
+    hirl_mt19937_t *st = nullptr;
+    int32_t n = 0, k = 0;
+    int32_t *out = nullptr;
+};
+HostWorker *g_worker = nullptr;   // leaked on purpose: the detached thread may outlive static destructors
+void host_worker_main(HostWorker *w) {
+    for (;;) {
+        std::unique_lock<std::mutex> lk(w->m);
+        w->cv.wait(lk, [w] { return w->has_job; });
+        hirl_mt19937_t *st = w->st;
+        const int32_t n = w->n, k = w->k;
+        int32_t *out = w->out;
+        w->has_job = false;
+        lk.unlock();
+        choice_noreplace_impl(st, n, k, out);
+        lk.lock();
+        w->done = true;
+        w->cv.notify_all();
+    }
+}
+}  // namespace
+int hirl_host_choice_noreplace_async(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t *out) {
+    if (!choice_args_ok(st, population, size, out)) return fail(HIRL_E_INVALID, "bad argument");
+    if (!g_worker) {
+        g_worker = new HostWorker;
+        std::thread(host_worker_main, g_worker).detach();
+    }
+    HostWorker *w = g_worker;
+    std::lock_guard<std::mutex> lk(w->m);
+    if (!w->done) return fail(HIRL_E_UNSUPPORTED, "a host draw is already pending (one at a time)");
+    w->st = st; w->n = population; w->k = size; w->out = out;
+    w->done = false; w->has_job = true;
+    w->cv.notify_all();
+    return 0;
+}
+int hirl_host_async_wait(void) {
+    HostWorker *w = g_worker;
+    if (!w) return 0;
+    std::unique_lock<std::mutex> lk(w->m);
+    w->cv.wait(lk, [w] { return w->done; });
     return 0;
 }
 

@@ -191,6 +191,18 @@ def choice_noreplace_on(rs, n: int, k: int):
     return _c_choice(_np_live(rs), n, k)
 
 
+_exit_join_registered = False
+
+
+def _register_exit_join():
+    """The worker thread writes into Python-owned buffers: never let the interpreter tear them down under it."""
+    global _exit_join_registered
+    if not _exit_join_registered:
+        import atexit
+        atexit.register(lambda: _lib.load().hirl_host_async_wait())
+        _exit_join_registered = True
+
+
 class Predraw:
     """Speculative draws for the next call (see the module docstring).  ``kind`` is "py" (random.sample stream:
     a list of (n, k) draws made back to back) or "np" (np.random.choice stream: one (n, k) draw)."""
@@ -198,6 +210,7 @@ class Predraw:
     def __init__(self, kind: str):
         self.kind = kind
         self._snap = None
+        self._pending = False
         self.hits = self.misses = 0
 
     def _live(self) -> MTState:
@@ -206,19 +219,39 @@ class Predraw:
     def enabled(self) -> bool:
         return py_fast() if self.kind == "py" else np_fast()
 
+    def _join(self):
+        """A draw handed to the library's worker thread is finished (its state copy and output array are ours again)."""
+        if self._pending:
+            _lib.load().hirl_host_async_wait()
+            self._pending = False
+
     def prepare(self, requests):
-        """requests: list of (n, k) expected at the next call."""
+        """requests: list of (n, k) expected at the next call.  The np stream (one full shuffle, the longest thing the host
+        does per call) runs on the library's worker thread; take() collects it."""
+        self._join()
         self._snap = None
         if not self.enabled() or any(not (0 <= k <= n and 0 < n < (1 << 31)) for n, k in requests):
             return
         snap = self._live()
         work = _copy(snap)
+        if self.kind == "np" and len(requests) == 1:
+            n, k = requests[0]
+            out = np.empty(k, np.int32)
+            if _lib.load().hirl_host_choice_noreplace_async(C.byref(work), n, k, _lib.ptr(out)) == 0:
+                _register_exit_join()
+                self._pending = True
+                self._snap, self._after, self._req, self._outs = snap, work, list(requests), [out]
+                return
         fn = _c_sample if self.kind == "py" else _c_choice
         outs = [fn(work, n, k) for n, k in requests]
         self._snap, self._after, self._req, self._outs = snap, work, list(requests), outs
 
+    def ready(self) -> bool:
+        return self._snap is not None
+
     def take(self, requests):
         """Returns the pre-drawn index arrays if they are exactly what drawing now would give, else None."""
+        self._join()
         snap, self._snap = self._snap, None
         if snap is None or list(requests) != self._req or not _live_equals(self.kind, snap):
             self.misses += 1

@@ -191,6 +191,10 @@ int hirl_agent_stream(hirl_agent_t *h, void **stream_out);
 typedef struct hirl_mt19937 { uint32_t key[624]; int32_t pos; } hirl_mt19937_t;
 int hirl_host_sample_indices(hirl_mt19937_t *st, int32_t n, int32_t k, int32_t *out);
 int hirl_host_choice_noreplace(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t *out);
+/* the same draw on a library-owned worker thread (one job at a time): `st` must be a private copy that stays alive,
+ * together with `out`, until hirl_host_async_wait() returns.  HIRL_E_UNSUPPORTED if a job is already pending. */
+int hirl_host_choice_noreplace_async(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t *out);
+int hirl_host_async_wait(void);
 
 /* ---- test hooks ------------------------------------------------------------------------ */
 /* stop the next hirl_learn after this many stages of its first step (0 = run everything) */

@@ -16,18 +16,22 @@ run() {   # name tool env... -- args...
 : > "$out/summary.txt"
 nvcc --version | tail -1 >> "$out/summary.txt"
 for tool in ${TOOLS:-memcheck racecheck synccheck}; do
-  run fp32_b64       $tool HIRL_TC=0 HIRL_CLUSTER=0 -- --batch 64
-  run g1tc_b256      $tool HIRL_TC=2 HIRL_CLUSTER=0 -- --batch 256
-  run fulltc_b256    $tool HIRL_TC=1 HIRL_CLUSTER=0 -- --batch 256
-  run cluster_b64    $tool HIRL_CLUSTER=1 -- --batch 64
+  run tcc_b256       $tool HIRL_TCC=1 HIRL_CLUSTER=0 -- --batch 256
+  run tcc_b100       $tool HIRL_TCC=1 HIRL_CLUSTER=0 -- --batch 100
+  run fp32_b64       $tool HIRL_TCC=0 HIRL_TC=0 HIRL_CLUSTER=0 -- --batch 64
+  run g1tc_b256      $tool HIRL_TCC=0 HIRL_TC=2 HIRL_CLUSTER=0 -- --batch 256
+  run fulltc_b256    $tool HIRL_TCC=0 HIRL_TC=1 HIRL_CLUSTER=0 -- --batch 256
+  run dp1_b64        $tool HIRL_TCC=0 HIRL_TC=0 HIRL_CLUSTER=0 -- --batch 64 --dp
+  run cluster_b64    $tool HIRL_TCC=0 HIRL_CLUSTER=1 -- --batch 64
   run ensemble_b128  $tool HIRL_CLUSTER=0 -- --batch 128 --ensemble 3 --steps 4
 done
-run g1tc_b256 initcheck HIRL_TC=2 HIRL_CLUSTER=0 -- --batch 256
+run g1tc_b256 initcheck HIRL_TCC=0 HIRL_TC=2 HIRL_CLUSTER=0 -- --batch 256
+run tcc_b256 initcheck HIRL_TCC=1 HIRL_CLUSTER=0 -- --batch 256
 # the stage_g8-as-a-separate-function build (update.cuh: HIRL_G8_NOINLINE), when present: does the round-1 fault reproduce?
 if [ -f hirl4ucav_b200/_lib/libhirl_g8noinline.so ]; then
   for tool in memcheck racecheck initcheck; do
-    run g8noinline_fp32_b64  $tool HIRL_LIB_PATH=$PWD/hirl4ucav_b200/_lib/libhirl_g8noinline.so HIRL_TC=0 HIRL_CLUSTER=0 -- --batch 64
-    run g8noinline_g1tc_b256 $tool HIRL_LIB_PATH=$PWD/hirl4ucav_b200/_lib/libhirl_g8noinline.so HIRL_TC=2 HIRL_CLUSTER=0 -- --batch 256
+    run g8noinline_fp32_b64  $tool HIRL_LIB_PATH=$PWD/hirl4ucav_b200/_lib/libhirl_g8noinline.so HIRL_TCC=0 HIRL_TC=0 HIRL_CLUSTER=0 -- --batch 64
+    run g8noinline_g1tc_b256 $tool HIRL_LIB_PATH=$PWD/hirl4ucav_b200/_lib/libhirl_g8noinline.so HIRL_TCC=0 HIRL_TC=2 HIRL_CLUSTER=0 -- --batch 256
   done
 fi
 cat "$out/summary.txt"

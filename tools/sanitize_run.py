@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--steps", type=int, default=6)
 ap.add_argument("--ensemble", type=int, default=0, help="replicas (0: single agent)")
+ap.add_argument("--dp", action="store_true", help="data-parallel mode with one rank (stage-range launches + NCCL all-reduces)")
 a = ap.parse_args()
 es, ea = synth.expert_table(1500)
 set_seed(0)
@@ -37,7 +38,8 @@ if a.ensemble:
     print("ensemble ok", out[:, -1, :4].tolist())
 else:
     from hirl4ucav_b200.agents.HIRL import Agent
-    ag = Agent(1e-3, 1e-3, 13, 4, 256, 512, 0.005, 0.99, 10 ** 4, a.batch, True, "Harfang_GYM", es, ea, 0.5, True, max_fused_steps=8)
+    ag = Agent(1e-3, 1e-3, 13, 4, 256, 512, 0.005, 0.99, 10 ** 4, a.batch, True, "Harfang_GYM", es, ea, 0.5, True, max_fused_steps=8,
+               **({"data_parallel": (0, 1)} if a.dp else {}))
     synth.fill_agent(ag, 3000, expert_states=es, expert_actions=ea)
     out = ag.learn_many([(100, a.batch // 4, 0)] * a.steps)
     print("single ok", [float(x) for x in out[-1]])
