@@ -364,10 +364,6 @@ class Agent(object):
             else:
                 pre = self._pre_np.take([(n_bc, B)]) if k == 0 and not self.buffer.upsample else None
                 idx_bc = pre[0] if pre is not None else fast_rng.choice_noreplace(n_bc, B)   # == np.random.choice(n_bc, B, replace=False)
-                if self.PREDRAW and k == 0 and not forced and not self.buffer.upsample and not self.expert_upsample:
-                    # the NEXT call's cloning batch starts now, on the library's worker thread (a full 20 000-element
-                    # shuffle, ~60 us: longer than the kernel); it has this whole call to finish
-                    self._pre_np.prepare([(n_bc, B)])
             self._st_bc[k, :] = idx_bc
             if self.expert_upsample and "bc" not in forced:
                 # HIRL.py:253-257: one random row of the cloning batch is replaced by a firing expert row
@@ -452,9 +448,10 @@ class Agent(object):
         self._n_online_prev = n_now
         n_ex = int(expert_num_now) if (self.expert_warm_up and expert_num_now) else 0
         if not self.buffer.upsample:
-            self._pre_py.prepare(self._py_requests(n_next, n_ex))
-            if self._MODE != 1 and not self._pre_np.ready():     # (HIRL: already started at the top of this call, see _draw)
+            if self._MODE != 1:
+                # a full 20 000-element shuffle (~60 us): handed to the library's worker thread, collected by the next call's take()
                 self._pre_np.prepare([(len(self.expert_states), self.batchSize)])
+            self._pre_py.prepare(self._py_requests(n_next, n_ex))
 
     def _pre_launch(self):
         self.buffer.flush()

@@ -917,6 +917,7 @@ static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_de
         c.steps = steps_dev; c.idx_online = ion; c.idx_expert = iex; c.idx_bc = ibc; c.out_scalars = out_dev;
         L.bar_flags = h->d_bar; L.k_steps = k_steps; L.ncl = h->tcc_ncl;
         L.prof = h->prof_on ? h->d_prof : nullptr;
+        { const char *e = getenv("HIRL_TCC_JITTER"); L.jitter = e ? (unsigned)atoi(e) : 0u; }
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3(h->tcc_ncl * tcc::CL); lc.blockDim = dim3(tcc::TTHREADS);
         lc.dynamicSmemBytes = tcc::SMEM_BYTES;

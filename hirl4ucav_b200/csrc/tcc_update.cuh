@@ -69,7 +69,7 @@ constexpr int O_X = O_D + 16384 + 17408;                        // 8 KB    gathe
 constexpr int O_ACT = O_X + 8192;                        // 1 KB    action columns of the critic input [64][4]
 constexpr int O_GPI = O_ACT + 1024;                      // 1 KB    d pi [64][4]
 constexpr int O_PC = O_GPI + 1024;                       // 2 KB    parameter cache of the pass: b2 | g2 | be2 | w3[nout] (this CTA's 64 features) | b3
-constexpr int O_RED = O_PC + 2048;                       // 2 KB    [1K,2K) half-row combine scratch of the exchanges
+constexpr int O_RED = O_PC + 2048;                       // 2 KB    half-row combine scratch of the exchanges, one KB per exchange parity
 constexpr int SMEM_USED = O_RED + 2048;
 constexpr size_t SMEM_BYTES = SMEM_USED + 1024;          // + alignment slack
 static_assert(SMEM_BYTES + 1200 <= 232448, "shared memory budget (227 KB per CTA incl. static)");
@@ -100,6 +100,7 @@ struct TccLaunch {
     unsigned *bar_flags;   // [MAX_NCL][32] cluster flags of the grid barrier
     int k_steps, ncl;
     long long *prof;       // [PROF_STEPS][PROF_WORDS] SM-clock stamps of cluster 0 / CTA 0 (may be null)
+    unsigned jitter;       // debug (HIRL_TCC_JITTER=seed): pseudo-random per-CTA delays at the synchronisation sites; results must not change
 };
 
 struct Ctl {
@@ -115,6 +116,7 @@ struct Ctl {
     unsigned *flags, *pflags;
     long long *pr, *pr2;   // pr: stamps of cluster 0 / CTA 0;  pr2: of the first online unit's cluster (phase A) / CTA 0
     int pb;   // base index of the fine-grained stamps of the current pass (0: off)
+    unsigned jit, jit_n;   // timing-perturbation test: seed (0 = off) and site counter
 };
 __device__ __forceinline__ void stamp(const Ctl &k, int id) { if (k.pr && threadIdx.x == 0) k.pr[id] = clock64(); }
 __device__ __forceinline__ void stamp2(const Ctl &k, int id) { if (k.pr2 && threadIdx.x == 0) k.pr2[id] = clock64(); }
@@ -124,7 +126,20 @@ __device__ __forceinline__ void pstamp(const Ctl &k, int i) {
 }
 
 // ---- synchronisation -----------------------------------------------------------------------------------------------
+// Timing-perturbation hook: with HIRL_TCC_JITTER set every CTA (and, at warp-level sites, every warp) sleeps a pseudo-random
+// 0-4 us at the synchronisation sites.  The kernel's results must be bit-identical with and without it
+// (tests/test_gpu_update.py::test_tcc_results_do_not_depend_on_timing): every cross-CTA hand-over is ordered by a barrier,
+// an mbarrier or a release/acquire flag, never by timing.
+__device__ __forceinline__ void jitter(Ctl &k, bool per_warp = false) {
+    if (k.jit == 0u) return;
+    k.jit_n += 1u;
+    unsigned h = k.jit * 2654435761u ^ (k.jit_n * 40503u) ^ ((unsigned)(k.cid * CL + k.crank) * 2246822519u) ^ (per_warp ? (unsigned)k.warp * 3266489917u : 0u);
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    if ((h & 3u) == 0u) return;
+    __nanosleep(h % 4000u);
+}
 __device__ __forceinline__ void grid_sync(Ctl &k) {
+    jitter(k);
     cluster_sync();                                                    // the whole cluster has arrived (cluster-scope release / acquire)
     k.gen += 1u;
     if (threadIdx.x < 32) {                                            // one flag per cluster, polled by every CTA (no second cluster barrier)
@@ -145,6 +160,7 @@ __device__ __forceinline__ void grid_sync(Ctl &k) {
 }
 // producer side of a point-to-point flag: the CTA's global writes, then one release store
 __device__ __forceinline__ void flag_publish(Ctl &k, int word, unsigned value) {
+    jitter(k);
     __syncthreads();
     if (threadIdx.x == 0) st_release_u32(k.pflags + word * FLAG_STRIDE, value);
 }
@@ -172,10 +188,12 @@ __device__ __forceinline__ float4 *xslot(const Ctl &k, int buf, int src, int row
 }
 __device__ __forceinline__ void exchange_push(Ctl &k, float a, float b, float c, float d, bool chan) {
     const int buf = k.xr & 1;
-    float4 *half = reinterpret_cast<float4 *>(k.sm + O_RED + 1024);               // [64 rows] contribution of the upper column half
+    float4 *half = reinterpret_cast<float4 *>(k.sm + O_RED + 1024 * buf);         // [64 rows] contribution of the upper column half (one buffer per parity:
+                                                                                  //  the next write is behind the next exchange's bar.sync, not only behind the mbarrier)
     if (k.act && k.wh == 1) half[k.row] = make_float4(a, b, c, d);
     if (threadIdx.x == 0) mbar_expect_tx(k.bars + B_X0 + buf, CL * RB * 16);
     __syncthreads();
+    jitter(k, true);
     if (k.act && k.wh == 0) {
         const float4 o = half[k.row];
         float4 v;
@@ -379,6 +397,7 @@ __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const floa
                                              float (&xh)[32], float &rstd, float (&out)[L::nout], OwnRow &own, const float *next_units) {
     char *sm = k.sm;
     const float *unit0 = slice_of(k, img);                             // this CTA's slice: 8 k-blocks of hi | lo
+    jitter(k);
     float pcv[2], b3v;
     pc_fetch<L>(k, tw, pcv, b3v);
     stage_w1<L>(k, tw);
@@ -389,6 +408,7 @@ __device__ __forceinline__ void pass_forward(Ctl &k, const float *tw, const floa
     l1_rows<L>(k, tw, soff, acts, slope, k.h1img, hrow, own);
     pc_store<L>(k, pcv, b3v);                                          // read after the cluster barrier below
     pstamp(k, 1);
+    jitter(k, true);
     // every CTA's rows of the H1 image (and of the H1^T image) are in L2, and every CTA is past its last use of the
     // operand-tile region (it arrives here only after that): the multicast below may land everywhere
     cluster_sync();
@@ -577,6 +597,7 @@ template <class L, bool WITH_DW>
 __device__ __forceinline__ void pass_backward(Ctl &k, const float *tw, const float *imgt, float slope, const float (&dz)[32], const OwnRow &own,
                                               float *dh1p_unit, const float *h1t, float *gw2p_slot, BwdOut &o, const float *next_units) {
     char *sm = k.sm;
+    jitter(k);
     const float *units = slice_of(k, imgt);                           // 8 sub-units: (mb, cc, hi | lo)
     stream_begin(k, units);
     if (WITH_DW && threadIdx.x == PRODUCER) {                         // H1^T image of the row block -> the (dead) H1 region
@@ -686,6 +707,7 @@ __device__ __forceinline__ void pass_backward(Ctl &k, const float *tw, const flo
         k.h1t_n += 1u;
     }
     pstamp(k, 4);
+    jitter(k, true);
     cluster_sync();                                                   // every CTA's dH1 partial is visible (cluster-scope release / acquire)
     pstamp(k, 5);
     // (6) the CTA's own 8 rows: sum the 8 partials in a fixed order, LayerNorm1 backward (xhat1 / rstd1 kept from the forward)
@@ -949,6 +971,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
     k.flags = Lc.bar_flags;
     k.gen = ld_relaxed_u32(k.flags + k.cid * FLAG_STRIDE);
     k.pr = k.pr2 = nullptr; k.pb = 0; k.pre = nullptr;
+    k.jit = Lc.jitter; k.jit_n = 0u;
     if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot);
     if (threadIdx.x == 32) {
         for (int i = 0; i < N_BARS; ++i) tc::mbar_init(bars + i, (i >= B_EMPTY && i < B_ACC + 2) ? ISSUERS : 1);

@@ -260,6 +260,30 @@ def test_learn_many_is_bit_identical_to_single_calls_and_deterministic():
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("B,en", [(256, 64), (100, 25)])
+def test_tcc_results_do_not_depend_on_timing(B, en, monkeypatch):
+    """The cluster kernel hands data between CTAs / clusters through barriers, mbarriers and release/acquire flags only.
+    HIRL_TCC_JITTER makes every CTA (and warp) sleep a pseudo-random 0-4 us at each synchronisation site: 12 fused calls
+    (the persistent launch overlaps consecutive calls where no grid barrier is needed) and 6 single calls must give the
+    same bits as the unperturbed run."""
+    monkeypatch.setenv("HIRL_TCC", "1")
+    monkeypatch.setenv("HIRL_CLUSTER", "0")
+    sc = scenarios.make_scenario(max(1000, 4 * B), max(600, 3 * B))
+    runs = []
+    for seed in ("0", "1", "7", "12345"):
+        monkeypatch.setenv("HIRL_TCC_JITTER", seed)
+        ag = scenarios.build_agent(Agent, sc, B, 3)
+        assert ag.backend == "tcc"
+        scenarios.seed_all(5)
+        outs = ag.learn_many([(100, en, 0)] * 12) + [ag.learn(100, en, 0) for _ in range(6)]
+        runs.append((np.array([[float(x) for x in o] for o in outs]), [ag.export_flat(nid) for _, nid in NETS]))
+        del ag
+    for other in runs[1:]:
+        assert np.array_equal(runs[0][0], other[0])
+        for a, b in zip(runs[0][1], other[1]):
+            assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("tc_mode", ["0", "1"])
 @pytest.mark.parametrize("ns", ["1", "2", "4"])
 def test_split_k_variants_agree(ns, tc_mode, monkeypatch):
