@@ -32,6 +32,10 @@ class Step(C.Structure):
                 ("actor_neg_step", C.c_float), ("actor_bc2_sqrt", C.c_float), ("mode", C.c_int32)]
 
 
+class DrawJob(C.Structure):     # hirl_draw_job_t
+    _fields_ = [("py", C.c_void_p), ("np", C.c_void_p), ("online_len", C.c_int32), ("expert_len", C.c_int32)]
+
+
 STEP_DTYPE = np.dtype([("n_online", "<i4"), ("n_expert", "<i4"), ("do_actor", "<i4"), ("do_polyak", "<i4"),
                        ("bc_weight_now", "<f4"), ("bc_warm_up", "<f4"), ("force_soft_weight", "<f4"),
                        ("noise", "<f4", (4,)), ("critic_neg_step", "<f4"), ("critic_bc2_sqrt", "<f4"),
@@ -72,6 +76,7 @@ SYMBOLS = {
     "hirl_host_choice_noreplace": (_i, [_vp, _i, _i, _vp]),
     "hirl_host_choice_noreplace_async": (_i, [_vp, _i, _i, _vp]),
     "hirl_host_async_wait": (_i, []),
+    "hirl_host_draw_many": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
     "hirl_debug_stop_after": (_i, [_vp, _i]),
     "hirl_debug_profile": (_i, [_vp, _i, _vp, _sz]),
     "hirl_debug_export": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_sz)]),

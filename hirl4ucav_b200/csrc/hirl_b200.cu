@@ -918,6 +918,7 @@ static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_de
         L.bar_flags = h->d_bar; L.k_steps = k_steps; L.ncl = h->tcc_ncl;
         L.prof = h->prof_on ? h->d_prof : nullptr;
         { const char *e = getenv("HIRL_TCC_JITTER"); L.jitter = e ? (unsigned)atoi(e) : 0u; }
+        { const char *e = getenv("HIRL_TCC_JITTER_NS"); L.jitter_ns = e ? (unsigned)atoi(e) : 0u; }
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3(h->tcc_ncl * tcc::CL); lc.blockDim = dim3(tcc::TTHREADS);
         lc.dynamicSmemBytes = tcc::SMEM_BYTES;
@@ -1330,6 +1331,42 @@ int hirl_host_sample_indices(hirl_mt19937_t *st, int32_t n, int32_t k, int32_t *
         }
     }
     st->pos = g.pos;
+    return 0;
+}
+
+// Every host index draw of a sweep of `k_calls` learn() calls for `n_jobs` independent generator pairs (ensemble replicas),
+// spread over worker threads: job j runs, per call and in the reference's order, random.sample(range(online_len), n_online[k])
+// [, random.sample(range(expert_len), n_expert[k])] on ITS py state and np.random.choice(bc_population, batch, replace=False)
+// on ITS np state.  Generators of different jobs are independent, so the result does not depend on the thread count.
+int hirl_host_draw_many(const hirl_draw_job_t *jobs, int32_t n_jobs, int32_t k_calls, const int32_t *n_online, const int32_t *n_expert,
+                        int32_t bc_population, int32_t batch, int32_t *idx_online, int32_t *idx_expert, int32_t *idx_bc, int32_t n_threads) {
+    if (!jobs || !n_online || !n_expert || !idx_online || !idx_expert || n_jobs < 0 || k_calls < 1 || batch < 1)
+        return fail(HIRL_E_INVALID, "bad argument");
+    for (int32_t j = 0; j < n_jobs; ++j) {
+        const hirl_draw_job_t &jb = jobs[j];
+        if (!jb.py || jb.py->pos < 0 || jb.py->pos > 624 || (idx_bc && (!jb.np || jb.np->pos < 0 || jb.np->pos > 624))) return fail(HIRL_E_INVALID, "bad generator state");
+        for (int32_t k = 0; k < k_calls; ++k)
+            if (n_online[k] < 0 || n_expert[k] < 0 || n_online[k] + n_expert[k] != batch || n_online[k] > jb.online_len || n_expert[k] > jb.expert_len)
+                return fail(HIRL_E_INVALID, "sample larger than population or batch split mismatch");
+    }
+    if (idx_bc && (bc_population < batch)) return fail(HIRL_E_INVALID, "expert table smaller than the batch");
+    const int nt = std::max(1, std::min<int>(n_threads, n_jobs));
+    auto work = [&](int t) {
+        for (int32_t j = t; j < n_jobs; j += nt) {
+            const hirl_draw_job_t &jb = jobs[j];
+            for (int32_t k = 0; k < k_calls; ++k) {
+                const size_t row = ((size_t)j * k_calls + k) * batch;
+                hirl_host_sample_indices(jb.py, jb.online_len, n_online[k], idx_online + row);
+                if (n_expert[k]) hirl_host_sample_indices(jb.py, jb.expert_len, n_expert[k], idx_expert + row);
+                if (idx_bc) choice_noreplace_impl(jb.np, bc_population, batch, idx_bc + row);
+            }
+        }
+    };
+    if (nt == 1) { work(0); return 0; }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
     return 0;
 }
 

@@ -101,6 +101,7 @@ struct TccLaunch {
     int k_steps, ncl;
     long long *prof;       // [PROF_STEPS][PROF_WORDS] SM-clock stamps of cluster 0 / CTA 0 (may be null)
     unsigned jitter;       // debug (HIRL_TCC_JITTER=seed): pseudo-random per-CTA delays at the synchronisation sites; results must not change
+    unsigned jitter_ns;    // upper bound of one delay (HIRL_TCC_JITTER_NS, default 4000)
 };
 
 struct Ctl {
@@ -116,7 +117,7 @@ struct Ctl {
     unsigned *flags, *pflags;
     long long *pr, *pr2;   // pr: stamps of cluster 0 / CTA 0;  pr2: of the first online unit's cluster (phase A) / CTA 0
     int pb;   // base index of the fine-grained stamps of the current pass (0: off)
-    unsigned jit, jit_n;   // timing-perturbation test: seed (0 = off) and site counter
+    unsigned jit, jit_n, jit_ns;   // timing-perturbation test: seed (0 = off), site counter, delay bound
 };
 __device__ __forceinline__ void stamp(const Ctl &k, int id) { if (k.pr && threadIdx.x == 0) k.pr[id] = clock64(); }
 __device__ __forceinline__ void stamp2(const Ctl &k, int id) { if (k.pr2 && threadIdx.x == 0) k.pr2[id] = clock64(); }
@@ -127,7 +128,7 @@ __device__ __forceinline__ void pstamp(const Ctl &k, int i) {
 
 // ---- synchronisation -----------------------------------------------------------------------------------------------
 // Timing-perturbation hook: with HIRL_TCC_JITTER set every CTA (and, at warp-level sites, every warp) sleeps a pseudo-random
-// 0-4 us at the synchronisation sites.  The kernel's results must be bit-identical with and without it
+// 0-4 us (HIRL_TCC_JITTER_NS: other bound) at the synchronisation sites.  The kernel's results must be bit-identical with and without it
 // (tests/test_gpu_update.py::test_tcc_results_do_not_depend_on_timing): every cross-CTA hand-over is ordered by a barrier,
 // an mbarrier or a release/acquire flag, never by timing.
 __device__ __forceinline__ void jitter(Ctl &k, bool per_warp = false) {
@@ -136,7 +137,11 @@ __device__ __forceinline__ void jitter(Ctl &k, bool per_warp = false) {
     unsigned h = k.jit * 2654435761u ^ (k.jit_n * 40503u) ^ ((unsigned)(k.cid * CL + k.crank) * 2246822519u) ^ (per_warp ? (unsigned)k.warp * 3266489917u : 0u);
     h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
     if ((h & 3u) == 0u) return;
-    __nanosleep(h % 4000u);
+    for (unsigned left = h % k.jit_ns; left > 0u;) {   // __nanosleep is capped near 1 ms per call
+        const unsigned d = left > 500000u ? 500000u : left;
+        __nanosleep(d);
+        left -= d;
+    }
 }
 __device__ __forceinline__ void grid_sync(Ctl &k) {
     jitter(k);
@@ -816,8 +821,12 @@ __device__ __forceinline__ void adam_tcc(Ctl &k, int rank, int size, int ntowers
                                          const float *part, int n1, int nq, float neg_step, float bc2_sqrt, float *img, float *imgt,
                                          float *target, float *timg, bool polyak, float tau, float omt, float sc0 = 1.f, float sc1 = 1.f) {
     // BRANCHES: the partial slots are two halves (RL branch | cloning branch) whose sums are scaled by sc0 / sc1
-    // (a) everything but W2
+    // (a) everything but W2: runs between the loads and the arithmetic of the first W2 tile round (both are bound by L2
+    //     round trips, so their latencies overlap instead of adding up)
     const int nsmall = ntowers * L::SMALL;
+    bool small_done = false;
+    auto small_params = [&]() {
+    small_done = true;
     for (int i = rank * TTHREADS + threadIdx.x; i < nsmall; i += size * TTHREADS) {
         const int tower = i / L::SMALL, si = i - tower * L::SMALL;
         const int off = si < L::W2 ? si : si + H2 * H1, e = tower * L::SIZE + off;
@@ -844,6 +853,7 @@ __device__ __forceinline__ void adam_tcc(Ctl &k, int rank, int size, int ntowers
         w[e] = wv; m[e] = mv; v[e] = vv;
         if (polyak) target[e] = polyak_elem(target[e], wv, tau, omt);
     }
+    };
     // (b) W2 tiles, up to 3 tiles' loads in flight per CTA (the loop is bound by L2 round trips, not by arithmetic)
     float *ts = reinterpret_cast<float *>(k.sm + O_R);                 // [32 features][17]
     const int tiles = ntowers * 16 * 16, tk = threadIdx.x & 15, tn = threadIdx.x >> 4;
@@ -877,6 +887,7 @@ __device__ __forceinline__ void adam_tcc(Ctl &k, int rank, int size, int ntowers
                 }
             }
         }
+        if (!small_done) small_params();
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             const int t = t0 + u * size;
@@ -916,6 +927,7 @@ __device__ __forceinline__ void adam_tcc(Ctl &k, int rank, int size, int ntowers
             }
         }
     }
+    if (!small_done) small_params();
 }
 // Polyak of a network whose online copy did not change in this phase (the critic, in phase D)
 template <class L>
@@ -971,7 +983,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
     k.flags = Lc.bar_flags;
     k.gen = ld_relaxed_u32(k.flags + k.cid * FLAG_STRIDE);
     k.pr = k.pr2 = nullptr; k.pb = 0; k.pre = nullptr;
-    k.jit = Lc.jitter; k.jit_n = 0u;
+    k.jit = Lc.jitter; k.jit_n = 0u; k.jit_ns = Lc.jitter_ns ? Lc.jitter_ns : 4000u;
     if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot);
     if (threadIdx.x == 32) {
         for (int i = 0; i < N_BARS; ++i) tc::mbar_init(bars + i, (i >= B_EMPTY && i < B_ACC + 2) ? ISSUERS : 1);
@@ -1098,7 +1110,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                 flag_publish(k, PF_TQ + r * 2 + t, fgen);
             }
             stamp2(k, 39);
-            if (k.act) {
+            load_pc<CriticL>(k, c.critic + t * CriticL::SIZE);         // the parameter cache held the target tower's (free since flag_publish's barrier);
+            if (k.act) {                                               // these loads and the parked state travel while we wait for the partner
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
                     const float4 v4 = __ldcg(reinterpret_cast<const float4 *>(xpark + e));
@@ -1106,7 +1119,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                 }
             }
             rstd = rstd_c;
-            flag_wait(k, PF_TQ + r * 2 + (1 - t), fgen);
+            flag_wait(k, PF_TQ + r * 2 + (1 - t), fgen);               // (its barrier also publishes the parameter cache)
             stamp2(k, 36);
             const float tq_other = __ldcg(c.tcc.TQX + (r * 2 + (1 - t)) * RB + k.row);
             const float *xs = reinterpret_cast<const float *>(k.sm + O_X);
@@ -1121,8 +1134,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
             }
             float dout[1] = {valid ? (2.f / (float)B) * delta : 0.f};                                          // mse_loss backward, mean reduction
             float dz[32], dy[32], h[32];
-            load_pc<CriticL>(k, c.critic + t * CriticL::SIZE);         // the parameter cache held the target tower's
-            __syncthreads();
             head_ln2_backward<CriticL>(k, xh, rstd, dout, slope, dz, dy, h);
             // second-layer small parameters of this CTA's 64 features: db2, dgamma2, dbeta2, dW3 (+ db3, loss by CTA 0)
             float *part = c.tcc.PARTC + ((size_t)r * CL * 2 + t) * CriticL::SMALL;                             // slot 8 r (+ tower)

@@ -142,27 +142,62 @@ class AgentEnsemble(object):
             trainable = not trainable
         self.actorTrainable, self.update_count, self._critic_t, self._actor_t = trainable, upd, ct, at
         mean, std = torch.zeros(self.actionDim), torch.ones(self.actionDim) * self.TD3LearningNoise
+        split = []
+        for bcw, en, warm in calls:
+            n_ex = int(en) if (self.expert_warm_up and en) else 0
+            if B - n_ex <= 0:
+                raise TypeError("expert_num_now == batchSize leaves no online rows")
+            split.append((B - n_ex, n_ex))
+        if fast_rng.py_fast() and fast_rng.np_fast():
+            # every index draw of the sweep in ONE library call, replicas spread over worker threads (their generators are
+            # independent: exact C replicas of the reference's draws on each replica's private state, utils/fast_rng.py)
+            self._draw_indices_threaded(split, on, ex, bc)
+        else:
+            for r in range(R):
+                st = self.streams[r]
+                for k, (n_on, n_ex) in enumerate(split):
+                    on[r, k, :n_on] = fast_rng.sample_indices_on(st.py, self.online_len[r], n_on)
+                    if n_ex:
+                        ex[r, k, :n_ex] = fast_rng.sample_indices_on(st.py, self.expert_len[r], n_ex)
+                    bc[r, k, :] = fast_rng.choice_noreplace_on(st.np, self.n_expert, B)
+        # the step records: the schedule is the same for every replica, only the noise differs
+        i32 = self._steps_t.numpy().view(np.int32)[: R * K * 16].reshape(R, K, 16)
+        f32 = self._steps_t.numpy().view(np.float32)[: R * K * 16].reshape(R, K, 16)
+        for k, ((bcw, en, warm), (n_on, n_ex)) in enumerate(zip(calls, split)):
+            i32[:, k, 0:4] = (n_on, n_ex, int(sched[k][0]), int(sched[k][1]))
+            f32[:, k, 4:7] = (bcw, warm, -1.0)
+            f32[:, k, 11:15] = sched[k][2] + sched[k][3]
+            i32[:, k, 15] = 0
+        for r in range(R):
+            g = self.streams[r].torch
+            for k in range(K):
+                f32[r, k, 7:11] = torch.normal(mean=mean, std=std, generator=g).numpy()
+        return K
+
+    def _draw_indices_threaded(self, split, on, ex, bc):
+        import os
+        R, K, B = self.R, len(split), self.batchSize
+        Kmax = on.shape[1]
+        py_states = (fast_rng.MTState * R)()
+        jobs = (_lib.DrawJob * R)()
         for r in range(R):
             st = self.streams[r]
-            for k, (bcw, en, warm) in enumerate(calls):
-                n_ex = int(en) if (self.expert_warm_up and en) else 0
-                n_on = B - n_ex
-                if n_on <= 0:
-                    raise TypeError("expert_num_now == batchSize leaves no online rows")
-                # exact C replicas of the reference's draws on this replica's private generators (utils/fast_rng.py)
-                on[r, k, :n_on] = fast_rng.sample_indices_on(st.py, self.online_len[r], n_on)
-                if n_ex:
-                    ex[r, k, :n_ex] = fast_rng.sample_indices_on(st.py, self.expert_len[r], n_ex)
-                bc[r, k, :] = fast_rng.choice_noreplace_on(st.np, self.n_expert, B)
-                s = steps[r, k]
-                s["n_online"], s["n_expert"] = n_on, n_ex
-                s["do_actor"], s["do_polyak"] = int(sched[k][0]), int(sched[k][1])
-                s["bc_weight_now"], s["bc_warm_up"], s["force_soft_weight"] = bcw, warm, -1.0
-                s["noise"] = torch.normal(mean=mean, std=std, generator=st.torch).numpy()
-                s["critic_neg_step"], s["critic_bc2_sqrt"] = sched[k][2]
-                s["actor_neg_step"], s["actor_bc2_sqrt"] = sched[k][3]
-                s["mode"] = 0
-        return K
+            live = fast_rng._py_live(st.py)
+            C.memmove(py_states[r].key, live.state, 624 * 4)
+            py_states[r].pos = live.index
+            jobs[r].py = C.addressof(py_states[r])
+            jobs[r].np = st.np._bit_generator.ctypes.state_address
+            jobs[r].online_len, jobs[r].expert_len = int(self.online_len[r]), int(self.expert_len[r])
+        n_on = np.array([s_[0] for s_ in split], np.int32)
+        n_ex = np.array([s_[1] for s_ in split], np.int32)
+        o = np.empty((R, K, B), np.int32); e = np.empty((R, K, B), np.int32); b = np.empty((R, K, B), np.int32)
+        _lib.check(self._lib.hirl_host_draw_many(jobs, R, K, _lib.ptr(n_on), _lib.ptr(n_ex), self.n_expert, B, _lib.ptr(o), _lib.ptr(e),
+                                                 _lib.ptr(b), min(32, os.cpu_count() or 1)))
+        for r in range(R):
+            fast_rng._py_write(py_states[r], self.streams[r].py)
+        on[:, :K] = o
+        ex[:, :K] = e
+        bc[:, :K] = b
 
     def launch(self, K):
         """hirl_learn over the staged streams: [R][K] everything, host buffers."""

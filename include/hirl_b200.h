@@ -195,6 +195,13 @@ int hirl_host_choice_noreplace(hirl_mt19937_t *st, int32_t population, int32_t s
  * together with `out`, until hirl_host_async_wait() returns.  HIRL_E_UNSUPPORTED if a job is already pending. */
 int hirl_host_choice_noreplace_async(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t *out);
 int hirl_host_async_wait(void);
+/* all index draws of k_calls consecutive learn() calls for n_jobs independent generator pairs (ensemble replicas), on
+ * n_threads worker threads.  Per job and call, in the reference's order: random.sample(range(online_len), n_online[k]),
+ * random.sample(range(expert_len), n_expert[k]) if n_expert[k] > 0 (both on *py), np.random.choice(bc_population, batch,
+ * replace=False) on *np (skipped when idx_bc is NULL).  Outputs are [n_jobs][k_calls][batch] int32 (leading entries used). */
+typedef struct hirl_draw_job { hirl_mt19937_t *py; hirl_mt19937_t *np; int32_t online_len; int32_t expert_len; } hirl_draw_job_t;
+int hirl_host_draw_many(const hirl_draw_job_t *jobs, int32_t n_jobs, int32_t k_calls, const int32_t *n_online, const int32_t *n_expert,
+                        int32_t bc_population, int32_t batch, int32_t *idx_online, int32_t *idx_expert, int32_t *idx_bc, int32_t n_threads);
 
 /* ---- test hooks ------------------------------------------------------------------------ */
 /* stop the next hirl_learn after this many stages of its first step (0 = run everything) */

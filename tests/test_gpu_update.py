@@ -270,8 +270,9 @@ def test_tcc_results_do_not_depend_on_timing(B, en, monkeypatch):
     monkeypatch.setenv("HIRL_CLUSTER", "0")
     sc = scenarios.make_scenario(max(1000, 4 * B), max(600, 3 * B))
     runs = []
-    for seed in ("0", "1", "7", "12345"):
+    for seed, ns in (("0", "4000"), ("1", "4000"), ("7", "4000"), ("12345", "4000"), ("3", "300000")):   # the last: up to 0.3 ms per site
         monkeypatch.setenv("HIRL_TCC_JITTER", seed)
+        monkeypatch.setenv("HIRL_TCC_JITTER_NS", ns)
         ag = scenarios.build_agent(Agent, sc, B, 3)
         assert ag.backend == "tcc"
         scenarios.seed_all(5)

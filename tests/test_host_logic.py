@@ -134,3 +134,51 @@ def test_predraw_is_exact_under_reseeding_foreign_draws_and_wrong_guesses():
     got, py, npd = with_predraw(script)
     assert want == got
     assert py.hits >= 5 and py.misses >= 4 and npd.hits >= 6
+
+
+def test_threaded_ensemble_draws_equal_per_replica_sequential_draws():
+    """hirl_host_draw_many: the whole sweep of index draws of R replicas on worker threads == the reference's draws made
+    replica by replica on private generators (random.Random / np.random.RandomState), for any thread count, and the
+    generators end in the same state."""
+    import ctypes as C
+    import random
+    from hirl4ucav_b200 import _lib
+    from hirl4ucav_b200.utils import fast_rng as fr
+    assert fr.py_fast() and fr.np_fast()
+    lib = _lib.load()
+    R, K, B, n_bc = 9, 5, 64, 3000
+    split = [(48, 16), (64, 0), (40, 24), (48, 16), (63, 1)]
+    lens = [(500 + 37 * r, 100 + r) for r in range(R)]
+    want_on = np.zeros((R, K, B), np.int64); want_ex = np.zeros((R, K, B), np.int64); want_bc = np.zeros((R, K, B), np.int64)
+    tails = []
+    for r in range(R):
+        py, rs = random.Random(100 + r), np.random.RandomState(100 + r)
+        for k, (n_on, n_ex) in enumerate(split):
+            want_on[r, k, :n_on] = py.sample(range(lens[r][0]), n_on)
+            if n_ex:
+                want_ex[r, k, :n_ex] = py.sample(range(lens[r][1]), n_ex)
+            want_bc[r, k] = rs.choice(n_bc, B, replace=False)
+        tails.append((py.random(), rs.rand()))
+    for threads in (1, 4, 32):
+        pys = [random.Random(100 + r) for r in range(R)]
+        rss = [np.random.RandomState(100 + r) for r in range(R)]
+        states = (fr.MTState * R)()
+        jobs = (_lib.DrawJob * R)()
+        for r in range(R):
+            live = fr._py_live(pys[r])
+            C.memmove(states[r].key, live.state, 624 * 4)
+            states[r].pos = live.index
+            jobs[r].py, jobs[r].np = C.addressof(states[r]), rss[r]._bit_generator.ctypes.state_address
+            jobs[r].online_len, jobs[r].expert_len = lens[r]
+        n_on = np.array([s[0] for s in split], np.int32); n_ex = np.array([s[1] for s in split], np.int32)
+        o = np.zeros((R, K, B), np.int32); e = np.zeros((R, K, B), np.int32); b = np.zeros((R, K, B), np.int32)
+        _lib.check(lib.hirl_host_draw_many(jobs, R, K, _lib.ptr(n_on), _lib.ptr(n_ex), n_bc, B, _lib.ptr(o), _lib.ptr(e), _lib.ptr(b), threads))
+        for r in range(R):
+            fr._py_write(states[r], pys[r])
+            for k, (a, c) in enumerate(split):
+                assert np.array_equal(o[r, k, :a], want_on[r, k, :a]) and np.array_equal(e[r, k, :c], want_ex[r, k, :c])
+            assert np.array_equal(b[r], want_bc[r])
+            assert (pys[r].random(), rss[r].rand()) == tails[r], "generator state after the sweep differs"
+    bad = np.array([600] + [0] * (K - 1), np.int32)     # sample larger than the population -> ValueError like random.sample
+    with pytest.raises(ValueError):
+        _lib.check(lib.hirl_host_draw_many(jobs, R, K, _lib.ptr(bad), _lib.ptr(n_ex), n_bc, B, _lib.ptr(o), _lib.ptr(e), _lib.ptr(b), 2))

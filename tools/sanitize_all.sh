@@ -3,8 +3,9 @@
 # One log per (tool, back-end) under gpurun_out/sanitizer/; the summary lines are collected into summary.txt.
 mkdir -p gpurun_out/sanitizer
 out=gpurun_out/sanitizer
-run() {   # name tool env... -- args...
+run() {   # name tool env... -- args...   (ONLY=<substring> restricts the sweep to matching run names)
   local name=$1 tool=$2; shift 2
+  if [ -n "$ONLY" ] && [[ "$name" != *"$ONLY"* ]]; then return; fi
   local envs=()
   while [ "$1" != "--" ]; do envs+=("$1"); shift; done
   shift
