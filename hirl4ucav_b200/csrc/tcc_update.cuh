@@ -131,17 +131,20 @@ __device__ __forceinline__ void pstamp(const Ctl &k, int i) {
 // 0-4 us (HIRL_TCC_JITTER_NS: other bound) at the synchronisation sites.  The kernel's results must be bit-identical with and without it
 // (tests/test_gpu_update.py::test_tcc_results_do_not_depend_on_timing): every cross-CTA hand-over is ordered by a barrier,
 // an mbarrier or a release/acquire flag, never by timing.
-__device__ __forceinline__ void jitter(Ctl &k, bool per_warp = false) {
-    if (k.jit == 0u) return;
-    k.jit_n += 1u;
-    unsigned h = k.jit * 2654435761u ^ (k.jit_n * 40503u) ^ ((unsigned)(k.cid * CL + k.crank) * 2246822519u) ^ (per_warp ? (unsigned)k.warp * 3266489917u : 0u);
+__device__ __noinline__ void jitter_sleep(unsigned seed, unsigned site, unsigned who, unsigned bound_ns) {
+    unsigned h = seed * 2654435761u ^ (site * 40503u) ^ (who * 2246822519u);
     h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
     if ((h & 3u) == 0u) return;
-    for (unsigned left = h % k.jit_ns; left > 0u;) {   // __nanosleep is capped near 1 ms per call
+    for (unsigned left = h % bound_ns; left > 0u;) {   // __nanosleep is capped near 1 ms per call
         const unsigned d = left > 500000u ? 500000u : left;
         __nanosleep(d);
         left -= d;
     }
+}
+__device__ __forceinline__ void jitter(Ctl &k, bool per_warp = false) {
+    if (k.jit == 0u) return;
+    k.jit_n += 1u;
+    jitter_sleep(k.jit, k.jit_n, (unsigned)(k.cid * CL + k.crank) * 8u + (per_warp ? (unsigned)k.warp : 0u), k.jit_ns);
 }
 __device__ __forceinline__ void grid_sync(Ctl &k) {
     jitter(k);

@@ -2,8 +2,9 @@
 
 Each replica is a complete agent of the reference (hirl/agents/HIRL.py:148-190): its own five
 networks, Adam state, replay rings and its own three RNG streams, seeded exactly like a single run
-with ``set_seed(seed)`` (hirl/utils/seed.py:5-10) -- replica i behaves like ``Agent`` constructed
-under that seed.  Only the read-only expert (s, a) table is shared.  On the device the grid is cut
+with ``set_seed(seed)`` (hirl/utils/seed.py:5-10) -- replica i has the weights of an ``Agent`` constructed
+under that seed and, after ``reseed()``, consumes the same three streams (see ``_Streams``).  Only the read-only
+expert (s, a) table is shared.  On the device the grid is cut
 into teams of CTAs; each team runs whole replicas with team-local barriers
 (csrc/hirl_b200.cu: hirl_ensemble_kernel).  No collective: replicas shard over GPUs with
 ``parallel.shard_range``.
@@ -22,8 +23,10 @@ from .agents.HIRL import SOFT_SENTINEL, _adam_scalars
 
 
 class _Streams:
-    """The reference's three host RNG streams for one replica (private generators, same sequences
-    as the global ones after set_seed(seed))."""
+    """The reference's three host RNG streams for one replica: private generators seeded like set_seed(seed).  The py / np
+    streams reproduce a single run's exactly; the torch stream is a FRESH generator, whereas a single agent's global torch
+    generator has already been advanced by the weight initialisation -- call ``AgentEnsemble.reseed()`` (what a run does with
+    set_seed before its update loop, and what the parity tests do) to put all three streams in a single run's state."""
 
     def __init__(self, seed):
         self.py = random.Random(seed)
@@ -66,6 +69,8 @@ class AgentEnsemble(object):
         self.streams = []
         self.online_len = [0] * self.R
         self.expert_len = [0] * self.R
+        self._online_pos = [0] * self.R      # ring write positions (buffer.py:12,31-36: position wraps, len saturates)
+        self._expert_pos = [0] * self.R
         for r, seed in enumerate(self.seeds):
             # initial weights: the reference's construction order under torch.manual_seed(seed)
             with torch.random.fork_rng(devices=[]):
@@ -98,15 +103,20 @@ class AgentEnsemble(object):
 
     # ---- data ---------------------------------------------------------------------------------
     def store_rows(self, replica, rows32, expert=False):
-        """Appends pre-packed 32-word rows to one replica's online / expert ring (no wrap handling
-        beyond the ring itself: rows are written at the current length modulo capacity)."""
+        """Appends pre-packed 32-word rows to one replica's online / expert ring at its write position (buffer.py:31-36:
+        the position wraps around the capacity, the length saturates)."""
         rows32 = _lib.f32c(rows32).reshape(-1, 32)
         cap = self.n_expert + 10 if expert else self.bufferSize
-        lens = self.expert_len if expert else self.online_len
-        first = lens[replica] % cap
-        _lib.check(self._lib.hirl_store_rows(self._h, replica, _lib.BUF_EXPERT if expert else _lib.BUF_ONLINE, first,
-                                             rows32.shape[0], _lib.ptr(rows32)))
-        lens[replica] = min(cap, lens[replica] + rows32.shape[0])
+        lens, pos = (self.expert_len, self._expert_pos) if expert else (self.online_len, self._online_pos)
+        which = _lib.BUF_EXPERT if expert else _lib.BUF_ONLINE
+        rows32 = rows32[-cap:] if rows32.shape[0] > cap else rows32           # only the last `cap` rows survive a longer append
+        n, first = rows32.shape[0], pos[replica]
+        head = min(n, cap - first)
+        _lib.check(self._lib.hirl_store_rows(self._h, replica, which, first, head, _lib.ptr(np.ascontiguousarray(rows32[:head]))))
+        if n > head:                                                           # wrapped: the rest goes to the start of the ring
+            _lib.check(self._lib.hirl_store_rows(self._h, replica, which, 0, n - head, _lib.ptr(np.ascontiguousarray(rows32[head:]))))
+        pos[replica] = (first + n) % cap
+        lens[replica] = min(cap, lens[replica] + n)
 
     def reseed(self, offset=1):
         """set_seed(seed + offset) for every replica's streams (what bench/tests do before the timed loop)."""
