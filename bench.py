@@ -48,15 +48,16 @@ def emit(line: dict) -> None:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures
-# (profiles/r2_ncu_full_tcc_kernel_raw.csv, r1_ncu_full_update_kernel_v10_raw.csv, r1_ncu_full_env_step_kernel_v8_raw.csv),
-# per unit of work so that it scales to the launch this run times:
-# tensor-core cluster kernel (round 2 default at batch <= 256), soft256: 18.58 MB read + 4.37 MB written in a 12-call launch
-#   -> 1.91 MB per call (activations stay on the SMs; what is left are the per-row-block gradient partials and operand images);
-# stage kernel (round 1), soft256: 10.72 MB read + 53.91 MB written in a 12-call launch -> 5.39 MB per call;
-# env kernel: 640.1 MB read + 557.7 MB written for 10 M states -> 119.8 B per state (algorithmic 124 B).
-NCU_TRAFFIC_SOURCE = "profiles/r2_ncu_full_tcc_kernel_raw.csv (tcc) / r1_ncu_full_update_kernel_v10_raw.csv (stage) / r1_ncu_full_env_step_kernel_v8_raw.csv, scaled to this launch"
-NCU_UPDATE_DRAM_BYTES_PER_STEP = {("soft256", "tcc"): (18.580480e6 + 4.370688e6) / 12, ("soft256", "stage"): (10.721024e6 + 53.908480e6) / 12}
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) from committed ncu captures, per unit of work so that it
+# scales to the launch this run times.  Update kernels (profiles/r2_ncu_dram_steady.csv: the same persistent launch with
+# 12 and with 36 calls, so the first touch of the 19 MB working set separates from the steady per-call traffic):
+#   tensor-core cluster kernel (round 2 default at batch <= 256): 21.68 MB @ 12 calls, 26.69 MB @ 36 calls
+#       -> 19.17 MB once per launch + 0.209 MB per call (gradient partials and operand images; activations stay on the SMs);
+#   stage kernel (round 1): 69.32 MB @ 12, 193.67 MB @ 36 -> 7.14 MB once + 5.18 MB per call (scratch draining from L2).
+# env kernel (profiles/r1_ncu_full_env_step_kernel_v8_raw.csv): 640.1 MB read + 557.7 MB written for 10 M states -> 119.8 B per
+# state (algorithmic 124 B).
+NCU_TRAFFIC_SOURCE = "profiles/r2_ncu_dram_steady.csv (update kernels: once-per-launch + per-call bytes) / r1_ncu_full_env_step_kernel_v8_raw.csv, scaled to this launch"
+NCU_UPDATE_DRAM_BYTES = {("soft256", "tcc"): (19.17e6, 0.2088e6), ("soft256", "stage"): (7.14e6, 5.181e6)}   # (per launch, per call)
 NCU_ENV_DRAM_BYTES_PER_STATE = (640.081664e6 + 557.742080e6) / 10_000_000
 
 
@@ -392,7 +393,9 @@ def time_single_agent(name, K, W, local, rank, world, fp32_peak, tf32_peak, peak
                  "stage": "hirl_update_kernel"}.get(backend, backend)
         rec["roofline"] = {"kernel": kname, "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                            "frac": achieved / fp32_peak if fp32_peak else None,
-                           "traffic": NCU_UPDATE_DRAM_BYTES_PER_STEP[(name, backend)] * K if (name, backend) in NCU_UPDATE_DRAM_BYTES_PER_STEP else None,
+                           "traffic": (NCU_UPDATE_DRAM_BYTES[(name, backend)][0] + NCU_UPDATE_DRAM_BYTES[(name, backend)][1] * K)
+                                      if (name, backend) in NCU_UPDATE_DRAM_BYTES else None,
+                           "traffic_per_call_steady": NCU_UPDATE_DRAM_BYTES.get((name, backend), (None, None))[1],
                            "traffic_source": NCU_TRAFFIC_SOURCE,
                            "frac_of_tf32_over_3": achieved / (tf32_peak / 3.0) if tf32_peak else None,
                            "peak_source": "in-run register-resident FFMA loop (hirl_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",

@@ -494,8 +494,13 @@ class Agent(object):
             try:
                 # pipelined: while the GPU runs sub-chunk j the host draws sub-chunk j+1 (launches queue on one stream,
                 # so the device still executes the calls back to back, in order)
-                for lo in range(0, len(chunk), self.FUSE_SUB):
-                    hi = min(len(chunk), lo + self.FUSE_SUB)
+                # The first sub-chunks are short (1, 2, 4 calls): nothing overlaps the very first draw, so it should be brief.
+                bounds, lo, step = [], 0, 1
+                while lo < len(chunk):
+                    hi = min(len(chunk), lo + min(step, self.FUSE_SUB))
+                    bounds.append((lo, hi))
+                    lo, step = hi, step * 2
+                for lo, hi in bounds:
                     # The np.random stream (one cloning batch per call: the longest draw) is advanced by a helper
                     # thread while this thread draws the random / torch streams of the same calls.  The three
                     # generators are independent and each is still consumed in call order; the C draws release the
