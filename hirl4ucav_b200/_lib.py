@@ -75,6 +75,7 @@ SYMBOLS = {
     "hirl_host_sample_indices": (_i, [_vp, _i, _i, _vp]),
     "hirl_host_choice_noreplace": (_i, [_vp, _i, _i, _vp]),
     "hirl_host_choice_noreplace_async": (_i, [_vp, _i, _i, _vp]),
+    "hirl_host_choice_many_async": (_i, [_vp, _i, _i, _i, _vp]),
     "hirl_host_async_wait": (_i, []),
     "hirl_host_draw_many": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
     "hirl_debug_stop_after": (_i, [_vp, _i]),

@@ -505,17 +505,29 @@ class Agent(object):
                     # thread while this thread draws the random / torch streams of the same calls.  The three
                     # generators are independent and each is still consumed in call order; the C draws release the
                     # GIL.  Not with forced streams or the up-sampling switches (those use np.random elsewhere too).
-                    fut = None
+                    fut = pend = None
                     if self._MODE == 0 and not forced and not self.buffer.upsample and not self.expert_upsample:
                         n_bc, B = len(self.expert_states), self.batchSize
-                        fut = _draw_pool().submit(lambda m=hi - lo: [fast_rng.choice_noreplace(n_bc, B) for _ in range(m)])
+                        if fast_rng.np_fast() and 0 < B <= n_bc < (1 << 31):
+                            # all cloning batches of the sub-chunk in ONE library call on the library's worker thread, straight
+                            # on numpy's live MT19937 state (nothing else touches np.random until it is joined below)
+                            self._pre_np._join()
+                            buf = np.empty((hi - lo, B), np.int32)
+                            live = fast_rng._np_live()
+                            if self._lib.hirl_host_choice_many_async(C.byref(live), n_bc, B, hi - lo, _lib.ptr(buf)) == 0:
+                                pend = buf
+                        if pend is None:
+                            fut = _draw_pool().submit(lambda m=hi - lo: [fast_rng.choice_noreplace(n_bc, B) for _ in range(m)])
                     try:
                         for k in range(lo, hi):
                             c = chunk[k]
                             flags.append(self._draw(k, c[0], c[1], c[2] if len(c) > 2 else 0, forced[base + k] if forced else None,
-                                                    defer_bc=fut is not None))
-                    finally:
-                        ready = fut.result() if fut is not None else None    # always joined: np.random must be quiescent afterwards
+                                                    defer_bc=fut is not None or pend is not None))
+                    finally:                                                  # always joined: np.random must be quiescent afterwards
+                        ready = fut.result() if fut is not None else None
+                        if pend is not None:
+                            self._lib.hirl_host_async_wait()
+                            ready = pend
                     if ready is not None:
                         for k in range(lo, hi):
                             self._st_bc[k, :] = ready[k - lo]

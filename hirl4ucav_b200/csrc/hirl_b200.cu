@@ -281,6 +281,9 @@ struct hirl_agent {
     bool use_graph = true;
     cudaGraphExec_t graph_exec = nullptr;
     const void *graph_key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // per-call path: the step record and the three index rows travel as ONE packed H2D copy (library-owned pinned block)
+    char *h_pack = nullptr, *d_pack = nullptr;
+    size_t pack_bytes = 0;
     size_t scratch_elems[32];
     bool coop_ok = true;         // cooperative attribute accepted for cluster launches
     int ncl = 0;                 // cluster kernel: co-resident clusters of 8 CTAs used per launch
@@ -707,6 +710,7 @@ int hirl_agent_destroy(hirl_agent_t *h) {
     if (h->d_act_s) cudaFree(h->d_act_s);
     if (h->d_act_a) cudaFree(h->d_act_a);
     if (h->nccl_comm && h->dp_own_comm && g_nccl.destroy) g_nccl.destroy(h->nccl_comm);
+    if (h->h_pack) cudaFreeHost(h->h_pack);
     for (void *p : h->allocs) cudaFree(p);
     delete h;
     return 0;
@@ -1068,12 +1072,36 @@ int hirl_learn_async(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, con
     };
     const bool graphable = h->use_graph && k_steps == 1 && h->ctxs.size() == 1 && !h->prof_on && h->stop_after == 0 && h->dp_world == 0;
     if (graphable) {
-        const void *key[5] = {steps, idx_online, idx_expert, idx_bc, out_scalars};
-        if (!h->graph_exec && !h->graph_key[0]) {   // built once, for the first set of staging pointers seen
+        // One call = [packed H2D copy, cooperative launch, D2H of 8 scalars], captured once into a CUDA graph.  The caller's four
+        // staging pieces (64 B + 3 x B x 4 B) are gathered by the CPU into a library-owned pinned block first, so the graph
+        // has one copy node instead of four and does not depend on the caller's staging addresses.  The block is reused: the
+        // stream must be idle (it is, for the per-call API: learn() waits for its result); otherwise plain calls.
+        const size_t rowb = B * 4, need = sizeof(hirl_step_t) + 3 * rowb;
+        if (!h->h_pack) {
+            if (cudaHostAlloc((void **)&h->h_pack, need, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); h->h_pack = nullptr; }
+            else if (dev_alloc(h, &h->d_pack, need)) { cudaFreeHost(h->h_pack); h->h_pack = nullptr; }
+            h->pack_bytes = need;
+        }
+        if (!h->h_pack || cudaStreamQuery(h->stream) != cudaSuccess) { cudaGetLastError(); return enqueue(); }
+        std::memcpy(h->h_pack, steps, sizeof(hirl_step_t));
+        std::memcpy(h->h_pack + sizeof(hirl_step_t), idx_online, rowb);
+        if (idx_expert) std::memcpy(h->h_pack + sizeof(hirl_step_t) + rowb, idx_expert, rowb);
+        if (idx_bc) std::memcpy(h->h_pack + sizeof(hirl_step_t) + 2 * rowb, idx_bc, rowb);
+        auto enqueue_packed = [&]() -> int {
+            CU(cudaMemcpyAsync(h->d_pack, h->h_pack, need, cudaMemcpyHostToDevice, h->stream));
+            const char *d = h->d_pack;
+            if (int rc = launch_update(h, 1, (const hirl_step_t *)d, (const int32_t *)(d + sizeof(hirl_step_t)),
+                                       (const int32_t *)(d + sizeof(hirl_step_t) + rowb), (const int32_t *)(d + sizeof(hirl_step_t) + 2 * rowb),
+                                       h->d_out, h->stream)) return rc;
+            CU(cudaMemcpyAsync(out_scalars, h->d_out, HIRL_OUT_SCALARS * 4, cudaMemcpyDeviceToHost, h->stream));
+            return 0;
+        };
+        const void *key[5] = {out_scalars, nullptr, nullptr, nullptr, nullptr};
+        if (!h->graph_exec && !h->graph_key[0]) {   // built once, for the first result buffer seen
             cudaGraph_t g = nullptr;
             bool ok = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
             if (ok) {
-                ok = enqueue() == 0;
+                ok = enqueue_packed() == 0;
                 ok = (cudaStreamEndCapture(h->stream, &g) == cudaSuccess) && ok && g;
             }
             if (ok) ok = cudaGraphInstantiate(&h->graph_exec, g, 0) == cudaSuccess;
@@ -1085,12 +1113,13 @@ int hirl_learn_async(hirl_agent_t *h, int k_steps, const hirl_step_t *steps, con
             }
             std::memcpy(h->graph_key, key, sizeof(key));
         }
-        if (h->graph_exec && std::memcmp(key, h->graph_key, sizeof(key)) != 0) return enqueue();   // other buffers: plain calls
+        if (h->graph_exec && std::memcmp(key, h->graph_key, sizeof(key)) != 0) return enqueue_packed();   // another result buffer: plain calls
         if (h->graph_exec) {
             CU(cudaGraphLaunch(h->graph_exec, h->stream));
             h->last_launches = 1;
             return 0;
         }
+        return enqueue_packed();
     }
     return enqueue();
 }
@@ -1239,7 +1268,7 @@ struct HostWorker {
     std::condition_variable cv;
     bool has_job = false, done = true;
     hirl_mt19937_t *st = nullptr;
-    int32_t n = 0, k = 0;
+    int32_t n = 0, k = 0, count = 1;
     int32_t *out = nullptr;
 };
 HostWorker *g_worker = nullptr;   // leaked on purpose: the detached thread may outlive static destructors
@@ -1248,19 +1277,19 @@ void host_worker_main(HostWorker *w) {
         std::unique_lock<std::mutex> lk(w->m);
         w->cv.wait(lk, [w] { return w->has_job; });
         hirl_mt19937_t *st = w->st;
-        const int32_t n = w->n, k = w->k;
+        const int32_t n = w->n, k = w->k, count = w->count;
         int32_t *out = w->out;
         w->has_job = false;
         lk.unlock();
-        choice_noreplace_impl(st, n, k, out);
+        for (int32_t i = 0; i < count; ++i) choice_noreplace_impl(st, n, k, out + (size_t)i * k);
         lk.lock();
         w->done = true;
         w->cv.notify_all();
     }
 }
 }  // namespace
-int hirl_host_choice_noreplace_async(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t *out) {
-    if (!choice_args_ok(st, population, size, out)) return fail(HIRL_E_INVALID, "bad argument");
+int hirl_host_choice_many_async(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t count, int32_t *out) {
+    if (!choice_args_ok(st, population, size, out) || count < 1) return fail(HIRL_E_INVALID, "bad argument");
     if (!g_worker) {
         g_worker = new HostWorker;
         std::thread(host_worker_main, g_worker).detach();
@@ -1268,10 +1297,13 @@ int hirl_host_choice_noreplace_async(hirl_mt19937_t *st, int32_t population, int
     HostWorker *w = g_worker;
     std::lock_guard<std::mutex> lk(w->m);
     if (!w->done) return fail(HIRL_E_UNSUPPORTED, "a host draw is already pending (one at a time)");
-    w->st = st; w->n = population; w->k = size; w->out = out;
+    w->st = st; w->n = population; w->k = size; w->count = count; w->out = out;
     w->done = false; w->has_job = true;
     w->cv.notify_all();
     return 0;
+}
+int hirl_host_choice_noreplace_async(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t *out) {
+    return hirl_host_choice_many_async(st, population, size, 1, out);
 }
 int hirl_host_async_wait(void) {
     HostWorker *w = g_worker;

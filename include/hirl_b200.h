@@ -194,6 +194,8 @@ int hirl_host_choice_noreplace(hirl_mt19937_t *st, int32_t population, int32_t s
 /* the same draw on a library-owned worker thread (one job at a time): `st` must be a private copy that stays alive,
  * together with `out`, until hirl_host_async_wait() returns.  HIRL_E_UNSUPPORTED if a job is already pending. */
 int hirl_host_choice_noreplace_async(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t *out);
+/* `count` consecutive draws on the same state (the cloning batches of `count` fused learn() calls): out[count][size] */
+int hirl_host_choice_many_async(hirl_mt19937_t *st, int32_t population, int32_t size, int32_t count, int32_t *out);
 int hirl_host_async_wait(void);
 /* all index draws of k_calls consecutive learn() calls for n_jobs independent generator pairs (ensemble replicas), on
  * n_threads worker threads.  Per job and call, in the reference's order: random.sample(range(online_len), n_online[k]),

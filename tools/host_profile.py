@@ -29,3 +29,26 @@ for _ in range(N):
 pr.disable()
 st = pstats.Stats(pr)
 st.sort_stats("tottime").print_stats(18)
+
+# ---- the fused form: learn_many(60) ------------------------------------------------------------------------------------
+chunk = [(100, 64, 0)] * 60
+ag.learn_many(chunk)
+t0 = time.perf_counter()
+for _ in range(20):
+    ag.learn_many(chunk)
+dt = (time.perf_counter() - t0) / (20 * 60) * 1e6
+print(f"learn_many(60): {dt:.1f} us/call")
+for sub in (4, 16, 32):
+    ag.FUSE_SUB = sub
+    ag.learn_many(chunk)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ag.learn_many(chunk)
+    print(f"  FUSE_SUB={sub}: {(time.perf_counter() - t0) / (20 * 60) * 1e6:.1f} us/call")
+ag.FUSE_SUB = 8
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(20):
+    ag.learn_many(chunk)
+pr.disable()
+pstats.Stats(pr).sort_stats("tottime").print_stats(14)
