@@ -327,8 +327,10 @@ def test_target_update_schedule_matches_oracle():
     assert changed_o == changed_c and sum(changed_c) == 2   # fires on calls 5 and 11 (every 3rd actor update)
 
 
-def test_drift_envelope_300_steps():
-    B, steps = 256, 300
+@pytest.mark.parametrize("steps,mark_at", [(300, (30, 100, 300)), (1000, (100, 300, 1000))])
+def test_drift_envelope(steps, mark_at):
+    """Free-running drift against the fp64 twin over 300 and over 1 000 calls (north star: "drift bounded over 1k steps")."""
+    B = 256
     sc = scenarios.make_scenario(4000, 2000)
     orc = scenarios.build_agent(OracleAgent, sc, B, 0)
     o64 = scenarios.build_agent(OracleAgent, sc, B, 0, dtype=torch.float64)
@@ -342,10 +344,10 @@ def test_drift_envelope_300_steps():
         f = {"online": d["online"], "expert": d["expert"], "bc": d["bc"], "noise": d["noise"]}
         o64.learn(0.5, 64, 0, forced=f)
         forced_all.append(f)
-        if t + 1 in (30, 100, 300):
+        if t + 1 in mark_at:
             marks[t + 1] = (orc.flat("critic").copy(), o64.flat("critic").copy(), orc.flat("actor").copy(), o64.flat("actor").copy())
     done = 0
-    for t_mark in (30, 100, 300):
+    for t_mark in mark_at:
         ag.learn_many([(0.5, 64, 0)] * (t_mark - done), forced=forced_all[done:t_mark])
         done = t_mark
         c32, c64, a32, a64 = marks[t_mark]
