@@ -438,12 +438,15 @@ def time_data_parallel(K, W, local, rank, world):
         sync_all(world)
     assert np.isfinite([float(v) for v in out[-1][:4]]).all()
     sec = median_over_repeats(times, torch.device("cuda", local), world)
+    variant = getattr(ag, "dp_variant", None)
     rec = {"workload": "dp4096: ONE HIRL agent (fixed BC weight), global batch 4096 cut into %d shard(s) of %d rows, gradients all-reduced over NVLink" % (world, wl["batch"] // world),
            "value": K / sec, "unit": "updates/s", "ms_per_step": sec / K * 1e3, "steps": K, "scaling": "strong", "global_batch": wl["batch"],
-           "rows_per_gpu": wl["batch"] // world, "backend": ag.backend,
-           "collectives_per_call": "critic-only call: 1 grouped NCCL all-reduce (276 482 fp32 gradient + loss); actor call: + filter count + 1 grouped all-reduce (138 756 fp32 + 4 scalars)",
-           "launches_per_call": "2 (critic-only) / 5 (actor call) stage-range launches of hirl_update_kernel",
-           "timing": "end to end through Agent.learn_many (host draws + sharding + H2D + launches + NCCL + D2H), median of 5, max over ranks"}
+           "rows_per_gpu": wl["batch"] // world, "backend": ag.backend, "variant": variant,
+           "collectives_per_call": "critic-only call: all-reduce of 276 482 fp32 gradient + loss; actor call: + filter count + all-reduce of 138 756 fp32 + 4 scalars",
+           "how": ("fused: the all-reduces run INSIDE the update kernel (every rank sums the ranks' exchange blocks in rank order with P2P loads over NVLink "
+                   "peer memory, CUDA IPC); a call is one launch" if variant == "fused" else
+                   "nccl: 2 (critic-only) / 5 (actor call) stage-range launches of hirl_update_kernel with ncclAllReduce between them"),
+           "timing": "end to end through Agent.learn_many (host draws + sharding + H2D + launches + all-reduces + D2H), median of 5, max over ranks"}
     del ag
     return rec
 

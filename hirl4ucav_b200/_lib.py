@@ -52,6 +52,8 @@ SYMBOLS = {
     "hirl_agent_sm_count": (_i, [_vp]),
     "hirl_agent_backend": (_i, [_vp]),
     "hirl_nccl_unique_id": (_i, [_vp]),
+    "hirl_dp_fused_export": (_i, [_vp, _i, _i, _i, _vp]),
+    "hirl_dp_fused_attach": (_i, [_vp, _vp, _i]),
     "hirl_allreduce_init": (_i, [_vp, _vp, _i, _i, _i]),
     "hirl_allreduce_attach": (_i, [_vp, _vp, _i, _i, _i]),
     "hirl_params_import": (_i, [_vp, _i, _i, _vp, _sz]),

@@ -160,7 +160,32 @@ class Agent(object):
             self._attach_data_parallel()
 
     def _attach_data_parallel(self):
+        """Fused variant first (all-reduce inside the kernel over IPC-mapped NVLink peer memory: a call stays one launch);
+        the NCCL variant (stage-range launches + ncclAllReduce) if CUDA IPC is unavailable or HIRL_DP_NCCL=1."""
         rank, world = self._dp
+        self.dp_variant = None
+        if os.environ.get("HIRL_DP_NCCL") != "1":
+            h64 = np.zeros(64, np.uint8)
+            rc = self._lib.hirl_dp_fused_export(self._h, rank, world, self.batchSize, _lib.ptr(h64))
+            ok = rc == 0
+            handles = h64
+            if world > 1:
+                import torch.distributed as dist
+                box = [None] * world
+                dist.all_gather_object(box, (ok, h64.tobytes()))
+                ok = all(b[0] for b in box)
+                handles = np.frombuffer(b"".join(b[1] for b in box), np.uint8).copy()
+            if ok:
+                ok = self._lib.hirl_dp_fused_attach(self._h, _lib.ptr(handles), world) == 0
+                if world > 1:
+                    box = [None] * world
+                    dist.all_gather_object(box, ok)
+                    ok = all(box)
+            if ok:
+                self.dp_variant = "fused"
+                return
+            raise _lib.HirlError("fused data-parallel attach failed on some rank (" + self._lib.hirl_last_error().decode(errors="replace")
+                                 + "); set HIRL_DP_NCCL=1 for the NCCL variant")
         uid = np.zeros(128, np.uint8)
         if rank == 0:
             _lib.check(self._lib.hirl_nccl_unique_id(_lib.ptr(uid)))
@@ -170,6 +195,7 @@ class Agent(object):
             dist.broadcast_object_list(box, src=0)
             uid = np.frombuffer(box[0], np.uint8).copy()
         _lib.check(self._lib.hirl_allreduce_init(self._h, _lib.ptr(uid), rank, world, self.batchSize))
+        self.dp_variant = "nccl"
 
     @property
     def backend(self):

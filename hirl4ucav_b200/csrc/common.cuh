@@ -163,7 +163,12 @@ struct AgentCtx {
     float *carry;          // [8] scalars carried between calls (stale-value semantics, HIRL.py:334)
     int B;
     int Bg;                // batch the loss means run over: B, or the global batch in the data-parallel mode (this agent holds B of its rows)
-    float *dp_count;       // data-parallel mode: soft-count word, written by the launch that ends with stage G6, all-reduced, read by stage R6 (else null)
+    float *dp_count;       // data-parallel mode, NCCL variant: soft-count word, written by the launch that ends with stage G6, all-reduced, read by stage R6 (else null)
+    // data-parallel mode, FUSED variant (in-kernel all-reduce over NVLink peer memory, update.cuh: dp_*): every rank's exchange
+    // block (layout DPX_*), own block included, mapped into this process with CUDA IPC; 0 ranks = off
+    int dp_world, dp_rank;
+    unsigned *dp_gen_ctr;  // calls executed so far by this agent (device word; the flag generations of a launch start here)
+    char *dp_peer[8];
     int zsplit;            // allocated split-K slots per Z2 / DH1 buffer (max of ns[])
     int ns[NS_COUNT];      // split-K factor per GEMM group
     int activation;
@@ -177,6 +182,16 @@ struct AgentCtx {
     int cluster_ri, Bpad;  // Bpad = row blocks * rows per block
     float gamma, tau, noise_clamp, loss_lambda;
 };
+
+// Exchange block of the fused data-parallel mode (floats from the block base).  Gradients and scalars are double-buffered by
+// call parity: a rank overwrites a buffer only two all-reduces after its peers read it, and nobody can be two all-reduces
+// ahead of anybody (every all-reduce waits for every rank).  Flags are generations (call numbers), never reset.
+constexpr size_t DPX_GC = 0;                                     // [2][CRITIC_SIZE] this rank's critic gradient of its shard
+constexpr size_t DPX_GA = DPX_GC + 2 * (size_t)CRITIC_SIZE;      // [2][ACTOR_SIZE]
+constexpr size_t DPX_SC = DPX_GA + 2 * (size_t)ACTOR_SIZE;       // [2][32]: 0 critic loss, 1..4 actor scalars (carry[1..4]), 5 soft count
+constexpr size_t DPX_FLAGS = DPX_SC + 64;                        // unsigned [3][32]: critic gradient / count / actor gradient ready
+constexpr size_t DPX_FLOATS = DPX_FLAGS + 3 * 32;
+enum { DPF_CRITIC = 0, DPF_COUNT = 1, DPF_ACTOR = 2 };
 
 struct LaunchCtx {
     AgentCtx agent;        // single-agent launch: the context travels as a kernel parameter

@@ -51,8 +51,12 @@ __global__ void __launch_bounds__(THREADS, 1) hirl_update_kernel(const __grid_co
     tm.tmem_base = any_tc ? tmem_slot : 0u;
     tm.tc_smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
     tm.tc_bars = &tc_bars;
+    // fused data-parallel mode: the generations of this launch's exchange flags continue from the calls executed so far
+    const unsigned dp_base = ctx.dp_world > 0 ? ld_relaxed_u32(ctx.dp_gen_ctr) : 0u;
     for (int step = 0; step < L.k_steps; ++step)
-        if (learn_step(ctx, L.step0 + step, tm, smem, step == 0 ? L.stop_after : 0, L.prof, L.first_stage, L.last_stage, L.adam_phase)) break;
+        if (learn_step(ctx, L.step0 + step, tm, smem, step == 0 ? L.stop_after : 0, L.prof, L.first_stage, L.last_stage, L.adam_phase, dp_base)) break;
+    // (every CTA read the counter before the first grid barrier of the launch; CTA 0 leaves after the last one)
+    if (ctx.dp_world > 0 && blockIdx.x == 0 && threadIdx.x == 0) *ctx.dp_gen_ctr = dp_base + (unsigned)L.k_steps;
     if (any_tc) {
         __syncthreads();
         if (threadIdx.x < 32) tc::tmem_dealloc(tm.tmem_base);
@@ -294,6 +298,10 @@ struct hirl_agent {
     int dp_world = 0, dp_rank = 0;
     float *d_dp_count = nullptr;
     std::vector<int> dp_do_actor, dp_mode;   // host copy of the step records' control words of the launch being enqueued
+    // fused variant: in-kernel all-reduce over IPC-mapped peer memory
+    bool dp_fused = false;
+    float *d_dp_xchg = nullptr;
+    std::vector<void *> dp_opened;           // peer mappings to close
 };
 
 template <class T>
@@ -495,6 +503,8 @@ int hirl_agent_create(const hirl_config_t *cfg, hirl_agent_t **out) {
     proto.B = cfg->batch;
     proto.Bg = cfg->batch;
     proto.dp_count = nullptr;
+    proto.dp_world = 0; proto.dp_rank = 0; proto.dp_gen_ctr = nullptr;
+    for (int r = 0; r < 8; ++r) proto.dp_peer[r] = nullptr;
     proto.activation = cfg->activation;
     proto.gamma = cfg->gamma; proto.tau = cfg->tau; proto.noise_clamp = cfg->noise_clamp; proto.loss_lambda = cfg->loss_lambda;
     // split-K factors (unit = one 64x64 output tile over the layer's full K)
@@ -711,6 +721,7 @@ int hirl_agent_destroy(hirl_agent_t *h) {
     if (h->d_act_a) cudaFree(h->d_act_a);
     if (h->nccl_comm && h->dp_own_comm && g_nccl.destroy) g_nccl.destroy(h->nccl_comm);
     if (h->h_pack) cudaFreeHost(h->h_pack);
+    for (void *p : h->dp_opened) cudaIpcCloseMemHandle(p);
     for (void *p : h->allocs) cudaFree(p);
     delete h;
     return 0;
@@ -739,6 +750,55 @@ static int dp_enable(hirl_agent *h, void *comm, bool own, int rank, int world, i
     c.dp_count = h->d_dp_count;
     h->nccl_comm = comm; h->dp_own_comm = own; h->dp_rank = rank; h->dp_world = world;
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    return 0;
+}
+
+// ---- data-parallel mode, fused variant: all-reduce inside the update kernel over NVLink peer memory -------------------------
+// hirl_dp_fused_export allocates this rank's exchange block (common.cuh: DPX_*) and returns its CUDA IPC handle; the caller
+// gathers the handles of all ranks by any side channel and hirl_dp_fused_attach maps them.  From then on a call is ONE launch
+// (several calls per launch work too): every rank writes its shard's gradient into its block, raises a generation flag and
+// sums all ranks' blocks in rank order with P2P loads -- bit-identical on every rank, no NCCL call, no extra launch.
+int hirl_dp_fused_export(hirl_agent_t *h, int rank, int world, int global_batch, void *handle64) {
+    if (!h || !handle64) return fail(HIRL_E_INVALID, "null argument");
+    if (h->ctxs.size() != 1) return fail(HIRL_E_UNSUPPORTED, "data-parallel mode is for a single agent per handle");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return fail(HIRL_E_INVALID, "bad rank / world (1..8 ranks)");
+    if (global_batch != h->cfg.batch * world) return fail(HIRL_E_INVALID, "global_batch must be world * cfg.batch (equal shards)");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (!h->d_dp_xchg) {
+        if (int rc = dev_alloc(h, &h->d_dp_xchg, DPX_FLOATS)) return rc;
+    }
+    AgentCtx &c = h->ctxs[0];
+    if (!c.dp_gen_ctr) { if (int rc = dev_alloc(h, &c.dp_gen_ctr, 1)) return rc; }
+    cudaIpcMemHandle_t ih;
+    CU(cudaIpcGetMemHandle(&ih, h->d_dp_xchg));
+    static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle64, &ih, 64);
+    c.use_tcc = 0; c.use_cluster = 0;          // the stage kernel carries the mode (see dp_enable)
+    c.Bg = global_batch;
+    c.dp_rank = rank;
+    c.dp_world = 0;                            // enabled by hirl_dp_fused_attach
+    h->dp_rank = rank;
+    return 0;
+}
+int hirl_dp_fused_attach(hirl_agent_t *h, const void *handles, int world) {
+    if (!h || !handles) return fail(HIRL_E_INVALID, "null argument");
+    if (!h->d_dp_xchg) return fail(HIRL_E_INVALID, "call hirl_dp_fused_export first");
+    if (world < 1 || world > 8) return fail(HIRL_E_INVALID, "bad world");
+    CU(cudaSetDevice(h->cfg.device));
+    AgentCtx &c = h->ctxs[0];
+    for (int r = 0; r < world; ++r) {
+        if (r == c.dp_rank) { c.dp_peer[r] = reinterpret_cast<char *>(h->d_dp_xchg); continue; }
+        cudaIpcMemHandle_t ih;
+        std::memcpy(&ih, static_cast<const char *>(handles) + (size_t)r * 64, 64);
+        void *p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+        h->dp_opened.push_back(p);
+        c.dp_peer[r] = static_cast<char *>(p);
+    }
+    c.dp_world = world;
+    h->dp_fused = true;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; h->graph_key[0] = nullptr; }
     return 0;
 }
 int hirl_nccl_unique_id(void *id128) {
@@ -977,6 +1037,7 @@ static int launch_update(hirl_agent *h, int k_steps, const hirl_step_t *steps_de
         L.prof = h->prof_on ? h->d_prof : nullptr;
         L.step0 = 0; L.first_stage = 1; L.last_stage = ST_END; L.adam_phase = 0;
         if (h->dp_world > 0) return launch_update_dp(h, L, k_steps, stream);
+        if (h->dp_fused) L.adam_phase = 4;      // whole calls in one launch, all-reduces inside the kernel
         void *args[] = {&L};
         CU(cudaLaunchCooperativeKernel((void *)hirl_update_kernel, dim3(h->grid), dim3(THREADS), args, SMEM_BYTES, stream));
     } else {
@@ -1005,6 +1066,7 @@ static int check_steps(hirl_agent *h, int k_steps, const hirl_step_t *steps) {
         if (s.mode != 2 && (s.n_online < 0 || s.n_expert < 0 || s.n_online + s.n_expert != h->cfg.batch))
             return fail(HIRL_E_INVALID, "n_online + n_expert must equal the batch size");
         if (s.mode < 0 || s.mode > 2) return fail(HIRL_E_INVALID, "bad step mode");
+        if (s.mode != 0 && h->dp_fused) return fail(HIRL_E_UNSUPPORTED, "data-parallel mode implements the HIRL step (mode 0)");
         if (s.mode != 0 && h->ctxs[0].use_tcc) return fail(HIRL_E_INVALID, "TD3 / BC step modes run on the stage kernel (create the agent with HIRL_TCC=0)");
         if (s.mode != 1 && s.do_actor && h->cfg.bc_rows < h->cfg.batch) return fail(HIRL_E_INVALID, "expert table smaller than the batch (np.random.choice without replacement)");
     }

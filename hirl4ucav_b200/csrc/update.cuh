@@ -580,6 +580,40 @@ __device__ __forceinline__ float lp_sum(const AgentCtx &c, const Team &tm, int w
     return warp_sum(s);
 }
 
+// ---- fused data-parallel mode: all-reduce over NVLink peer memory inside the kernel ---------------------------------------
+// Every rank writes its contribution into ITS exchange block, raises a generation flag (release at system scope) and then
+// reads every rank's contribution straight out of the peers' memory (P2P loads over NVLink, L1 bypassed) and adds them in
+// rank order -- all ranks compute bit-identical sums, so their weights never diverge.  No NCCL call, no extra launch.
+__device__ __forceinline__ float *dpx(const AgentCtx &c, int r) { return reinterpret_cast<float *>(c.dp_peer[r]); }
+__device__ __forceinline__ void dp_signal(const AgentCtx &c, int which, unsigned gen) {   // ONE thread, after the barrier that completes the data
+    __threadfence_system();
+    unsigned *f = reinterpret_cast<unsigned *>(dpx(c, c.dp_rank) + DPX_FLAGS) + which * 32;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(gen) : "memory");
+}
+__device__ __forceinline__ void dp_wait(const AgentCtx &c, int which, unsigned gen) {     // one full warp: lane r watches rank r
+    const int lane = threadIdx.x & 31;
+    if (lane < c.dp_world) {
+        const unsigned *f = reinterpret_cast<const unsigned *>(dpx(c, lane) + DPX_FLAGS) + which * 32;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int)(v - gen) >= 0) break;
+            if (clock64() - t0 > 40000000000LL) {
+                printf("hirl data-parallel: rank %d waited ~20 s for rank %d (flag %d, call %u)\n", c.dp_rank, lane, which, gen);
+                __trap();
+            }
+        }
+    }
+    __syncwarp();
+}
+// sum over ranks of word `off` of the exchange blocks, rank order (one thread)
+__device__ __forceinline__ float dp_sum_word(const AgentCtx &c, size_t off) {
+    float s = 0.f;
+    for (int r = 0; r < c.dp_world; ++r) s += __ldcv(dpx(c, r) + off);
+    return s;
+}
+
 // eight consecutive batch entries of one column of a [TILE_ROWS][ld] shared tile -> 32 contiguous bytes of a
 // transposed global buffer (full sectors instead of eight scattered 4-byte writes)
 __device__ __forceinline__ void store_col8(float *dst, const float *tile_col, int ld) {
@@ -1006,15 +1040,22 @@ __device__ __forceinline__ float polyak_elem(float t, float p, float tau, float 
 template <class L>
 __device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w, float *gw, const float *w2parts, int nparts, float *m, float *v, const float *part,
                                            int part_towers, int nslots, float neg_step, float bc2_sqrt, float *target, bool polyak,
-                                           float tau, float one_minus_tau, float *w2t, int phase = 0) {
+                                           float tau, float one_minus_tau, float *w2t, int phase = 0,
+                                           const AgentCtx *dpc = nullptr, size_t dp_off = 0, float *gw_out = nullptr, const float *gw_in = nullptr) {
+    // gw_in: where a GEMM stage wrote dW2 directly (nparts == 0) when that is not gw itself (fused data-parallel: gw is the exchange buffer)
     // phase (data-parallel mode): 0 whole stage; 1 only the fixed-order sums of the partials -> gw (the gradient of this
-    // shard, all-reduced between the two launches); 2 only Adam (+ Polyak) from gw
+    // shard, all-reduced between the two launches); 2 only Adam (+ Polyak) from gw; 3 (fused variant) Adam from the sum over the
+    // ranks' exchange blocks at float offset dp_off, read over NVLink in rank order; the summed gradient is kept in gw_out
     const int total = ntowers * L::SIZE;
     for (int e = tm.rank * THREADS + threadIdx.x; e < total; e += tm.size * THREADS) {
         const int tower = e / L::SIZE, off = e - tower * L::SIZE;
         float g;
         const bool in_w2 = off >= L::W2 && off < L::B2;
-        if (phase == 2) {
+        if (phase == 3) {
+            g = 0.f;
+            for (int r = 0; r < dpc->dp_world; ++r) g += __ldcv(dpx(*dpc, r) + dp_off + e);
+            gw_out[e] = g;
+        } else if (phase == 2) {
             g = __ldcg(gw + e);
         } else if (in_w2) {
             if (nparts > 0) {   // fixed-order sum of the split-K / per-branch partial buffers
@@ -1023,7 +1064,8 @@ __device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w
                 for (int q = 1; q < nparts; ++q) g += __ldcg(p0 + (size_t)q * H2 * H1);
                 gw[e] = g;
             } else {
-                g = __ldcg(gw + e);
+                g = __ldcg((gw_in ? gw_in : gw) + e);
+                if (gw_in) gw[e] = g;
             }
         } else {
             const int si = L::small_index(off);
@@ -1058,17 +1100,35 @@ __device__ __forceinline__ Team arena_team(const Team &tm) {
     return t;
 }
 
-__device__ __noinline__ void stage_g4(const AgentCtx &c, const hirl_step_t &st, const Team &tm, int phase) {
+__device__ __noinline__ void stage_g4(const AgentCtx &c, const hirl_step_t &st, Team &tm, int phase, unsigned gen) {
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
     const int P = gsize < nchunks ? gsize : nchunks;
     const Team at = arena_team(tm);
+    const bool fused = phase == 4;      // fused data-parallel variant: shard sums -> exchange block -> in-kernel all-reduce -> Adam
+    const size_t par = gen & 1u;
+    float *gsum = fused ? dpx(c, c.dp_rank) + DPX_GC + par * CRITIC_SIZE : c.g_critic;
     if (tm.rank < at.size)
-        adam_arena<CriticL>(at, 2, c.critic, c.g_critic, c.sc.GW2P, c.dw_split > 1 ? c.dw_split : 0, c.m_critic, c.v_critic, c.sc.PART_C, 2, P,
-                            st.critic_neg_step, st.critic_bc2_sqrt, nullptr, false, 0.f, 0.f, c.use_tc ? c.w2t_critic : nullptr, phase);
+        adam_arena<CriticL>(at, 2, c.critic, gsum, c.sc.GW2P, c.dw_split > 1 ? c.dw_split : 0, c.m_critic, c.v_critic, c.sc.PART_C, 2, P,
+                            st.critic_neg_step, st.critic_bc2_sqrt, nullptr, false, 0.f, 0.f, c.use_tc ? c.w2t_critic : nullptr, fused ? 1 : phase,
+                            nullptr, 0, nullptr, fused ? c.g_critic : nullptr);
     if (phase != 2 && tm.rank == tm.size - 1 && threadIdx.x < 32) {
         // critic_loss = mse(Q1,y) + mse(Q2,y): even ranks hold tower 0, odd ranks tower 1
         const float s0 = lp_sum(c, tm, 0, 0), s1 = lp_sum(c, tm, 0, 1);
-        if (threadIdx.x == 0) c.carry[0] = __fadd_rn(s0 / (float)c.Bg, s1 / (float)c.Bg);
+        if (threadIdx.x == 0) {
+            const float loss = __fadd_rn(s0 / (float)c.Bg, s1 / (float)c.Bg);
+            if (fused) dpx(c, c.dp_rank)[DPX_SC + par * 32 + 0] = loss;
+            else c.carry[0] = loss;
+        }
+    }
+    if (fused) {
+        team_sync(tm);                                                 // this rank's gradient and loss are complete
+        if (tm.rank == 0 && threadIdx.x == 0) dp_signal(c, DPF_CRITIC, gen);
+        if (threadIdx.x < 32) dp_wait(c, DPF_CRITIC, gen);
+        __syncthreads();
+        if (tm.rank < at.size)
+            adam_arena<CriticL>(at, 2, c.critic, gsum, c.sc.GW2P, 0, c.m_critic, c.v_critic, c.sc.PART_C, 2, P, st.critic_neg_step, st.critic_bc2_sqrt,
+                                nullptr, false, 0.f, 0.f, c.use_tc ? c.w2t_critic : nullptr, 3, &c, DPX_GC + par * CRITIC_SIZE, c.g_critic);
+        if (tm.rank == tm.size - 1 && threadIdx.x == 0) c.carry[0] = dp_sum_word(c, DPX_SC + par * 32 + 0);
     }
 }
 
@@ -1159,14 +1219,22 @@ __device__ __noinline__ void stage_g6(const AgentCtx &c, const Team &tm, float *
 // the behaviour-cloning weight of this call (HIRL.py:292-308), evaluated identically by every CTA
 // (call with a full warp: the soft count is a warp-collective sum)
 struct BcWeight { float w, one_minus_w, count; };
-__device__ __forceinline__ BcWeight bc_weight_of(const AgentCtx &c, const hirl_step_t &st, const Team &tm) {
+__device__ __forceinline__ BcWeight bc_weight_of(const AgentCtx &c, const hirl_step_t &st, const Team &tm, unsigned gen = 0u) {
     BcWeight r;
     r.count = 0.f;
     double w = (double)st.bc_weight_now;
     if (st.mode == 2) w = 1.0;       // BC: the loss IS the cloning term
     else if (st.mode != 0) w = 0.0;
     else if (st.bc_weight_now == 100.f) {
-        r.count = c.dp_count ? __ldcg(c.dp_count) : lp_sum(c, tm, 1);   // data-parallel: the all-reduced count of every shard
+        if (c.dp_world > 0) {   // fused data-parallel: every rank published its shard's count before stage G6 (learn_step); sum in rank order
+            dp_wait(c, DPF_COUNT, gen);
+            const int lane = threadIdx.x & 31;
+            const float mine = lane < c.dp_world ? __ldcv(dpx(c, lane) + DPX_SC + (gen & 1u) * 32 + 5) : 0.f;
+            float cnt = 0.f;
+            for (int q = 0; q < c.dp_world; ++q) cnt += __shfl_sync(0xffffffffu, mine, q);
+            r.count = cnt;
+        } else
+        r.count = c.dp_count ? __ldcg(c.dp_count) : lp_sum(c, tm, 1);   // NCCL data-parallel: the all-reduced count of every shard
         const float mean = st.force_soft_weight >= 0.f ? st.force_soft_weight : r.count / (float)c.Bg;  // .float().mean()
         w = (double)mean + (double)st.bc_warm_up;
     }
@@ -1178,14 +1246,14 @@ __device__ __forceinline__ BcWeight bc_weight_of(const AgentCtx &c, const hirl_s
 
 // R6: group 0: d pi from the critic, actor head backward on batch states (rl branch);
 //     group 1: BC loss (HIRL.py:310-311) and actor head backward on expert states.
-__device__ __noinline__ void stage_r6(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem) {
+__device__ __noinline__ void stage_r6(const AgentCtx &c, const hirl_step_t &st, const Team &tm, float *smem, unsigned gen) {
     const int B = c.B, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunks = (B + TILE_ROWS - 1) / TILE_ROWS;
     const float slope = slope_of(c);
     const int gsize = tm.size >> 1, branch = tm.rank & 1, grank = tm.rank >> 1;
     RowSmem sm = row_smem(smem);
     if (tid < 32) {
-        const BcWeight b0 = bc_weight_of(c, st, tm);   // warp-collective
+        const BcWeight b0 = bc_weight_of(c, st, tm, gen);   // warp-collective
         if (tid == 0) { sm.red[32] = b0.w; sm.red[33] = b0.one_minus_w; }
     }
     __syncthreads();
@@ -1314,9 +1382,9 @@ __device__ __noinline__ void stage_r7(const AgentCtx &c, const hirl_step_t &st, 
 #define HIRL_G8_NOINLINE 0   // 1: build stage_g8 as a separate function again (tools/sanitize_all.sh re-tests the round-1 fault)
 #endif
 #if HIRL_G8_NOINLINE
-__device__ __noinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm, int phase) {
+__device__ __noinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, Team &tm, int phase, unsigned gen) {
 #else
-__device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, const Team &tm, int phase) {
+__device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &st, Team &tm, int phase, unsigned gen) {
 #endif
     const int nchunks = (c.B + TILE_ROWS - 1) / TILE_ROWS, gsize = tm.size >> 1;
     const int P = gsize < nchunks ? gsize : nchunks;
@@ -1327,12 +1395,15 @@ __device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &s
     const float *part_a = c.sc.PART_A + part_off;
     const float *w2parts = c.sc.GW2P + w2_off;
     const Team at = arena_team(tm);
+    const bool fused = phase == 4;      // fused data-parallel variant (see stage_g4)
+    const size_t par = gen & 1u;
+    float *gsum = fused ? dpx(c, c.dp_rank) + DPX_GA + par * ACTOR_SIZE : c.g_actor;
     if (tm.rank < at.size)
-        adam_arena<ActorL>(at, 1, c.actor, c.g_actor, w2parts, (st.mode == 0 ? 2 : 1) * c.dw_split, c.m_actor, c.v_actor, part_a, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
-                       c.tactor, st.do_polyak != 0, tau, omt, c.use_tc ? c.w2t_actor : nullptr, phase);
-    if (phase != 1 && st.do_polyak && tm.rank < at.size) polyak_arena<CriticL>(at, 2, c.critic, c.tcritic, tau, omt);
+        adam_arena<ActorL>(at, 1, c.actor, gsum, w2parts, (st.mode == 0 ? 2 : 1) * c.dw_split, c.m_actor, c.v_actor, part_a, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
+                       c.tactor, st.do_polyak != 0, tau, omt, c.use_tc ? c.w2t_actor : nullptr, fused ? 1 : phase, nullptr, 0, nullptr, fused ? c.g_actor : nullptr);
+    if (!fused && phase != 1 && st.do_polyak && tm.rank < at.size) polyak_arena<CriticL>(at, 2, c.critic, c.tcritic, tau, omt);
     if (phase != 2 && tm.rank == tm.size - 1 && threadIdx.x < 32) {
-        const BcWeight bw = bc_weight_of(c, st, tm);
+        const BcWeight bw = bc_weight_of(c, st, tm, gen);
         const float rl_loss = st.mode == 2 ? 0.f : -(lp_sum(c, tm, 2) / (float)c.Bg);     // HIRL.py:297
         float bc_loss = 0.f, fire = 0.f;
         if (st.mode == 0) {
@@ -1342,12 +1413,29 @@ __device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &s
             bc_loss = lp_sum(c, tm, 3) / (float)(A * c.Bg);                                // BC.py:179
         }
         if (threadIdx.x == 0) {
-        c.carry[1] = __fadd_rn(__fmul_rn(bc_loss, bw.w), __fmul_rn(rl_loss, bw.one_minus_w));  // HIRL.py:321
-        c.carry[2] = bc_loss;
-        c.carry[3] = rl_loss;
-        c.carry[4] = fire;
-        c.carry[5] = bw.w;
-        c.carry[6] = bw.count;
+            // (fused data-parallel: these are this shard's parts of the global means; they are summed over the ranks below)
+            float *dst = fused ? dpx(c, c.dp_rank) + DPX_SC + par * 32 : c.carry;
+            dst[1] = __fadd_rn(__fmul_rn(bc_loss, bw.w), __fmul_rn(rl_loss, bw.one_minus_w));  // HIRL.py:321
+            dst[2] = bc_loss;
+            dst[3] = rl_loss;
+            dst[4] = fire;
+            c.carry[5] = bw.w;
+            c.carry[6] = bw.count;
+        }
+    }
+    if (fused) {
+        team_sync(tm);                                                 // this rank's gradient and scalars are complete
+        if (tm.rank == 0 && threadIdx.x == 0) dp_signal(c, DPF_ACTOR, gen);
+        if (threadIdx.x < 32) dp_wait(c, DPF_ACTOR, gen);
+        __syncthreads();
+        if (tm.rank < at.size) {
+            adam_arena<ActorL>(at, 1, c.actor, gsum, w2parts, 0, c.m_actor, c.v_actor, part_a, 1, nslots, st.actor_neg_step, st.actor_bc2_sqrt,
+                               c.tactor, st.do_polyak != 0, tau, omt, c.use_tc ? c.w2t_actor : nullptr, 3, &c, DPX_GA + par * ACTOR_SIZE, c.g_actor);
+            if (st.do_polyak) polyak_arena<CriticL>(at, 2, c.critic, c.tcritic, tau, omt);
+        }
+        if (tm.rank == tm.size - 1 && threadIdx.x == 0) {
+#pragma unroll
+            for (int j = 1; j <= 4; ++j) c.carry[j] = dp_sum_word(c, DPX_SC + par * 32 + j);
         }
     }
 }
@@ -1357,7 +1445,9 @@ __device__ __forceinline__ void stage_g8(const AgentCtx &c, const hirl_step_t &s
 // ranges [first, last] with the gradient all-reduces between them; every stage keeps its state in global memory, so a
 // range simply resumes where the previous launch stopped.  Defaults: whole call (first = 1, last = ST_END, phase 0).
 __device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm, float *smem, int stop_after, long long *prof,
-                                           int first = 1, int last = ST_END, int adam_phase = 0) {
+                                           int first = 1, int last = ST_END, int adam_phase = 0, unsigned dp_base = 0u) {
+    // adam_phase 4: fused data-parallel variant (in-kernel all-reduce over NVLink peer memory); gen: this call's number
+    const unsigned gen = dp_base + (unsigned)step + 1u;
     __shared__ hirl_step_t st;
     if (threadIdx.x < (int)(sizeof(hirl_step_t) / sizeof(int)))
         reinterpret_cast<int *>(&st)[threadIdx.x] = reinterpret_cast<const int *>(c.steps + step)[threadIdx.x];
@@ -1401,19 +1491,28 @@ __device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm
         HIRL_STAGE(ST_R2, stage_r2(c, st, tm, smem))
         HIRL_STAGE(ST_G3, stage_g3(c, tm, smem))
         HIRL_STAGE(ST_R3, stage_r3(c, tm, smem))
-        HIRL_STAGE(ST_G4, stage_g4(c, st, tm, adam_phase))
+        HIRL_STAGE(ST_G4, stage_g4(c, st, tm, adam_phase, gen))
     }
     if (bc_only || do_actor) {
         if (!bc_only) {
             HIRL_STAGE(ST_R4, stage_r4(c, st, tm))
             HIRL_STAGE(ST_G5, stage_g5(c, st, tm, smem))
             HIRL_STAGE(ST_R5, stage_r5(c, st, tm, smem))
+            if (adam_phase == 4 && tm.rank == tm.size - 1 && threadIdx.x < 32) {
+                // fused data-parallel: this shard's count of soft_Q > rl_Q (complete since stage R5's barrier) goes out now;
+                // the peers' counts travel over NVLink while stage G6 computes and are summed at the top of stage R6
+                const float cnt_ = lp_sum(c, tm, 1);
+                if (threadIdx.x == 0) {
+                    dpx(c, c.dp_rank)[DPX_SC + (gen & 1u) * 32 + 5] = cnt_;
+                    dp_signal(c, DPF_COUNT, gen);
+                }
+            }
             HIRL_STAGE(ST_G6, stage_g6(c, tm, smem))
         }
-        HIRL_STAGE(ST_R6, stage_r6(c, st, tm, smem))
+        HIRL_STAGE(ST_R6, stage_r6(c, st, tm, smem, gen))
         HIRL_STAGE(ST_G7, stage_g7(c, st, tm, smem))
         HIRL_STAGE(ST_R7, stage_r7(c, st, tm, smem))
-        HIRL_STAGE(ST_G8, stage_g8(c, st, tm, adam_phase))
+        HIRL_STAGE(ST_G8, stage_g8(c, st, tm, adam_phase, gen))
     }
 #undef HIRL_STAGE
     if (tm.rank == tm.size - 1 && threadIdx.x < HIRL_OUT_SCALARS) c.out_scalars[(size_t)step * HIRL_OUT_SCALARS + threadIdx.x] = c.carry[threadIdx.x];

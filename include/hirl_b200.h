@@ -120,6 +120,13 @@ int hirl_agent_backend(hirl_agent_t *h);
  *   hirl_allreduce_init: collective; creates this handle's own communicator from the id;
  *   hirl_allreduce_attach: use an existing ncclComm_t instead (not destroyed with the handle). */
 int hirl_nccl_unique_id(void *id128);
+/* FUSED variant (preferred; the NCCL variant above is the fallback where CUDA IPC between the ranks is unavailable): the
+ * all-reduces happen INSIDE the update kernel over NVLink peer memory, a call stays one launch.  hirl_dp_fused_export
+ * allocates this rank's exchange block and writes its 64-byte cudaIpcMemHandle_t; the caller gathers all ranks' handles
+ * ([world][64], rank order) and passes them to hirl_dp_fused_attach (world <= 8: one node).  Every rank adds the ranks'
+ * contributions in rank order, so the summed gradients and therefore the weights are bit-identical everywhere. */
+int hirl_dp_fused_export(hirl_agent_t *h, int rank, int world, int global_batch, void *handle64);
+int hirl_dp_fused_attach(hirl_agent_t *h, const void *handles, int world);
 int hirl_allreduce_init(hirl_agent_t *h, const void *id128, int rank, int world, int global_batch);
 int hirl_allreduce_attach(hirl_agent_t *h, void *nccl_comm, int rank, int world, int global_batch);
 
