@@ -528,6 +528,8 @@ class Agent(object):
                 # so the device still executes the calls back to back, in order)
                 # The first sub-chunks are short (1, 2, 4 calls): nothing overlaps the very first draw, so it should be brief.
                 bounds, lo, step = [], 0, 1
+                if self.FUSE_SUB >= len(chunk):        # the caller asked for ONE launch (profilers set FUSE_SUB = max_fused_steps)
+                    bounds, lo = [(0, len(chunk))], len(chunk)
                 while lo < len(chunk):
                     hi = min(len(chunk), lo + min(step, self.FUSE_SUB))
                     bounds.append((lo, hi))

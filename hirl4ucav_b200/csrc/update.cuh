@@ -1037,25 +1037,79 @@ __device__ __forceinline__ float polyak_elem(float t, float p, float tau, float 
     return __fadd_rn(__fmul_rn(t, one_minus_tau), __fmul_rn(p, tau));
 }
 
-template <class L>
-__device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w, float *gw, const float *w2parts, int nparts, float *m, float *v, const float *part,
-                                           int part_towers, int nslots, float neg_step, float bc2_sqrt, float *target, bool polyak,
-                                           float tau, float one_minus_tau, float *w2t, int phase = 0,
-                                           const AgentCtx *dpc = nullptr, size_t dp_off = 0, float *gw_out = nullptr, const float *gw_in = nullptr) {
+template <class L, int U>
+__device__ __forceinline__ void adam_arena_impl(const Team &tm, int ntowers, float *w, float *gw, const float *w2parts, int nparts, float *m, float *v, const float *part,
+                                                int part_towers, int nslots, float neg_step, float bc2_sqrt, float *target, bool polyak,
+                                                float tau, float one_minus_tau, float *w2t, int phase,
+                                                const AgentCtx *dpc, size_t dp_off, float *gw_out, const float *gw_in) {
     // gw_in: where a GEMM stage wrote dW2 directly (nparts == 0) when that is not gw itself (fused data-parallel: gw is the exchange buffer)
     // phase (data-parallel mode): 0 whole stage; 1 only the fixed-order sums of the partials -> gw (the gradient of this
     // shard, all-reduced between the two launches); 2 only Adam (+ Polyak) from gw; 3 (fused variant) Adam from the sum over the
     // ranks' exchange blocks at float offset dp_off, read over NVLink in rank order; the summed gradient is kept in gw_out
+    // U elements per thread and iteration: every load of the U elements (partials, peers' blocks over NVLink, w / m / v) is issued
+    // before the first one is consumed -- the loop is bound by round trips (L2, or NVLink in the fused data-parallel mode), not
+    // by arithmetic.  The order of the additions inside an element is unchanged, so results are bit-identical for every U.
+    const int total = ntowers * L::SIZE, stride = tm.size * THREADS;
+    for (int e0 = tm.rank * THREADS + threadIdx.x; e0 < total; e0 += U * stride) {
+        float g[U], wv[U], mv[U], vv[U], tv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * stride;
+            g[u] = 0.f;
+            if (e >= total) continue;
+            const int tower = e / L::SIZE, off = e - tower * L::SIZE;
+            const bool in_w2 = off >= L::W2 && off < L::B2;
+            if (phase == 3) {
+                for (int r = 0; r < dpc->dp_world; ++r) g[u] += __ldcv(dpx(*dpc, r) + dp_off + e);
+            } else if (phase == 2) {
+                g[u] = __ldcg(gw + e);
+            } else if (in_w2) {
+                if (nparts > 0) {   // fixed-order sum of the split-K / per-branch partial buffers
+                    const float *p0 = w2parts + (size_t)tower * nparts * H2 * H1 + (off - L::W2);
+                    g[u] = __ldcg(p0);
+                    for (int q = 1; q < nparts; ++q) g[u] += __ldcg(p0 + (size_t)q * H2 * H1);
+                } else {
+                    g[u] = __ldcg((gw_in ? gw_in : gw) + e);
+                }
+            } else {
+                const int si = L::small_index(off);
+                for (int s = 0; s < nslots; ++s) g[u] += __ldcg(part + ((size_t)s * part_towers + tower) * L::SMALL + si);
+            }
+            if (phase != 1) {
+                wv[u] = w[e]; mv[u] = m[e]; vv[u] = v[e];
+                tv[u] = polyak ? target[e] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * stride;
+            if (e >= total) continue;
+            const int tower = e / L::SIZE, off = e - tower * L::SIZE;
+            const bool in_w2 = off >= L::W2 && off < L::B2;
+            if (phase == 3) gw_out[e] = g[u];
+            else if (phase != 2 && (!in_w2 || nparts > 0 || gw_in)) gw[e] = g[u];
+            if (phase == 1) continue;
+            adam_elem(g[u], wv[u], mv[u], vv[u], neg_step, bc2_sqrt);
+            w[e] = wv[u]; m[e] = mv[u]; v[e] = vv[u];
+            if (w2t && in_w2) {   // keep W2^T current for the tensor-core dX GEMMs
+                const int i = off - L::W2, n = i / H1, k = i - n * H1;
+                w2t[(size_t)tower * H1 * H2 + (size_t)k * H2 + n] = wv[u];
+            }
+            if (polyak) target[e] = polyak_elem(tv[u], wv[u], tau, one_minus_tau);
+        }
+    }
+}
+// one element per thread and iteration (the form round 1 shipped): kept for the many-part case, see adam_arena below
+template <class L>
+__device__ __forceinline__ void adam_arena_scalar(const Team &tm, int ntowers, float *w, float *gw, const float *w2parts, int nparts, float *m, float *v, const float *part,
+                                                  int part_towers, int nslots, float neg_step, float bc2_sqrt, float *target, bool polyak,
+                                                  float tau, float one_minus_tau, float *w2t, int phase, const float *gw_in) {
     const int total = ntowers * L::SIZE;
     for (int e = tm.rank * THREADS + threadIdx.x; e < total; e += tm.size * THREADS) {
         const int tower = e / L::SIZE, off = e - tower * L::SIZE;
         float g;
         const bool in_w2 = off >= L::W2 && off < L::B2;
-        if (phase == 3) {
-            g = 0.f;
-            for (int r = 0; r < dpc->dp_world; ++r) g += __ldcv(dpx(*dpc, r) + dp_off + e);
-            gw_out[e] = g;
-        } else if (phase == 2) {
+        if (phase == 2) {
             g = __ldcg(gw + e);
         } else if (in_w2) {
             if (nparts > 0) {   // fixed-order sum of the split-K / per-branch partial buffers
@@ -1083,6 +1137,20 @@ __device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w
         }
         if (polyak) target[e] = polyak_elem(target[e], wv, tau, one_minus_tau);
     }
+}
+// U = 4 where an element has few loads of its own (ensembles and small batches: dW2 in <= 2 parts; the peers' blocks of the fused
+// data-parallel all-reduce): ensemble128 +7 %.  With the 8-16 split-K parts of batch 4096 the batched form is SLOWER (stage G4
+// 22 -> 30 us, tools/stage_profile.py), so that case keeps one element per iteration.
+template <class L>
+__device__ __forceinline__ void adam_arena(const Team &tm, int ntowers, float *w, float *gw, const float *w2parts, int nparts, float *m, float *v, const float *part,
+                                           int part_towers, int nslots, float neg_step, float bc2_sqrt, float *target, bool polyak,
+                                           float tau, float one_minus_tau, float *w2t, int phase = 0,
+                                           const AgentCtx *dpc = nullptr, size_t dp_off = 0, float *gw_out = nullptr, const float *gw_in = nullptr) {
+    if (phase == 3 || nparts <= 2)
+        adam_arena_impl<L, 4>(tm, ntowers, w, gw, w2parts, nparts, m, v, part, part_towers, nslots, neg_step, bc2_sqrt, target, polyak, tau, one_minus_tau, w2t, phase,
+                              dpc, dp_off, gw_out, gw_in);
+    else
+        adam_arena_scalar<L>(tm, ntowers, w, gw, w2parts, nparts, m, v, part, part_towers, nslots, neg_step, bc2_sqrt, target, polyak, tau, one_minus_tau, w2t, phase, gw_in);
 }
 template <class L>
 __device__ __forceinline__ void polyak_arena(const Team &tm, int ntowers, const float *w, float *target, float tau, float one_minus_tau) {

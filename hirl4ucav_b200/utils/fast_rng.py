@@ -204,6 +204,10 @@ def choice_noreplace_on(rs, n: int, k: int):
 
 
 _exit_join_registered = False
+# The buffers of the job the library's worker thread is running (generator-state copy, output array).  Held HERE, not only by the
+# Predraw that started it: an agent may be garbage-collected while its pre-draw is still in flight, and the worker must never
+# write into freed memory.  One job at a time library-wide, so one slot is enough; cleared when the job is joined.
+_INFLIGHT = None
 
 
 def _register_exit_join():
@@ -233,13 +237,22 @@ class Predraw:
 
     def _join(self):
         """A draw handed to the library's worker thread is finished (its state copy and output array are ours again)."""
+        global _INFLIGHT
         if self._pending:
             _lib.load().hirl_host_async_wait()
             self._pending = False
+            _INFLIGHT = None
+
+    def __del__(self):
+        try:
+            self._join()
+        except Exception:
+            pass
 
     def prepare(self, requests):
         """requests: list of (n, k) expected at the next call.  The np stream (one full shuffle, the longest thing the host
         does per call) runs on the library's worker thread; take() collects it."""
+        global _INFLIGHT
         self._join()
         self._snap = None
         if not self.enabled() or any(not (0 <= k <= n and 0 < n < (1 << 31)) for n, k in requests):
@@ -251,6 +264,7 @@ class Predraw:
             out = np.empty(k, np.int32)
             if _lib.load().hirl_host_choice_noreplace_async(C.byref(work), n, k, _lib.ptr(out)) == 0:
                 _register_exit_join()
+                _INFLIGHT = (work, out)
                 self._pending = True
                 self._snap, self._after, self._req, self._outs = snap, work, list(requests), [out]
                 return

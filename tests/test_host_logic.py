@@ -201,3 +201,26 @@ def test_noise_draw_shortcut_is_the_reference_stream():
             got.append(buf.numpy() * std.numpy() + mean.numpy())
         tail_g = torch.rand(1, **kw).item()
         assert all(np.array_equal(a, b) for a, b in zip(want, got)) and tail_w == tail_g
+
+
+def test_predraw_in_flight_survives_its_owner():
+    """An agent can be garbage-collected while its np pre-draw still runs on the library's worker thread: the job's buffers
+    are held at module level and the destructor joins the worker (the worker must never write into freed memory)."""
+    import gc
+    from hirl4ucav_b200 import _lib
+    from hirl4ucav_b200.utils import fast_rng as fr
+    assert fr.np_fast()
+    np.random.seed(5)
+    want = np.random.choice(20000, 256, replace=False)
+    np.random.seed(5)
+    for _ in range(20):
+        p = fr.Predraw("np")
+        p.prepare([(20000, 256)])
+        del p                                   # owner gone while the shuffle may still be running
+        gc.collect()
+        assert fr._INFLIGHT is None             # joined by the destructor
+    q = fr.Predraw("np")
+    q.prepare([(20000, 256)])
+    got = q.take([(20000, 256)])                # the live state was never touched by the abandoned jobs
+    assert got is not None and np.array_equal(got[0], want)
+    assert _lib.load().hirl_host_async_wait() == 0
