@@ -369,10 +369,10 @@ class Agent(object):
         if pre is not None:
             idx_on, idx_ex = pre[0], (pre[1] if n_ex else [])
         elif warm:
-            idx_on = forced.get("online") if "online" in forced else self.buffer.sample_indices(B - n_ex)
-            idx_ex = forced.get("expert") if "expert" in forced else self.expert_buffer.sample_indices(n_ex)
+            idx_on = forced.get("online") if "online" in forced else self.buffer.sample_indices_array(B - n_ex)
+            idx_ex = forced.get("expert") if "expert" in forced else self.expert_buffer.sample_indices_array(n_ex)
         else:
-            idx_on = forced.get("online") if "online" in forced else self.buffer.sample_indices(B)
+            idx_on = forced.get("online") if "online" in forced else self.buffer.sample_indices_array(B)
             idx_ex = []
         n_on = B - n_ex
         if len(idx_on) != n_on or len(idx_ex) != n_ex:

@@ -231,6 +231,12 @@ class UniformMemory(object):
             return [int(i) for i in np.random.choice(self._size, batchSize, p=pr / np.sum(pr))]
         return fast_rng.sample_indices(self._size, batchSize)   # == random.sample(range(self._size), batchSize)
 
+    def sample_indices_array(self, batchSize):
+        """sample_indices as an int32 array (the update path: no Python list between the draw and the staging row)."""
+        if self.upsample:
+            return np.asarray(self.sample_indices(batchSize), np.int32)
+        return fast_rng.sample_indices_array(self._size, batchSize)
+
     def sample(self, batchSize):
         idx = self.sample_indices(batchSize)
         batch = Transition(*zip(*[self.memory[i] for i in idx]))

@@ -163,16 +163,22 @@ def py_fast() -> bool:
 
 
 # ---- public draws ------------------------------------------------------------------------------------------------
-def sample_indices(n: int, k: int):
-    """== random.sample(range(n), k) on the global generator."""
+def sample_indices_array(n: int, k: int):
+    """== random.sample(range(n), k) on the global generator, as an int32 array (no Python list in between: the update's staging
+    rows are int32 arrays; at batch 4096 the list round trip cost more than the draw)."""
     if not 0 <= k <= n:
         raise ValueError("Sample larger than population or is negative")     # random.sample's own error
     if n >= 1 << 31 or not py_fast():
-        return random.sample(range(n), k)
+        return np.asarray(random.sample(range(n), k), np.int32)
     st = _py_read()
     out = _c_sample(st, n, k)
     _py_write(st)
-    return out.tolist()
+    return out
+
+
+def sample_indices(n: int, k: int):
+    """== random.sample(range(n), k) on the global generator."""
+    return sample_indices_array(n, k).tolist()
 
 
 def choice_noreplace(n: int, k: int) -> np.ndarray:
