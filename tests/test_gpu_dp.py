@@ -1,5 +1,6 @@
-"""GPU: data-parallel large-batch mode (include/hirl_b200.h).  The reference has no such path; the bar is
-"k shards == one GPU within summation-order tolerance", at the reference's two optimizer boundaries
+"""GPU: data-parallel large-batch mode (include/hirl_b200.h), both variants: "fused" (all-reduces inside the
+update kernel over NVLink peer memory, CUDA IPC) and "nccl" (stage-range launches + ncclAllReduce, HIRL_DP_NCCL=1).  The
+reference has no such path; the bar is "k shards == one GPU within summation-order tolerance", at the reference's two optimizer boundaries
 (/root/reference/hirl/agents/HIRL.py:286-288 and :323-325) and the batch mean of the soft Q-filter (:303)."""
 import os
 import subprocess
@@ -25,15 +26,19 @@ def _run_pair(B, bcw, en, steps, dp):
     return ag, outs, [ag.export_flat(i) for i in range(4)], ag.export_grads(_lib.NET_CRITIC), ag.export_grads(_lib.NET_ACTOR)
 
 
+@pytest.mark.parametrize("variant", ["fused", "nccl"])
 @pytest.mark.parametrize("B,bcw,en", [(64, 100, 16), (64, 0.5, 0), (512, 100, 128)])
-def test_world_1_data_parallel_equals_the_plain_stage_kernel(B, bcw, en, monkeypatch):
-    """One rank: the call runs as five launches over stage ranges with (trivial) NCCL all-reduces between them; the
-    arithmetic is the stage kernel's, so the result must be bit-identical to the single launch."""
+def test_world_1_data_parallel_equals_the_plain_stage_kernel(B, bcw, en, variant, monkeypatch):
+    """One rank: every reduction point runs (fused: exchange block, flag, rank-ordered sum over one rank inside the kernel;
+    nccl: five launches over stage ranges with trivial all-reduces between them); the arithmetic is the stage kernel's, so
+    the result must be bit-identical to the plain single launch."""
     monkeypatch.setenv("HIRL_TCC", "0")
     monkeypatch.setenv("HIRL_CLUSTER", "0")
+    monkeypatch.setenv("HIRL_DP_NCCL", "1" if variant == "nccl" else "0")
     a0, o0, w0, gc0, ga0 = _run_pair(B, bcw, en, 6, None)
     assert a0.backend == "stage"
     a1, o1, w1, gc1, ga1 = _run_pair(B, bcw, en, 6, (0, 1))
+    assert a1.dp_variant == variant
     for x, y in zip(o0, o1):
         assert [float(v) for v in x] == [float(v) for v in y]
     for x, y in zip(w0, w1):
@@ -54,8 +59,9 @@ def test_data_parallel_agent_moves_off_the_cluster_kernel():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
-def test_two_shards_match_one_gpu():
-    env = dict(os.environ, HIRL_TCC="0", HIRL_CLUSTER="0")
+@pytest.mark.parametrize("variant", ["fused", "nccl"])
+def test_two_shards_match_one_gpu(variant):
+    env = dict(os.environ, HIRL_TCC="0", HIRL_CLUSTER="0", HIRL_DP_NCCL="1" if variant == "nccl" else "0")
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", str(29600 + os.getpid() % 300), os.path.join(ROOT, "tests", "dp_worker.py")],
                          capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
