@@ -438,10 +438,40 @@ def time_data_parallel(K, W, local, rank, world):
         sync_all(world)
     assert np.isfinite([float(v) for v in out[-1][:4]]).all()
     sec = median_over_repeats(times, torch.device("cuda", local), world)
+    # device-resident form (fused variant only: a launch covers whole calls): Kd pre-drawn, pre-sharded calls in HBM, ONE launch per
+    # repeat on every rank, CUDA events on the launching stream, max over ranks -- what the kernels + in-kernel all-reduces cost
+    # without the host's per-call draws over the global batch and the launch skew between the ranks' Python processes
+    dev_ms = None
+    if getattr(ag, "dp_variant", None) == "fused":
+        from hirl4ucav_b200 import _lib
+        Kd = min(K, 48)
+        for k in range(Kd):
+            ag._draw(k, wl["bcw"], wl["expert_num"], 0, None)
+        ag._shard_slots(0, Kd)
+        dv = torch.device("cuda", local)
+        st_d = torch.from_numpy(ag._sh_steps_t.numpy()[: Kd * 64].copy()).to(dv)
+        on_d, ex_d, bc_d = ag._sh_on_t[:Kd].to(dv), ag._sh_ex_t[:Kd].to(dv), ag._sh_bc_t[:Kd].to(dv)
+        out_d = torch.zeros((Kd, 8), dtype=torch.float32, device=dv)
+        lib = _lib.load()
+
+        def launch():
+            _lib.check(lib.hirl_learn_dev(ag._h, Kd, st_d.data_ptr(), on_d.data_ptr(), ex_d.data_ptr(), bc_d.data_ptr(), out_d.data_ptr(),
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        launch(); torch.cuda.synchronize()
+        dts = []
+        for _ in range(7):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sync_all(world)
+            e0.record(); launch(); e1.record()
+            sync_all(world)
+            dts.append(e0.elapsed_time(e1))
+        dev_ms = median_over_repeats(dts, dv, world) / Kd
     variant = getattr(ag, "dp_variant", None)
     rec = {"workload": "dp4096: ONE HIRL agent (fixed BC weight), global batch 4096 cut into %d shard(s) of %d rows, gradients all-reduced over NVLink" % (world, wl["batch"] // world),
            "value": K / sec, "unit": "updates/s", "ms_per_step": sec / K * 1e3, "steps": K, "scaling": "strong", "global_batch": wl["batch"],
            "rows_per_gpu": wl["batch"] // world, "backend": ag.backend, "variant": variant,
+           "device_resident": None if dev_ms is None else {"value": 1e3 / dev_ms, "unit": "updates/s", "ms_per_step": dev_ms,
+                                                            "how": "pre-drawn, pre-sharded calls in HBM, one launch per repeat, CUDA events, max over ranks"},
            "collectives_per_call": "critic-only call: all-reduce of 276 482 fp32 gradient + loss; actor call: + filter count + all-reduce of 138 756 fp32 + 4 scalars",
            "how": ("fused: the all-reduces run INSIDE the update kernel (every rank sums the ranks' exchange blocks in rank order with P2P loads over NVLink "
                    "peer memory, CUDA IPC); a call is one launch" if variant == "fused" else

@@ -202,15 +202,10 @@ class Agent(object):
         """Name of the update kernel this agent launches."""
         return ("stage", "tcc", "cluster", "ensemble")[self._lib.hirl_agent_backend(self._h)]
 
-    def _submit(self, lo, n):
-        """Enqueues staging slots lo .. lo+n-1.  Data-parallel agents first cut every slot's index streams (drawn over the
-        global batch, identically on every rank) down to this rank's rows (parallel.shard_step)."""
-        if self._dp is None:
-            _lib.check(self._lib.hirl_learn_async(self._h, n, *(self._st_ptrs if lo == 0 else self._slot_ptrs(lo))))
-            return
+    def _shard_slots(self, lo, n):
+        """Cuts staging slots lo .. lo+n-1 (drawn over the global batch) down to this rank's rows (parallel.shard_step)."""
         from .. import parallel
         rank, world = self._dp
-        Bl = self._dev_batch
         for k in range(lo, lo + n):
             st = self._st_steps[k]
             n_on, n_ex, on, ex, bc = parallel.shard_step(int(st["n_online"]), int(st["n_expert"]), self._st_on[k], self._st_ex[k],
@@ -220,6 +215,15 @@ class Agent(object):
             self._sh_on[k, :n_on] = on
             self._sh_ex[k, :n_ex] = ex
             self._sh_bc[k, :] = bc
+
+    def _submit(self, lo, n):
+        """Enqueues staging slots lo .. lo+n-1.  Data-parallel agents first cut every slot's index streams (drawn over the
+        global batch, identically on every rank) down to this rank's rows (parallel.shard_step)."""
+        if self._dp is None:
+            _lib.check(self._lib.hirl_learn_async(self._h, n, *(self._st_ptrs if lo == 0 else self._slot_ptrs(lo))))
+            return
+        self._shard_slots(lo, n)
+        Bl = self._dev_batch
         a = self._sh_addr
         _lib.check(self._lib.hirl_learn_async(self._h, n, C.c_void_p(a[0] + lo * _lib.STEP_DTYPE.itemsize), C.c_void_p(a[1] + lo * Bl * 4),
                                               C.c_void_p(a[2] + lo * Bl * 4), C.c_void_p(a[3] + lo * Bl * 4),
