@@ -46,6 +46,20 @@ def test_world_1_data_parallel_equals_the_plain_stage_kernel(B, bcw, en, variant
     assert np.array_equal(gc0, gc1) and np.array_equal(ga0, ga1)
 
 
+def test_fused_variant_falls_back_to_nccl_when_ipc_is_unavailable(monkeypatch):
+    """If the exchange blocks cannot be shared (CUDA IPC unavailable on some rank) every rank falls back to the NCCL variant."""
+    monkeypatch.setenv("HIRL_TCC", "0")
+    monkeypatch.setenv("HIRL_DP_NCCL", "0")
+    monkeypatch.setenv("HIRL_DP_FUSED_FAIL", "1")
+    with pytest.warns(UserWarning, match="falling back to the NCCL variant"):
+        a1, o1, w1, gc1, ga1 = _run_pair(64, 100, 16, 4, (0, 1))
+    assert a1.dp_variant == "nccl"
+    monkeypatch.delenv("HIRL_DP_FUSED_FAIL")
+    a0, o0, w0, gc0, ga0 = _run_pair(64, 100, 16, 4, None)
+    for x, y in zip(w0, w1):
+        assert np.array_equal(x, y)
+
+
 def test_data_parallel_agent_moves_off_the_cluster_kernel():
     """An agent created at a batch the tensor-core cluster kernel would take is switched to the stage kernel on attach."""
     os.environ.pop("HIRL_TCC", None)
