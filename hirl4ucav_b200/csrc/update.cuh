@@ -1443,9 +1443,13 @@ __device__ __noinline__ void stage_r7(const AgentCtx &c, const hirl_step_t &st, 
         if (grank < P) ln1_write_partial<ActorL>(c.sc.PART_A + ((size_t)branch * P + grank) * ActorL::SMALL, acc);
     }
 }
-// forceinline, unlike the other stages: as a separate function the nvcc 12.9 build of this stage read a wrong
-// dW2-partials base in warps 1-7 (compute-sanitizer: out-of-bounds __ldcg in adam_arena) although the SASS data
-// flow looks right and any probe added to it made the fault disappear; inlined it is exact (tests/test_gpu_update.py).
+// forceinline, unlike the other stages.  Round 1: built as a separate function this stage once read a wrong dW2-partials base in
+// warps 1-7 (compute-sanitizer: out-of-bounds __ldcg in adam_arena) and any probe made the fault disappear.  Round 2
+// (tools/sanitize_all.sh, profiles/r2_sanitizer_summary_*.txt): rebuilt as a separate function (HIRL_G8_NOINLINE=1) the stage is
+// clean under memcheck and initcheck, and the only hazard racecheck found in the kernel -- the SHARED step record `st` being
+// rewritten by a warp that is already in the next call while a slower warp still reads it -- is exactly a mechanism that hands
+// this stage a stale st.mode / st.do_polyak (its partials base and slot count derive from them); it is fixed (learn_step takes
+// register copies, stages run between barriers) and the fault has not reproduced since.  The inlined form stays: one call site.
 #ifndef HIRL_G8_NOINLINE
 #define HIRL_G8_NOINLINE 0   // 1: build stage_g8 as a separate function again (tools/sanitize_all.sh re-tests the round-1 fault)
 #endif
@@ -1543,10 +1547,9 @@ __device__ __forceinline__ bool learn_step(const AgentCtx &c, int step, Team &tm
         return true;                                                                    \
     }                                                                                   \
     }
-    // NOTE: every stage function has exactly ONE call site.  ptxas specialises these non-inlined functions per
-    // kernel and lets them read caller registers directly; with a second call site (a separate BC sequence) the
-    // actor Adam received a corrupted pointer in some threads.  One call site each keeps that analysis trivially
-    // consistent; modes skip stages with conditions instead.
+    // NOTE: every stage function has exactly ONE call site; modes skip stages with conditions instead.  (Round 1 saw a
+    // corrupted pointer in the actor Adam with a second call site; see the note at stage_g8 for what round 2's sanitizer sweep
+    // found -- the shared step record race below -- which explains that symptom as well.)
     // Control flow uses register copies taken here: racecheck flagged the read of st.do_actor AFTER the last team barrier of
     // a critic-only call against the next call's write of `st` by a warp that is already one call ahead.
     const bool bc_only = st.mode == 2;   // behaviour cloning (BC.py:160-185): expert-state actor pass, backward, Adam
